@@ -1,0 +1,140 @@
+/* b200diar.h -- C ABI of the B200-native community-1 diarization hot path.
+ *
+ * Drop-in boundary for pyannote.audio's sliding-window inference path.  The reference is 100 % Python and has no
+ * FFI for this path, so each entry point cites the *Python* interface it replaces (paths relative to
+ * /root/reference/src/pyannote/audio).  All functions return 0 on success or a negative b200_status; the message
+ * for the calling thread's last failure is available from b200_last_error().  No exceptions cross this boundary,
+ * no torch types appear in it: device buffers are raw CUDA pointers owned by the caller, `stream` is a
+ * cudaStream_t passed as void*, weights are host fp32 arrays in PyTorch state-dict layout.
+ * One ctx per (process, device); a ctx is not thread-safe, use one per stream/thread.
+ */
+#ifndef B200DIAR_H_
+#define B200DIAR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_ctx b200_ctx;
+
+enum b200_status {
+  B200_STATUS_OK = 0,
+  B200_STATUS_INVALID = -1, /* bad argument / unsupported shape            -> ValueError  */
+  B200_STATUS_CUDA = -2,    /* CUDA runtime / driver failure               -> RuntimeError */
+  B200_STATUS_OOM = -3,     /* cudaErrorMemoryAllocation (inference.py:201-206 maps OOM to MemoryError) */
+  B200_STATUS_STATE = -4    /* weights not loaded, ctx misuse                -> RuntimeError */
+};
+
+/* fixed geometry of the path */
+#define B200_CHUNK_SAMPLES 160000
+#define B200_FRAMES_PER_CHUNK 589
+#define B200_LOCAL_SPEAKERS 3
+#define B200_POWERSET_CLASSES 7
+#define B200_EMBED_DIM 256
+#define B200_FBANK_FRAMES 998
+#define B200_MEL_BINS 80
+
+const char* b200_last_error(void);
+int b200_version(void);
+
+/* Model.to(device) / Inference.to(device)  (core/inference.py:169-180) */
+int b200_ctx_create(b200_ctx** ctx, int device);
+int b200_ctx_destroy(b200_ctx* ctx);
+/* conv_impl: 0 = CUDA-core reference conv, 1 = tcgen05 tensor-core conv (default), 2 = tcgen05 for stride-1 only */
+int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches claim) */
+int64_t b200_ctx_launch_count(const b200_ctx* ctx);
+
+/* ---- weights: Model.from_pretrained state_dict (core/model.py:497-655) ------------------------------------ */
+
+/* PyanNet (models/segmentation/PyanNet.py:92-161, models/blocks/sincnet.py:41-79). Index of LSTM arrays =
+ * layer * 2 + direction (0 = forward, 1 = "_reverse"); PyTorch layouts ([4H][I], [4H][H], [4H]), gate order i,f,g,o. */
+typedef struct b200_seg_weights {
+  float wav_norm_weight, wav_norm_bias;       /* sincnet.wav_norm1d.{weight,bias}                       */
+  const float* sinc_filters;                  /* [80][251] realised ParamSincFB bank (cos 0..39, sin 40..79) */
+  const float* norm_weight[3];                /* sincnet.norm1d.{0,1,2}.weight  (80, 60, 60)            */
+  const float* norm_bias[3];
+  const float* conv_weight[2];                /* sincnet.conv1d.{1,2}.weight  [60][80][5], [60][60][5]  */
+  const float* conv_bias[2];
+  int32_t lstm_layers;                        /* <= 4 */
+  const float* lstm_w_ih[8];
+  const float* lstm_w_hh[8];
+  const float* lstm_b_ih[8];
+  const float* lstm_b_hh[8];
+  const float* linear_weight[2];              /* linear.{0,1}.weight [128][256], [128][128]             */
+  const float* linear_bias[2];
+  const float* classifier_weight;             /* [7][128] */
+  const float* classifier_bias;               /* [7]      */
+} b200_seg_weights;
+int b200_seg_load(b200_ctx* ctx, const b200_seg_weights* w);
+
+/* WeSpeakerResNet34 (models/embedding/wespeaker/resnet.py:84-145, 214-252).  conv weight [Cout][Cin][k][k] fp32,
+ * eval-mode BatchNorm2d given by (weight, bias, running_mean, running_var), eps 1e-5; folded by the library. */
+typedef struct b200_conv_bn {
+  const float* conv_weight;                   /* NULL => layer absent (identity shortcut)               */
+  const float* bn_weight;
+  const float* bn_bias;
+  const float* bn_mean;
+  const float* bn_var;
+} b200_conv_bn;
+typedef struct b200_emb_weights {
+  b200_conv_bn stem;                          /* resnet.conv1 / resnet.bn1                               */
+  b200_conv_bn block_conv1[16];               /* resnet.layer{1..4}.{i}.conv1/bn1, blocks in order 3+4+6+3 */
+  b200_conv_bn block_conv2[16];
+  b200_conv_bn block_shortcut[16];            /* resnet.layer{2..4}.0.shortcut.{0,1}                      */
+  const float* seg1_weight;                   /* resnet.seg_1.weight [256][5120]                          */
+  const float* seg1_bias;                     /* [256]                                                    */
+} b200_emb_weights;
+int b200_emb_load(b200_ctx* ctx, const b200_emb_weights* w);
+
+/* ---- segmentation: Inference.infer / Inference.slide hot loop (core/inference.py:182-215, 295-313) --------
+ * `wav` is a device fp32 buffer; chunk i covers wav[chunk_off[i] .. chunk_off[i]+160000), of which only the first
+ * chunk_valid[i] samples are real (the rest is the zero padding of the last chunk, inference.py:270-278).
+ * chunk_off / chunk_valid are HOST arrays.  Output: powerset class id per frame, classes[num_chunks][589]
+ * (argmax of the LogSoftmax output, utils/powerset.py:135-140); optional log-probabilities [num_chunks][589][7]. */
+int b200_seg_forward(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, const int32_t* chunk_valid,
+                     int32_t num_chunks, uint8_t* classes, float* logp, void* stream);
+/* SincNet.forward alone (models/blocks/sincnet.py:163-184): out[num_chunks][589][60] fp32 (frame-major). */
+int b200_sincnet_forward(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, const int32_t* chunk_valid,
+                         int32_t num_chunks, float* out, void* stream);
+/* Powerset.to_multilabel, hard (utils/powerset.py:115-140): classes[n] -> multilabel[n][3] in {0,1} (u8). */
+int b200_powerset_to_multilabel(b200_ctx* ctx, const uint8_t* classes, int64_t n, uint8_t* multilabel, void* stream);
+
+/* ---- embeddings: SpeakerDiarization.get_embeddings hot loop (pipelines/speaker_diarization.py:399-459) over
+ * PyannoteAudioPretrainedSpeakerEmbedding.__call__ (pipelines/speaker_verification.py:704-716) and
+ * WeSpeakerResNet34.forward (models/embedding/wespeaker/__init__.py:324-343).  One trunk pass per chunk, the three
+ * local speakers share it (forward_frames + forward_embedding, :288-322); masks[num_chunks][3][589] u8 are the
+ * StatsPool weights; emb[num_chunks][3][256] fp32. */
+int b200_emb_forward(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, const int32_t* chunk_valid,
+                     int32_t num_chunks, const uint8_t* masks, float* emb, void* stream);
+/* compute_fbank (wespeaker/__init__.py:113-139): fbank[num_chunks][998][80], global-mean centred. */
+int b200_emb_fbank(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, const int32_t* chunk_valid,
+                   int32_t num_chunks, float* fbank, void* stream);
+/* ResNet.forward_frames on a given fbank (resnet.py:399-419): frames[num_chunks][256][10][125] fp32 (NCHW). */
+int b200_emb_trunk(b200_ctx* ctx, const float* fbank, int32_t num_chunks, float* frames, void* stream);
+/* StatsPool.forward (models/blocks/pooling.py:76-130): seq[B][F][T], weights[B][S][Tw] or NULL -> out[B][S][2F]. */
+int b200_stats_pool(b200_ctx* ctx, const float* seq, const float* weights, float* out, int32_t B, int32_t F, int32_t T,
+                    int32_t S, int32_t Tw, void* stream);
+
+/* ---- overlap-add / reconstruction (core/inference.py:498-620, pipelines/utils/diarization.py:150-268,
+ * pipelines/speaker_diarization.py:480-528).  seg[num_chunks][589][3] u8 in {0,1}; start_frame[num_chunks] HOST
+ * array with the global frame index of each chunk's first frame; num_frames = size of the global grid. */
+int b200_speaker_count(b200_ctx* ctx, const uint8_t* seg, const int32_t* start_frame, int32_t num_chunks,
+                       int32_t num_frames, uint8_t* count, void* stream);
+/* hard_clusters[num_chunks][3] int8 (-2 = inactive) HOST; count[num_frames] u8 device (already capped);
+ * out: discrete[num_frames][num_clusters_out] u8, num_clusters_out = max(K, max(count)). */
+int b200_reconstruct(b200_ctx* ctx, const uint8_t* seg, const int8_t* hard_clusters, const int32_t* start_frame,
+                     int32_t num_chunks, int32_t num_frames, int32_t num_clusters, const uint8_t* count,
+                     int32_t num_clusters_out, uint8_t* discrete, void* stream);
+
+/* ---- clustering (pipelines/clustering.py:77-140, 572-669; utils/vbx.py; scipy linkage/fcluster) --------------- */
+/* filter_embeddings: clean-frame counts per (chunk, speaker): out[num_chunks][3] int32, plus active[num_chunks][3] u8
+ * = any frame active (inactive speakers, speaker_diarization.py:681). */
+int b200_clean_frames(b200_ctx* ctx, const uint8_t* seg, int32_t num_chunks, int32_t* clean, uint8_t* active,
+                      void* stream);
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DIAR_H_ */

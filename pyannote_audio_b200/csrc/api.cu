@@ -1,0 +1,574 @@
+// extern "C" surface of libb200diar.so (declared in include/b200diar.h): context, weight ingestion
+// (BN folding, layout transforms, fp16 conversion on the host), and the forward entry points.
+#include "../../include/b200diar.h"
+#include "common.cuh"
+#include "emb.cuh"
+#include "post.cuh"
+#include "seg.cuh"
+#include <cmath>
+#include <cstdlib>
+
+using namespace b200;
+
+struct b200_ctx {
+  int device = 0;
+  int num_sms = 148;
+  int conv_impl = 1;
+  int seg_max_batch = 2368;     // chunks per segmentation sub-batch (37 LSTM tiles of 64 sequences x 2 directions)
+  int emb_max_batch = 256;      // chunks per embedding sub-batch
+  int64_t launches = 0;
+  SegWeights seg;
+  EmbWeights emb;
+  std::vector<void*> owned;     // device allocations holding weights
+  void* ws = nullptr;
+  size_t ws_cap = 0;
+  long long* d_off = nullptr;
+  int* d_valid = nullptr;
+  int meta_cap = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = 0;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
+  ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+template <typename T>
+int upload(b200_ctx* ctx, const std::vector<T>& h, T** out) {
+  void* p = nullptr;
+  B200_CUDA_OK(cudaMalloc(&p, h.size() * sizeof(T) + 16));
+  B200_CUDA_OK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  ctx->owned.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return B200_OK;
+}
+
+int ensure_ws(b200_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->ws_cap) return B200_OK;
+  if (ctx->ws) { cudaDeviceSynchronize(); cudaFree(ctx->ws); ctx->ws = nullptr; ctx->ws_cap = 0; }
+  B200_CUDA_OK(cudaMalloc(&ctx->ws, bytes));
+  ctx->ws_cap = bytes;
+  return B200_OK;
+}
+
+int ensure_meta(b200_ctx* ctx, int n) {
+  if (n <= ctx->meta_cap) return B200_OK;
+  if (ctx->d_off) { cudaDeviceSynchronize(); cudaFree(ctx->d_off); cudaFree(ctx->d_valid); }
+  const int cap = n + 1024;
+  B200_CUDA_OK(cudaMalloc((void**)&ctx->d_off, sizeof(long long) * cap));
+  B200_CUDA_OK(cudaMalloc((void**)&ctx->d_valid, sizeof(int) * cap));
+  ctx->meta_cap = cap;
+  return B200_OK;
+}
+
+int push_meta(b200_ctx* ctx, const int64_t* off, const int32_t* valid, int n, cudaStream_t st) {
+  int rc = ensure_meta(ctx, n);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i)
+    B200_CHECK(valid[i] >= 0 && valid[i] <= kChunk && off[i] >= 0, B200_ERR_INVALID,
+               "chunk %d: offset %lld / valid %d out of range", i, (long long)off[i], (int)valid[i]);
+  B200_CUDA_OK(cudaMemcpyAsync(ctx->d_off, off, sizeof(long long) * n, cudaMemcpyHostToDevice, st));
+  B200_CUDA_OK(cudaMemcpyAsync(ctx->d_valid, valid, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  return B200_OK;
+}
+
+// ---- kaldi mel bank / window / twiddles (torchaudio.compliance.kaldi.get_mel_banks, _feature_window_function) ----
+double mel_scale(double f) { return 1127.0 * std::log(1.0 + f / 700.0); }
+
+int build_fbank_constants(b200_ctx* ctx) {
+  EmbWeights& E = ctx->emb;
+  std::vector<float> window(400);
+  for (int i = 0; i < 400; ++i) window[i] = (float)(0.54 - 0.46 * std::cos(2.0 * M_PI * i / 399.0));
+  std::vector<float> tw(512);
+  for (int k = 0; k < 256; ++k) {
+    tw[2 * k] = (float)std::cos(2.0 * M_PI * k / 512.0);
+    tw[2 * k + 1] = (float)(-std::sin(2.0 * M_PI * k / 512.0));
+  }
+  const int nb = 80, nfft = 256;
+  const double low = 20.0, high = 8000.0, bw = 16000.0 / 512.0;
+  const double ml = mel_scale(low), mh = mel_scale(high), delta = (mh - ml) / (nb + 1);
+  std::vector<float> w;
+  std::vector<int> st(nb), ln(nb), off(nb);
+  for (int b = 0; b < nb; ++b) {
+    const double left = ml + b * delta, center = ml + (b + 1.0) * delta, right = ml + (b + 2.0) * delta;
+    int first = -1, last = -1;
+    std::vector<float> row(nfft, 0.f);
+    for (int k = 0; k < nfft; ++k) {
+      const double mel = mel_scale(bw * k);
+      const double up = (mel - left) / (center - left), down = (right - mel) / (right - center);
+      const double v = std::fmax(0.0, std::fmin(up, down));
+      row[k] = (float)v;
+      if (v > 0) { if (first < 0) first = k; last = k; }
+    }
+    if (first < 0) { first = 0; last = -1; }
+    st[b] = first; ln[b] = last - first + 1; off[b] = (int)w.size();
+    for (int k = first; k <= last; ++k) w.push_back(row[k]);
+  }
+  int rc;
+  if ((rc = upload(ctx, window, &E.window))) return rc;
+  if ((rc = upload(ctx, tw, &E.twiddle))) return rc;
+  if ((rc = upload(ctx, w, &E.mel_w))) return rc;
+  if ((rc = upload(ctx, st, &E.mel_start))) return rc;
+  if ((rc = upload(ctx, ln, &E.mel_len))) return rc;
+  if ((rc = upload(ctx, off, &E.mel_off))) return rc;
+  return B200_OK;
+}
+
+// fold eval-mode BatchNorm2d into a conv: w' = w * g/sqrt(v+eps),  b' = beta - mean * g/sqrt(v+eps)
+int make_conv(b200_ctx* ctx, const b200_conv_bn& src, int cin, int cout, int k, int stride, ConvLayer* L) {
+  B200_CHECK(src.conv_weight && src.bn_weight && src.bn_bias && src.bn_mean && src.bn_var, B200_ERR_INVALID,
+             "missing conv/bn tensor (cin=%d cout=%d)", cin, cout);
+  L->C_in = cin; L->C_out = cout; L->ksize = k; L->stride = stride;
+  std::vector<__half> w((size_t)k * k * cout * cin);
+  std::vector<float> bias(cout);
+  for (int co = 0; co < cout; ++co) {
+    const float s = src.bn_weight[co] / std::sqrt(src.bn_var[co] + 1e-5f);
+    bias[co] = src.bn_bias[co] - src.bn_mean[co] * s;
+    for (int ci = 0; ci < cin; ++ci)
+      for (int t = 0; t < k * k; ++t)
+        w[((size_t)t * cout + co) * cin + ci] = __float2half(src.conv_weight[((size_t)co * cin + ci) * k * k + t] * s);
+  }
+  int rc;
+  if ((rc = upload(ctx, w, &L->w))) return rc;
+  if ((rc = upload(ctx, bias, &L->bias))) return rc;
+  return B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200_last_error(void) { return b200::last_error(); }
+int b200_version(void) { return 100; }
+
+int b200_ctx_create(b200_ctx** out, int device) {
+  B200_CHECK(out != nullptr, B200_ERR_INVALID, "ctx pointer is NULL");
+  int ndev = 0;
+  B200_CUDA_OK(cudaGetDeviceCount(&ndev));
+  B200_CHECK(device >= 0 && device < ndev, B200_ERR_INVALID, "device %d not available (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  B200_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  B200_CHECK(prop.major == 10, B200_ERR_STATE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+             device, prop.major, prop.minor);
+  b200_ctx* c = new b200_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  if (const char* e = std::getenv("B200_CONV_IMPL")) c->conv_impl = std::atoi(e);
+  *out = c;
+  return B200_OK;
+}
+
+int b200_ctx_destroy(b200_ctx* ctx) {
+  if (!ctx) return B200_OK;
+  DeviceGuard g(ctx->device);
+  cudaDeviceSynchronize();
+  for (void* p : ctx->owned) cudaFree(p);
+  if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->d_off) cudaFree(ctx->d_off);
+  if (ctx->d_valid) cudaFree(ctx->d_valid);
+  delete ctx;
+  return B200_OK;
+}
+
+int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value) {
+  B200_CHECK(ctx && key, B200_ERR_INVALID, "NULL ctx/key");
+  std::string k(key);
+  if (k == "conv_impl") ctx->conv_impl = (int)value;
+  else if (k == "seg_max_batch") ctx->seg_max_batch = (int)value;
+  else if (k == "emb_max_batch") ctx->emb_max_batch = (int)value;
+  else B200_CHECK(false, B200_ERR_INVALID, "unknown option '%s'", key);
+  B200_CHECK(ctx->seg_max_batch >= 1 && ctx->emb_max_batch >= 1 && ctx->conv_impl >= 0 && ctx->conv_impl <= 2,
+             B200_ERR_INVALID, "option '%s' value %lld out of range", key, (long long)value);
+  return B200_OK;
+}
+
+int64_t b200_ctx_launch_count(const b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------------
+int b200_seg_load(b200_ctx* ctx, const b200_seg_weights* w) {
+  B200_CHECK(ctx && w, B200_ERR_INVALID, "NULL ctx/weights");
+  DeviceGuard g(ctx->device);
+  SegWeights& S = ctx->seg;
+  B200_CHECK(w->lstm_layers >= 1 && w->lstm_layers <= 4, B200_ERR_INVALID, "lstm_layers=%d unsupported",
+             (int)w->lstm_layers);
+  S.lstm_layers = w->lstm_layers;
+  S.wav_w = w->wav_norm_weight;
+  S.wav_b = w->wav_norm_bias;
+  int rc;
+  {  // half filter bank [126][80]; the kernel relies on the (anti)symmetry of ParamSincFB filters
+    B200_CHECK(w->sinc_filters, B200_ERR_INVALID, "sinc_filters is NULL");
+    std::vector<float> f(126 * 80);
+    for (int ch = 0; ch < 80; ++ch) {
+      const float* r = w->sinc_filters + ch * 251;
+      const float sign = ch < 40 ? 1.f : -1.f;
+      float mx = 0.f, err = 0.f;
+      for (int k = 0; k < 125; ++k) {
+        mx = std::fmax(mx, std::fabs(r[k]));
+        err = std::fmax(err, std::fabs(r[k] - sign * r[250 - k]));
+        f[k * 80 + ch] = r[k];
+      }
+      if (ch >= 40) err = std::fmax(err, std::fabs(r[125]));
+      B200_CHECK(err <= 1e-6f * (mx + 1e-30f) + 1e-12f, B200_ERR_INVALID,
+                 "sinc filter %d is not (anti)symmetric (err %g): not a ParamSincFB bank", ch, (double)err);
+      f[125 * 80 + ch] = ch < 40 ? r[125] : 0.f;
+    }
+    if ((rc = upload(ctx, f, &S.sinc_f))) return rc;
+  }
+  const int nch[3] = {80, 60, 60};
+  for (int i = 0; i < 3; ++i) {
+    B200_CHECK(w->norm_weight[i] && w->norm_bias[i], B200_ERR_INVALID, "norm1d.%d missing", i);
+    std::vector<float> gmm(w->norm_weight[i], w->norm_weight[i] + nch[i]), bt(w->norm_bias[i], w->norm_bias[i] + nch[i]);
+    if ((rc = upload(ctx, gmm, &S.in_gamma[i]))) return rc;
+    if ((rc = upload(ctx, bt, &S.in_beta[i]))) return rc;
+  }
+  const int cin[2] = {80, 60};
+  for (int i = 0; i < 2; ++i) {
+    B200_CHECK(w->conv_weight[i] && w->conv_bias[i], B200_ERR_INVALID, "conv1d.%d missing", i + 1);
+    std::vector<float> wc((size_t)cin[i] * 5 * 60), bc(w->conv_bias[i], w->conv_bias[i] + 60);
+    for (int co = 0; co < 60; ++co)
+      for (int ci = 0; ci < cin[i]; ++ci)
+        for (int k = 0; k < 5; ++k) wc[((size_t)ci * 5 + k) * 60 + co] = w->conv_weight[i][((size_t)co * cin[i] + ci) * 5 + k];
+    if ((rc = upload(ctx, wc, &S.conv_w[i]))) return rc;
+    if ((rc = upload(ctx, bc, &S.conv_b[i]))) return rc;
+  }
+  for (int l = 0; l < S.lstm_layers; ++l) {
+    const int I = l == 0 ? 60 : 256, Kp = l == 0 ? 64 : 256;
+    S.k_in[l] = Kp;
+    std::vector<float> wih((size_t)1024 * Kp, 0.f), bg(1024), whh((size_t)2 * 2 * 128 * 256);
+    for (int d = 0; d < 2; ++d) {
+      const float *Wi = w->lstm_w_ih[l * 2 + d], *Wh = w->lstm_w_hh[l * 2 + d];
+      const float *bi = w->lstm_b_ih[l * 2 + d], *bh = w->lstm_b_hh[l * 2 + d];
+      B200_CHECK(Wi && Wh && bi && bh, B200_ERR_INVALID, "lstm layer %d dir %d missing", l, d);
+      for (int u = 0; u < 128; ++u)
+        for (int gt = 0; gt < 4; ++gt) {
+          const int n = d * 512 + u * 4 + gt, src = gt * 128 + u;
+          for (int k = 0; k < I; ++k) wih[(size_t)n * Kp + k] = Wi[(size_t)src * I + k];
+          bg[n] = bi[src] + bh[src];
+        }
+      for (int r = 0; r < 2; ++r)
+        for (int k = 0; k < 128; ++k)
+          for (int p = 0; p < 2; ++p)
+            for (int tx = 0; tx < 32; ++tx)
+              for (int gt = 0; gt < 4; ++gt) {
+                const int unit = 64 * r + 2 * tx + p;
+                whh[(((size_t)(d * 2 + r) * 128 + k) * 256) + p * 128 + tx * 4 + gt] = Wh[(size_t)(gt * 128 + unit) * 128 + k];
+              }
+    }
+    if ((rc = upload(ctx, wih, &S.w_ih[l]))) return rc;
+    if ((rc = upload(ctx, bg, &S.b_g[l]))) return rc;
+    if ((rc = upload(ctx, whh, &S.w_hh[l]))) return rc;
+  }
+  const int lin_in[2] = {256, 128};
+  for (int i = 0; i < 2; ++i) {
+    B200_CHECK(w->linear_weight[i] && w->linear_bias[i], B200_ERR_INVALID, "linear.%d missing", i);
+    std::vector<float> lw(w->linear_weight[i], w->linear_weight[i] + 128 * lin_in[i]), lb(w->linear_bias[i], w->linear_bias[i] + 128);
+    if ((rc = upload(ctx, lw, &S.lin_w[i]))) return rc;
+    if ((rc = upload(ctx, lb, &S.lin_b[i]))) return rc;
+  }
+  B200_CHECK(w->classifier_weight && w->classifier_bias, B200_ERR_INVALID, "classifier missing");
+  std::vector<float> cw(w->classifier_weight, w->classifier_weight + 7 * 128), cb(w->classifier_bias, w->classifier_bias + 7);
+  if ((rc = upload(ctx, cw, &S.cls_w))) return rc;
+  if ((rc = upload(ctx, cb, &S.cls_b))) return rc;
+  S.loaded = true;
+  return B200_OK;
+}
+
+int b200_emb_load(b200_ctx* ctx, const b200_emb_weights* w) {
+  B200_CHECK(ctx && w, B200_ERR_INVALID, "NULL ctx/weights");
+  DeviceGuard g(ctx->device);
+  EmbWeights& E = ctx->emb;
+  int rc;
+  if ((rc = build_fbank_constants(ctx))) return rc;
+  {
+    const b200_conv_bn& s = w->stem;
+    B200_CHECK(s.conv_weight && s.bn_weight && s.bn_bias && s.bn_mean && s.bn_var, B200_ERR_INVALID, "stem missing");
+    std::vector<float> cw(32 * 9), cb(32);
+    for (int c = 0; c < 32; ++c) {
+      const float sc = s.bn_weight[c] / std::sqrt(s.bn_var[c] + 1e-5f);
+      cb[c] = s.bn_bias[c] - s.bn_mean[c] * sc;
+      for (int k = 0; k < 9; ++k) cw[c * 9 + k] = s.conv_weight[c * 9 + k] * sc;
+    }
+    if ((rc = upload(ctx, cw, &E.conv1_w))) return rc;
+    if ((rc = upload(ctx, cb, &E.conv1_b))) return rc;
+  }
+  E.blocks.clear();
+  const int planes[4] = {32, 64, 128, 256}, nblk[4] = {3, 4, 6, 3}, strides[4] = {1, 2, 2, 2};
+  int in_planes = 32, bi = 0;
+  for (int l = 0; l < 4; ++l)
+    for (int i = 0; i < nblk[l]; ++i, ++bi) {
+      BlockWeights B;
+      const int s = i == 0 ? strides[l] : 1;
+      if ((rc = make_conv(ctx, w->block_conv1[bi], in_planes, planes[l], 3, s, &B.conv1))) return rc;
+      if ((rc = make_conv(ctx, w->block_conv2[bi], planes[l], planes[l], 3, 1, &B.conv2))) return rc;
+      B.has_shortcut = (s != 1 || in_planes != planes[l]);
+      if (B.has_shortcut) {
+        if ((rc = make_conv(ctx, w->block_shortcut[bi], in_planes, planes[l], 1, s, &B.shortcut))) return rc;
+      }
+      in_planes = planes[l];
+      E.blocks.push_back(B);
+    }
+  B200_CHECK(w->seg1_weight && w->seg1_bias, B200_ERR_INVALID, "seg_1 missing");
+  std::vector<float> sw(w->seg1_weight, w->seg1_weight + (size_t)256 * 5120), sb(w->seg1_bias, w->seg1_bias + 256);
+  if ((rc = upload(ctx, sw, &E.seg1_w))) return rc;
+  if ((rc = upload(ctx, sb, &E.seg1_b))) return rc;
+  E.loaded = true;
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+static int seg_run(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, const int32_t* chunk_valid, int n,
+                   uint8_t* classes, float* logp, float* sinc_out, cudaStream_t st) {
+  B200_CHECK(ctx && ctx->seg.loaded, B200_ERR_STATE, "segmentation weights not loaded");
+  B200_CHECK(wav && chunk_off && chunk_valid && n >= 0, B200_ERR_INVALID, "bad arguments");
+  if (n == 0) return B200_OK;
+  DeviceGuard g(ctx->device);
+  const int nbmax = n < ctx->seg_max_batch ? n : ctx->seg_max_batch;
+  const size_t x0_bytes = align_up((size_t)nbmax * kFrames * 64 * sizeof(float), 1024);
+  const size_t sinc_b = sincnet_workspace_bytes(nbmax), lstm_b = lstm_workspace_bytes(nbmax);
+  const size_t big = sinc_b > lstm_b ? sinc_b : lstm_b;    // the two phases reuse the same region
+  int rc = ensure_ws(ctx, x0_bytes + big + 4096);
+  if (rc) return rc;
+  if ((rc = push_meta(ctx, chunk_off, chunk_valid, n, st))) return rc;
+  float* x0 = reinterpret_cast<float*>(ctx->ws);
+  void* region = reinterpret_cast<char*>(ctx->ws) + x0_bytes;
+  for (int c0 = 0; c0 < n; c0 += nbmax) {
+    const int nb = (n - c0) < nbmax ? (n - c0) : nbmax;
+    float* x0_dst = sinc_out ? sinc_out + (size_t)c0 * kFrames * 64 : x0;
+    if ((rc = sincnet_forward(ctx->seg, wav, ctx->d_off + c0, ctx->d_valid + c0, nb, region, x0_dst, st))) return rc;
+    ctx->launches += 8;
+    if (sinc_out) continue;
+    if ((rc = lstm_head_forward(ctx->seg, x0, nb, region, classes + (size_t)c0 * kFrames,
+                                logp ? logp + (size_t)c0 * kFrames * kClasses : nullptr, ctx->num_sms, st)))
+      return rc;
+    ctx->launches += 2 * ctx->seg.lstm_layers + 3;
+  }
+  return B200_OK;
+}
+
+int b200_seg_forward(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, const int32_t* chunk_valid,
+                     int32_t num_chunks, uint8_t* classes, float* logp, void* stream) {
+  B200_CHECK(classes != nullptr, B200_ERR_INVALID, "classes is NULL");
+  return seg_run(ctx, wav, chunk_off, chunk_valid, num_chunks, classes, logp, nullptr, (cudaStream_t)stream);
+}
+
+__global__ void strip_pad_kernel(const float* __restrict__ x64, float* __restrict__ out, size_t rows) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * 60) return;
+  out[idx] = x64[(idx / 60) * 64 + idx % 60];
+}
+
+int b200_sincnet_forward(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, const int32_t* chunk_valid,
+                         int32_t num_chunks, float* out, void* stream) {
+  B200_CHECK(out != nullptr, B200_ERR_INVALID, "out is NULL");
+  if (num_chunks == 0) return B200_OK;
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* tmp = nullptr;
+  const size_t rows = (size_t)num_chunks * kFrames;
+  B200_CUDA_OK(cudaMalloc((void**)&tmp, rows * 64 * sizeof(float)));
+  int rc = seg_run(ctx, wav, chunk_off, chunk_valid, num_chunks, nullptr, nullptr, tmp, st);
+  if (rc == B200_OK) {
+    strip_pad_kernel<<<(unsigned)((rows * 60 + 255) / 256), 256, 0, st>>>(tmp, out, rows);
+    ctx->launches += 1;
+    cudaStreamSynchronize(st);
+  }
+  cudaFree(tmp);
+  return rc;
+}
+
+int b200_powerset_to_multilabel(b200_ctx* ctx, const uint8_t* classes, int64_t n, uint8_t* multilabel, void* stream) {
+  B200_CHECK(ctx && classes && multilabel && n >= 0, B200_ERR_INVALID, "bad arguments");
+  if (n == 0) return B200_OK;
+  DeviceGuard g(ctx->device);
+  ctx->launches += 1;
+  return powerset_to_multilabel(classes, n, multilabel, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------------
+struct EmbWs {
+  float *fbank, *fmean, *stats;
+  __half *A, *Bf, *Cf;
+};
+static size_t carve_emb(int NB, void* base, EmbWs* w) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    off = align_up(off, 1024);
+    void* p = base ? (char*)base + off : nullptr;
+    off += bytes;
+    return p;
+  };
+  EmbWs t;
+  const size_t act = (size_t)NB * kMel * kFbankFrames * 32 * sizeof(__half);   // largest activation (layer1)
+  t.fbank = (float*)take((size_t)NB * kFbankFrames * kMel * sizeof(float));
+  t.fmean = (float*)take((size_t)NB * kMel * sizeof(float));
+  t.stats = (float*)take((size_t)NB * kSpeakers * 2 * kStatsDim * sizeof(float));
+  t.A = (__half*)take(act);
+  t.Bf = (__half*)take(act);
+  t.Cf = (__half*)take(act);
+  if (w) *w = t;
+  return align_up(off, 1024);
+}
+
+// conv1 + 16 BasicBlocks; result (NHWC fp16 [nb][10][125][256]) is left in ws.A
+static int trunk_run(b200_ctx* ctx, const EmbWs& w, int nb, cudaStream_t st) {
+  const EmbWeights& E = ctx->emb;
+  int rc;
+  if ((rc = conv1_forward(w.fbank, w.fmean, E.conv1_w, E.conv1_b, w.A, nb, st))) return rc;
+  ctx->launches += 1;
+  int H = kMel, Wd = kFbankFrames;
+  for (const BlockWeights& B : E.blocks) {
+    const int s = B.conv1.stride;
+    const int impl1 = (ctx->conv_impl == 2) ? (s == 1 ? 1 : 0) : ctx->conv_impl;
+    const int impl_s1 = ctx->conv_impl == 0 ? 0 : 1;
+    const int Ho = (H + 2 - 3) / s + 1, Wo = (Wd + 2 - 3) / s + 1;
+    if ((rc = conv_forward(B.conv1, w.A, nullptr, w.Bf, nb, H, Wd, 1, impl1, ctx->num_sms, st))) return rc;
+    const __half* res = w.A;
+    if (B.has_shortcut) {
+      if ((rc = conv_forward(B.shortcut, w.A, nullptr, w.Cf, nb, H, Wd, 0, impl1, ctx->num_sms, st))) return rc;
+      res = w.Cf;
+      ctx->launches += 1;
+    }
+    if ((rc = conv_forward(B.conv2, w.Bf, res, w.A, nb, Ho, Wo, 1, impl_s1, ctx->num_sms, st))) return rc;
+    ctx->launches += 2;
+    H = Ho; Wd = Wo;
+  }
+  B200_CHECK(H == 10 && Wd == kEmbT, B200_ERR_STATE, "unexpected trunk output %dx%d", H, Wd);
+  return B200_OK;
+}
+
+int b200_emb_forward(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, const int32_t* chunk_valid,
+                     int32_t num_chunks, const uint8_t* masks, float* emb, void* stream) {
+  B200_CHECK(ctx && ctx->emb.loaded, B200_ERR_STATE, "embedding weights not loaded");
+  B200_CHECK(wav && chunk_off && chunk_valid && masks && emb && num_chunks >= 0, B200_ERR_INVALID, "bad arguments");
+  if (num_chunks == 0) return B200_OK;
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nbmax = num_chunks < ctx->emb_max_batch ? num_chunks : ctx->emb_max_batch;
+  int rc = ensure_ws(ctx, carve_emb(nbmax, nullptr, nullptr) + 4096);
+  if (rc) return rc;
+  if ((rc = push_meta(ctx, chunk_off, chunk_valid, num_chunks, st))) return rc;
+  EmbWs w;
+  carve_emb(nbmax, ctx->ws, &w);
+  for (int c0 = 0; c0 < num_chunks; c0 += nbmax) {
+    const int nb = (num_chunks - c0) < nbmax ? (num_chunks - c0) : nbmax;
+    if ((rc = fbank_forward(ctx->emb, wav, ctx->d_off + c0, ctx->d_valid + c0, nb, w.fbank, w.fmean, st))) return rc;
+    ctx->launches += 2;
+    if ((rc = trunk_run(ctx, w, nb, st))) return rc;
+    if ((rc = stats_pool_forward(w.A, masks + (size_t)c0 * kSpeakers * kFrames, w.stats, nb, st))) return rc;
+    if ((rc = sgemm_nt(w.stats, 2 * kStatsDim, ctx->emb.seg1_w, 2 * kStatsDim, emb + (size_t)c0 * kSpeakers * kEmbDim,
+                       kEmbDim, ctx->emb.seg1_b, nb * kSpeakers, kEmbDim, 2 * kStatsDim, 0, st)))
+      return rc;
+    ctx->launches += 2;
+  }
+  return B200_OK;
+}
+
+int b200_emb_fbank(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, const int32_t* chunk_valid,
+                   int32_t num_chunks, float* fbank, void* stream) {
+  B200_CHECK(ctx && ctx->emb.loaded, B200_ERR_STATE, "embedding weights not loaded");
+  B200_CHECK(wav && chunk_off && chunk_valid && fbank && num_chunks >= 0, B200_ERR_INVALID, "bad arguments");
+  if (num_chunks == 0) return B200_OK;
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_ws(ctx, (size_t)num_chunks * kMel * sizeof(float) + 4096);
+  if (rc) return rc;
+  if ((rc = push_meta(ctx, chunk_off, chunk_valid, num_chunks, st))) return rc;
+  float* fmean = reinterpret_cast<float*>(ctx->ws);
+  if ((rc = fbank_forward(ctx->emb, wav, ctx->d_off, ctx->d_valid, num_chunks, fbank, fmean, st))) return rc;
+  ctx->launches += 3;
+  return fbank_center(fbank, fmean, num_chunks, st);
+}
+
+int b200_emb_trunk(b200_ctx* ctx, const float* fbank, int32_t num_chunks, float* frames, void* stream) {
+  B200_CHECK(ctx && ctx->emb.loaded, B200_ERR_STATE, "embedding weights not loaded");
+  B200_CHECK(fbank && frames && num_chunks >= 0, B200_ERR_INVALID, "bad arguments");
+  if (num_chunks == 0) return B200_OK;
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nbmax = num_chunks < ctx->emb_max_batch ? num_chunks : ctx->emb_max_batch;
+  int rc = ensure_ws(ctx, carve_emb(nbmax, nullptr, nullptr) + 4096);
+  if (rc) return rc;
+  EmbWs w;
+  carve_emb(nbmax, ctx->ws, &w);
+  for (int c0 = 0; c0 < num_chunks; c0 += nbmax) {
+    const int nb = (num_chunks - c0) < nbmax ? (num_chunks - c0) : nbmax;
+    B200_CUDA_OK(cudaMemcpyAsync(w.fbank, fbank + (size_t)c0 * kFbankFrames * kMel,
+                                 (size_t)nb * kFbankFrames * kMel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    B200_CUDA_OK(cudaMemsetAsync(w.fmean, 0, (size_t)nb * kMel * sizeof(float), st));
+    if ((rc = trunk_run(ctx, w, nb, st))) return rc;
+    if ((rc = frames_to_nchw(w.A, frames + (size_t)c0 * 256 * 10 * kEmbT, nb, st))) return rc;
+    ctx->launches += 1;
+  }
+  return B200_OK;
+}
+
+int b200_stats_pool(b200_ctx* ctx, const float* seq, const float* weights, float* out, int32_t B, int32_t F, int32_t T,
+                    int32_t S, int32_t Tw, void* stream) {
+  B200_CHECK(ctx && seq && out && B >= 0 && F > 0 && T > 0 && S > 0, B200_ERR_INVALID, "bad arguments");
+  if (B == 0) return B200_OK;
+  DeviceGuard g(ctx->device);
+  ctx->launches += 1;
+  return stats_pool_generic(seq, weights, out, B, F, T, S, weights ? Tw : T, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------------
+static int push_ints(b200_ctx* ctx, const void* host, size_t bytes, void** dev, cudaStream_t st) {
+  // small per-call host arrays (start frames, hard clusters) ride in the tail of the meta buffers' allocation
+  void* p = nullptr;
+  B200_CUDA_OK(cudaMallocAsync(&p, bytes + 16, st));
+  B200_CUDA_OK(cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, st));
+  *dev = p;
+  return B200_OK;
+}
+
+int b200_speaker_count(b200_ctx* ctx, const uint8_t* seg, const int32_t* start_frame, int32_t num_chunks,
+                       int32_t num_frames, uint8_t* count, void* stream) {
+  B200_CHECK(ctx && seg && start_frame && count && num_chunks > 0 && num_frames > 0, B200_ERR_INVALID, "bad arguments");
+  for (int c = 1; c < num_chunks; ++c)
+    B200_CHECK(start_frame[c] >= start_frame[c - 1], B200_ERR_INVALID, "start_frame must be non-decreasing");
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  void* d_sf = nullptr;
+  int rc = push_ints(ctx, start_frame, sizeof(int) * num_chunks, &d_sf, st);
+  if (rc) return rc;
+  rc = speaker_count(seg, (const int*)d_sf, num_chunks, num_frames, count, st);
+  cudaFreeAsync(d_sf, st);
+  ctx->launches += 1;
+  return rc;
+}
+
+int b200_reconstruct(b200_ctx* ctx, const uint8_t* seg, const int8_t* hard_clusters, const int32_t* start_frame,
+                     int32_t num_chunks, int32_t num_frames, int32_t num_clusters, const uint8_t* count,
+                     int32_t num_clusters_out, uint8_t* discrete, void* stream) {
+  B200_CHECK(ctx && seg && hard_clusters && start_frame && count && discrete && num_chunks > 0 && num_frames > 0,
+             B200_ERR_INVALID, "bad arguments");
+  B200_CHECK(num_clusters_out >= num_clusters && num_clusters >= 0, B200_ERR_INVALID, "num_clusters_out < num_clusters");
+  for (int i = 0; i < num_chunks * 3; ++i)
+    B200_CHECK(hard_clusters[i] < num_clusters, B200_ERR_INVALID, "hard cluster %d >= %d", (int)hard_clusters[i],
+               num_clusters);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  void *d_sf = nullptr, *d_h = nullptr;
+  int rc = push_ints(ctx, start_frame, sizeof(int) * num_chunks, &d_sf, st);
+  if (rc) return rc;
+  if ((rc = push_ints(ctx, hard_clusters, (size_t)num_chunks * 3, &d_h, st))) return rc;
+  rc = reconstruct(seg, (const signed char*)d_h, (const int*)d_sf, num_chunks, num_frames, num_clusters_out, count,
+                   discrete, st);
+  cudaFreeAsync(d_sf, st);
+  cudaFreeAsync(d_h, st);
+  ctx->launches += 1;
+  return rc;
+}
+
+int b200_clean_frames(b200_ctx* ctx, const uint8_t* seg, int32_t num_chunks, int32_t* clean, uint8_t* active,
+                      void* stream) {
+  B200_CHECK(ctx && seg && clean && active && num_chunks >= 0, B200_ERR_INVALID, "bad arguments");
+  if (num_chunks == 0) return B200_OK;
+  DeviceGuard g(ctx->device);
+  ctx->launches += 1;
+  return clean_frames(seg, num_chunks, clean, active, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// Embedding path (kaldi fbank -> ResNet34 trunk -> masked stats pooling -> Linear) declarations.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct ConvLayer {
+  int C_in = 0, C_out = 0, ksize = 3, stride = 1;
+  __half* w = nullptr;     // device, [tap][C_out][C_in] fp16, BN scale folded
+  float* bias = nullptr;   // device, [C_out] fp32 (folded BN shift)
+};
+
+struct ConvParams {
+  int B, H_in, W_in, C_in;
+  int H_out, W_out, C_out;
+  int taps_h, taps_w, stride, pad;
+  int Ck, kblocks, tiles_w, num_tiles, relu;
+  const float* bias;
+  const __half* residual;
+  __half* out;
+  uint32_t a_bytes, b_bytes, nstages, idesc, swizzle;
+};
+
+struct BlockWeights {
+  ConvLayer conv1, conv2, shortcut;
+  bool has_shortcut = false;
+};
+
+struct EmbWeights {
+  bool loaded = false;
+  float* conv1_w = nullptr;      // [32][9] folded
+  float* conv1_b = nullptr;      // [32]
+  std::vector<BlockWeights> blocks;   // 16 BasicBlocks
+  float* seg1_w = nullptr;       // [256][5120] fp32 (PyTorch layout)
+  float* seg1_b = nullptr;       // [256]
+  // fbank constants
+  float* window = nullptr;       // [400] hamming
+  float* mel_w = nullptr;        // packed non-zero mel weights
+  int* mel_start = nullptr;      // [80] first fft bin
+  int* mel_len = nullptr;        // [80] number of bins
+  int* mel_off = nullptr;        // [80] offset into mel_w
+  float* twiddle = nullptr;      // [256][2] cos/sin(-2 pi k / 512)
+};
+
+// impl: 0 = SIMT reference conv, 1 = tcgen05 tensor-core conv
+int conv_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H_in, int W_in,
+                 int relu, int impl, int num_sms, cudaStream_t stream);
+int conv1_forward(const float* fbank, const float* fmean, const float* w, const float* bias, __half* out, int B,
+                  cudaStream_t stream);
+
+// fbank: wav chunks (device waveform, chunk c starts at c*step, zero padded past num_samples) -> [B][998][80] fp32
+int fbank_forward(const EmbWeights& W, const float* wav, const long long* chunk_off, const int* chunk_valid, int B,
+                  float* fbank, float* fmean, cudaStream_t stream);
+int fbank_center(float* fbank, const float* fmean, int B, cudaStream_t stream);
+// NHWC fp16 [B][10][125][256] -> NCHW fp32 [B][256][10][125]
+int frames_to_nchw(const __half* feat, float* out, int B, cudaStream_t stream);
+
+// masked statistics pooling: feat [B][10][125][256] fp16 NHWC, masks [B][3][589] u8 -> stats [B*3][5120] fp32
+int stats_pool_forward(const __half* feat, const unsigned char* masks, float* stats, int B, cudaStream_t stream);
+// generic weighted pooling used by the known-answer tests: seq [B][F][T] fp32, w [B][S][Tw] fp32 -> [B][S][2F]
+int stats_pool_generic(const float* seq, const float* w, float* out, int B, int F, int T, int S, int Tw,
+                       cudaStream_t stream);
+
+}  // namespace b200

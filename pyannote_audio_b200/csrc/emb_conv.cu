@@ -1,0 +1,477 @@
+// WeSpeaker ResNet34 trunk convolutions for sm_100a.
+//
+// Reference semantics: /root/reference/src/pyannote/audio/models/embedding/wespeaker/resnet.py
+//   BasicBlock.forward :140-145 (conv3x3-BN-ReLU-conv3x3-BN + shortcut -> ReLU), ResNet.forward :413-419.
+// Eval-mode BatchNorm is folded into the conv weights / a per-channel bias on the host (emb_weights.cu).
+//
+// conv_tc_kernel: implicit-GEMM convolution on the 5th-gen tensor cores.
+//   GEMM view  D[M=128 output pixels of one image row][N=C_out] += A[M][K] * B[N][K]^T,
+//   K = taps * C_in walked tap by tap in chunks of Ck channels.  Activations are NHWC fp16 so that one
+//   TMA box (Ck channels x 128 consecutive pixels) lands in shared memory as a K-major, hardware-swizzled
+//   A tile; convolution padding is TMA out-of-bounds zero fill, stride-2 is the tensor map's element stride.
+//   Weights [tap][C_out][C_in] land the same way as the K-major B tile.  Accumulators live in TMEM
+//   (two stages of N columns so the epilogue of tile i overlaps the MMAs of tile i+1).
+//   Warp roles: warp0 = TMA producer, warp1 = tcgen05.mma issuer (+TMEM alloc), warps2-5 = epilogue
+//   (tcgen05.ld -> +bias (+residual) -> ReLU -> fp16 NHWC store).  Persistent over tiles.
+#include "common.cuh"
+#include "emb.cuh"
+#include <cuda.h>
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, hardware swizzle (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout type
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor-core implicit GEMM conv
+// ------------------------------------------------------------------------------------------------
+constexpr int kTcThreads = 192;
+constexpr int kTileM = 128;
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;            // swizzle-128B operands need 1024 B alignment
+  uint8_t* gbase = smem_raw + (base - raw);
+  // [0,1024): barriers + tmem pointer, [1024,2048): bias, [2048,...): stages
+  const uint32_t bar_full = base;                            // 8 x 8 B
+  const uint32_t bar_empty = base + 64;                      // 8 x 8 B
+  const uint32_t bar_tfull = base + 128;                     // 2 x 8 B
+  const uint32_t bar_tempty = base + 144;                    // 2 x 8 B
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + 192);
+  float* s_bias = reinterpret_cast<float*>(gbase + 1024);
+  const uint32_t stage0 = base + 2048;
+  const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int N = p.C_out;
+
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s_bias[i] = p.bias[i];
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < p.nstages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int cchunks = p.C_in / p.Ck;
+  const int ksteps = p.Ck / 16;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int wt = tile % p.tiles_w;
+        const int bh = tile / p.tiles_w;
+        const int h = bh % p.H_out;
+        const int b = bh / p.H_out;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          const int tap = kb / cchunks, cc = kb - tap * cchunks;
+          const int kh = tap / p.taps_w, kw = tap - kh * p.taps_w;
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          mbar_expect_tx(bar_full + 8 * stage, stage_bytes);
+          const uint32_t sa = stage0 + stage * stage_bytes;
+          tma_load_4d(&tmA, bar_full + 8 * stage, sa, cc * p.Ck, wt * kTileM * p.stride + kw - p.pad,
+                      h * p.stride + kh - p.pad, b);
+          tma_load_3d(&tmB, bar_full + 8 * stage, sa + p.a_bytes, cc * p.Ck, 0, tap);
+          if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      const uint32_t sbo = (p.swizzle == 128) ? 1024u : 512u;
+      const uint32_t ltype = (p.swizzle == 128) ? 2u : 4u;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)N;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = stage0 + stage * stage_bytes;
+          const uint64_t adesc = make_kmajor_desc(sa, sbo, ltype);
+          const uint64_t bdesc = make_kmajor_desc(sa + p.a_bytes, sbo, ltype);
+          for (int k = 0; k < ksteps; ++k) {
+            // +32 B per K=16 step inside the swizzle row: start-address field is in 16 B units
+            tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) != 0);
+          }
+          tc_commit(bar_empty + 8 * stage);   // frees the smem stage once these MMAs have read it
+          if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(bar_tfull + 8 * acc);       // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;                   // TMEM lane quadrant this warp may access
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int wt = tile % p.tiles_w;
+      const int bh = tile / p.tiles_w;        // = b * H_out + h
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const int w = wt * kTileM + q * 32 + lane;
+      const bool valid = w < p.W_out;
+      const size_t pix = ((size_t)bh * p.W_out + (valid ? w : 0)) * (size_t)N;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)N;
+      for (int n0 = 0; n0 < N; n0 += 32) {
+        uint32_t r[32];
+        tc_ld32(taddr + n0, r);
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[n0 + j];
+          if (p.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix + n0);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              uint4 u = __ldg(rp + j4);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 f = __half22float2(h2[e]);
+                v[j4 * 8 + 2 * e] += f.x;
+                v[j4 * 8 + 2 * e + 1] += f.y;
+              }
+            }
+          }
+          uint4* op = reinterpret_cast<uint4*>(p.out + pix + n0);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint4 u;
+            __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a = v[j4 * 8 + 2 * e], c = v[j4 * 8 + 2 * e + 1];
+              if (p.relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+              h2[e] = __floats2half2_rn(a, c);
+            }
+            op[j4] = u;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT reference conv (same math, CUDA cores) -- debugging aid and A/B check for the tensor-core path
+// ------------------------------------------------------------------------------------------------
+__global__ void conv_simt_kernel(const __half* __restrict__ in, const __half* __restrict__ wt, ConvParams p) {
+  // one thread = one output pixel x 8 output channels
+  const int groups = p.C_out / 8;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)p.B * p.H_out * p.W_out * groups;
+  if (idx >= total) return;
+  const int g = idx % groups;
+  size_t pixel = idx / groups;
+  const int w = pixel % p.W_out;
+  const int h = (pixel / p.W_out) % p.H_out;
+  const int b = pixel / ((size_t)p.W_out * p.H_out);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = p.bias[g * 8 + j];
+  for (int kh = 0; kh < p.taps_h; ++kh) {
+    const int hi = h * p.stride + kh - p.pad;
+    if (hi < 0 || hi >= p.H_in) continue;
+    for (int kw = 0; kw < p.taps_w; ++kw) {
+      const int wi = w * p.stride + kw - p.pad;
+      if (wi < 0 || wi >= p.W_in) continue;
+      const __half* ip = in + (((size_t)b * p.H_in + hi) * p.W_in + wi) * p.C_in;
+      const int tap = kh * p.taps_w + kw;
+      for (int ci = 0; ci < p.C_in; ci += 8) {
+        uint4 xu = *reinterpret_cast<const uint4*>(ip + ci);
+        const __half2* xh = reinterpret_cast<const __half2*>(&xu);
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __half22float2(xh[e]);
+          x[2 * e] = f.x;
+          x[2 * e + 1] = f.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 wu = *reinterpret_cast<const uint4*>(wt + ((size_t)tap * p.C_out + g * 8 + j) * p.C_in + ci);
+          const __half2* wh = reinterpret_cast<const __half2*>(&wu);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float2 f = __half22float2(wh[e]);
+            acc[j] = fmaf(x[2 * e], f.x, acc[j]);
+            acc[j] = fmaf(x[2 * e + 1], f.y, acc[j]);
+          }
+        }
+      }
+    }
+  }
+  const size_t o = (((size_t)b * p.H_out + h) * p.W_out + w) * p.C_out + g * 8;
+  if (p.residual) {
+    uint4 ru = *reinterpret_cast<const uint4*>(p.residual + o);
+    const __half2* rh = reinterpret_cast<const __half2*>(&ru);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 f = __half22float2(rh[e]);
+      acc[2 * e] += f.x;
+      acc[2 * e + 1] += f.y;
+    }
+  }
+  uint4 ou;
+  __half2* oh = reinterpret_cast<__half2*>(&ou);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float a = acc[2 * e], c = acc[2 * e + 1];
+    if (p.relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+    oh[e] = __floats2half2_rn(a, c);
+  }
+  *reinterpret_cast<uint4*>(p.out + o) = ou;
+}
+
+// ------------------------------------------------------------------------------------------------
+// first conv: 1 -> 32 channels on the (mean-centred) fbank, fp32 in, fp16 NHWC out
+//   x[b][h=f][w=t] = fbank[b][t][f] - mean[b][f]   (resnet.py:411-413 permute + wespeaker/__init__.py:138)
+// ------------------------------------------------------------------------------------------------
+__global__ void conv1_kernel(const float* __restrict__ fbank, const float* __restrict__ fmean,
+                             const float* __restrict__ w /*[32][9] folded*/, const float* __restrict__ bias /*[32]*/,
+                             __half* __restrict__ out, int B) {
+  __shared__ float sw[32 * 9];
+  __shared__ float sb[32];
+  for (int i = threadIdx.x; i < 288; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*80*998, h fastest for coalesced reads
+  const size_t total = (size_t)B * kMel * kFbankFrames;
+  if (idx >= total) return;
+  const int h = idx % kMel;
+  const int t = (idx / kMel) % kFbankFrames;
+  const int b = idx / ((size_t)kMel * kFbankFrames);
+  float x[9];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int hh = h + kh - 1, tt = t + kw - 1;
+      float v = 0.f;
+      if (hh >= 0 && hh < kMel && tt >= 0 && tt < kFbankFrames)
+        v = fbank[((size_t)b * kFbankFrames + tt) * kMel + hh] - fmean[b * kMel + hh];
+      x[kh * 3 + kw] = v;
+    }
+  __half2 o[16];
+#pragma unroll
+  for (int c = 0; c < 32; c += 2) {
+    float a0 = sb[c], a1 = sb[c + 1];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      a0 = fmaf(x[k], sw[c * 9 + k], a0);
+      a1 = fmaf(x[k], sw[(c + 1) * 9 + k], a1);
+    }
+    o[c / 2] = __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+  }
+  uint4* op = reinterpret_cast<uint4*>(out + (((size_t)b * kMel + h) * kFbankFrames + t) * 32);
+  const uint4* src = reinterpret_cast<const uint4*>(o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) op[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+int conv_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H_in, int W_in,
+                 int relu, int impl, int num_sms, cudaStream_t stream) {
+  ConvParams p{};
+  p.B = B; p.H_in = H_in; p.W_in = W_in; p.C_in = L.C_in; p.C_out = L.C_out;
+  p.taps_h = L.ksize; p.taps_w = L.ksize; p.stride = L.stride; p.pad = L.ksize / 2;
+  p.H_out = (H_in + 2 * p.pad - L.ksize) / L.stride + 1;
+  p.W_out = (W_in + 2 * p.pad - L.ksize) / L.stride + 1;
+  p.relu = relu; p.bias = L.bias; p.residual = residual; p.out = out;
+  p.Ck = (L.C_in >= 64) ? 64 : 32;
+  p.swizzle = (p.Ck == 64) ? 128 : 64;
+  p.kblocks = L.ksize * L.ksize * (L.C_in / p.Ck);
+  p.tiles_w = ceil_div(p.W_out, kTileM);
+  p.num_tiles = B * p.H_out * p.tiles_w;
+  p.a_bytes = kTileM * p.Ck * 2;
+  p.b_bytes = L.C_out * p.Ck * 2;
+  const uint32_t budget = 200 * 1024;
+  p.nstages = budget / (p.a_bytes + p.b_bytes);
+  if (p.nstages > 8) p.nstages = 8;
+  // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=f32, A=B=f16, K-major both, N>>3, M>>4
+  p.idesc = (1u << 4) | ((uint32_t)(L.C_out >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+
+  if (impl == 0) {
+    const size_t total = (size_t)B * p.H_out * p.W_out * (L.C_out / 8);
+    conv_simt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, L.w, p);
+    B200_CUDA_OK(cudaGetLastError());
+    return B200_OK;
+  }
+
+  PFN_encodeTiled enc = get_encode();
+  B200_CHECK(enc != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)L.C_in, (cuuint64_t)W_in, (cuuint64_t)H_in, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)L.C_in * 2, (cuuint64_t)W_in * L.C_in * 2,
+                             (cuuint64_t)H_in * W_in * L.C_in * 2};
+    cuuint32_t box[4] = {(cuuint32_t)p.Ck, (cuuint32_t)(kTileM * L.stride), 1, 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)L.stride, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(in), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     p.swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)L.C_in, (cuuint64_t)L.C_out, (cuuint64_t)(L.ksize * L.ksize)};
+    cuuint64_t strides[2] = {(cuuint64_t)L.C_in * 2, (cuuint64_t)L.C_out * L.C_in * 2};
+    cuuint32_t box[3] = {(cuuint32_t)p.Ck, (cuuint32_t)L.C_out, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(L.w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     p.swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+  }
+  const size_t smem = 1024 + 2048 + (size_t)p.nstages * (p.a_bytes + p.b_bytes);
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  conv_tc_kernel<<<grid, kTcThreads, smem, stream>>>(tmA, tmB, p);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+int conv1_forward(const float* fbank, const float* fmean, const float* w, const float* bias, __half* out, int B,
+                  cudaStream_t stream) {
+  const size_t total = (size_t)B * kMel * kFbankFrames;
+  conv1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(fbank, fmean, w, bias, out, B);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // namespace b200

@@ -1,0 +1,281 @@
+// Embedding path: kaldi-compatible log-mel fbank and masked statistics pooling.
+//
+// fbank follows torchaudio.compliance.kaldi.fbank as called by the reference
+//   (/root/reference/src/pyannote/audio/models/embedding/wespeaker/__init__.py:113-139):
+//   x*32768 -> frames of 400 @ hop 160 (snip_edges) -> remove DC -> pre-emphasis 0.97 (replicate pad) ->
+//   Hamming -> zero-pad to 512 -> |rFFT|^2 -> 80 triangular mel bins (20 Hz..Nyquist) -> log(max(., eps)).
+// The global-mean centring over frames (:137-139) is produced as a separate [B][80] vector that the first
+// conv subtracts on load.
+//
+// stats pooling follows models/blocks/pooling.py:30-61,76-130 via resnet.py:61-66 (TSTP): nearest
+// interpolation of the 589-frame mask onto the 125 trunk frames, weighted mean and weighted unbiased std.
+#include "common.cuh"
+#include "emb.cuh"
+
+namespace b200 {
+
+constexpr int kFrameLen = 400;
+constexpr int kFrameHop = 160;
+constexpr int kFft = 512;
+constexpr float kEps = 1.1920928955078125e-07f;
+
+__device__ __forceinline__ int bitrev9(int x) { return __brev((unsigned)x) >> 23; }
+
+__global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wav,
+                                                    const long long* __restrict__ chunk_off,
+                                                    const int* __restrict__ chunk_valid,
+                                                    const float* __restrict__ window,
+                                                    const float* __restrict__ twiddle, const float* __restrict__ mel_w,
+                                                    const int* __restrict__ mel_start, const int* __restrict__ mel_len,
+                                                    const int* __restrict__ mel_off, float* __restrict__ out) {
+  __shared__ float s_re[8][kFft];
+  __shared__ float s_im[8][kFft];
+  __shared__ float s_tw[256][2];
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) (&s_tw[0][0])[i] = twiddle[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int frame = blockIdx.x * 8 + warp;
+  const int b = blockIdx.y;
+  if (frame >= kFbankFrames) return;
+  float* re = s_re[warp];
+  float* im = s_im[warp];
+  const float* xw = wav + chunk_off[b];
+  const int valid = chunk_valid[b];
+  const int base = frame * kFrameHop;
+
+  // load + scale, frame mean
+  float x[13];
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 13; ++j) {
+    const int i = lane + 32 * j;
+    float v = 0.f;
+    if (i < kFrameLen) {
+      const int g = base + i;
+      v = (g < valid) ? xw[g] * 32768.0f : 0.f;
+    }
+    x[j] = v;
+    sum += v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)kFrameLen;
+#pragma unroll
+  for (int j = 0; j < 13; ++j) {
+    const int i = lane + 32 * j;
+    if (i < kFrameLen) im[i] = x[j] - mean;      // stage DC-removed samples in im[]
+  }
+  __syncwarp();
+  // pre-emphasis + window, scatter to bit-reversed order in re[]
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int i = lane + 32 * j;
+    float v = 0.f;
+    if (i < kFrameLen) {
+      const float cur = im[i];
+      const float prev = im[i > 0 ? i - 1 : 0];
+      v = (cur - 0.97f * prev) * window[i];
+    }
+    re[bitrev9(i)] = v;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) im[lane + 32 * j] = 0.f;
+  __syncwarp();
+  // radix-2 DIT FFT, 9 stages, 256 butterflies each
+  for (int s = 0; s < 9; ++s) {
+    const int half = 1 << s;
+    const int tstep = 256 >> s;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int bf = lane + 32 * j;
+      const int pos = bf & (half - 1);
+      const int i0 = ((bf >> s) << (s + 1)) + pos;
+      const int i1 = i0 + half;
+      const float wr = s_tw[pos * tstep][0], wi = s_tw[pos * tstep][1];
+      const float xr = re[i1], xi = im[i1];
+      const float tr = wr * xr - wi * xi;
+      const float ti = wr * xi + wi * xr;
+      const float ur = re[i0], ui = im[i0];
+      re[i0] = ur + tr; im[i0] = ui + ti;
+      re[i1] = ur - tr; im[i1] = ui - ti;
+    }
+    __syncwarp();
+  }
+  // power spectrum, bins 0..255 (the Nyquist bin carries zero mel weight: kaldi pads the bank with a zero column)
+  float pw[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = lane + 32 * j;
+    const float a = sqrtf(re[k] * re[k] + im[k] * im[k]);   // reference: rfft().abs().pow(2)
+    pw[j] = a * a;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) re[lane + 32 * j] = pw[j];
+  __syncwarp();
+  for (int m = lane; m < kMel; m += 32) {
+    const int st = mel_start[m], ln = mel_len[m], off = mel_off[m];
+    float acc = 0.f;
+    for (int i = 0; i < ln; ++i) acc = fmaf(re[st + i], mel_w[off + i], acc);
+    out[((size_t)b * kFbankFrames + frame) * kMel + m] = logf(fmaxf(acc, kEps));
+  }
+}
+
+__global__ void fbank_mean_kernel(const float* __restrict__ fb, float* __restrict__ fmean) {
+  const int b = blockIdx.x, m = threadIdx.x;
+  if (m >= kMel) return;
+  double s = 0.0;
+  for (int t = 0; t < kFbankFrames; ++t) s += (double)fb[((size_t)b * kFbankFrames + t) * kMel + m];
+  fmean[b * kMel + m] = (float)(s / kFbankFrames);
+}
+
+__global__ void fbank_center_kernel(float* __restrict__ fb, const float* __restrict__ fmean, size_t total) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int m = idx % kMel;
+  const int b = idx / ((size_t)kMel * kFbankFrames);
+  fb[idx] -= fmean[b * kMel + m];
+}
+
+int fbank_center(float* fbank, const float* fmean, int B, cudaStream_t stream) {
+  const size_t total = (size_t)B * kFbankFrames * kMel;
+  fbank_center_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(fbank, fmean, total);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+__global__ void frames_to_nchw_kernel(const __half* __restrict__ feat, float* __restrict__ out, size_t total) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over NCHW output
+  if (idx >= total) return;
+  const int t = idx % kEmbT;
+  const int h = (idx / kEmbT) % 10;
+  const int c = (idx / (kEmbT * 10)) % 256;
+  const size_t b = idx / ((size_t)kEmbT * 10 * 256);
+  out[idx] = __half2float(feat[((b * 10 + h) * kEmbT + t) * 256 + c]);
+}
+
+int frames_to_nchw(const __half* feat, float* out, int B, cudaStream_t stream) {
+  const size_t total = (size_t)B * 256 * 10 * kEmbT;
+  frames_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(feat, out, total);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+int fbank_forward(const EmbWeights& W, const float* wav, const long long* chunk_off, const int* chunk_valid, int B,
+                  float* fbank, float* fmean, cudaStream_t stream) {
+  dim3 grid(ceil_div(kFbankFrames, 8), B);
+  fbank_kernel<<<grid, 256, 0, stream>>>(wav, chunk_off, chunk_valid, W.window, W.twiddle, W.mel_w, W.mel_start,
+                                         W.mel_len, W.mel_off, fbank);
+  B200_CUDA_OK(cudaGetLastError());
+  fbank_mean_kernel<<<B, 96, 0, stream>>>(fbank, fmean);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// masked stats pooling on the trunk output, all 3 local speakers from one pass
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stats_pool_kernel(const __half* __restrict__ feat,
+                                                         const unsigned char* __restrict__ masks,
+                                                         float* __restrict__ stats) {
+  // grid (10 freq rows, B); thread = channel c; feat[b][h][t][c]
+  __shared__ float s_w[kSpeakers][kEmbT];
+  const int h = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
+  for (int i = threadIdx.x; i < kSpeakers * kEmbT; i += blockDim.x) {
+    const int s = i / kEmbT, t = i % kEmbT;
+    // F.interpolate(mode="nearest"): src = floor(dst * in / out)   (pooling.py:116-117)
+    const int src = (int)(((long long)t * kFrames) / kEmbT);
+    s_w[s][t] = (float)masks[((size_t)b * kSpeakers + s) * kFrames + src];
+  }
+  __syncthreads();
+  const __half* fp = feat + (((size_t)b * 10 + h) * kEmbT) * 256 + c;
+  float v1[kSpeakers], v2[kSpeakers], sx[kSpeakers];
+#pragma unroll
+  for (int s = 0; s < kSpeakers; ++s) { v1[s] = 0.f; v2[s] = 0.f; sx[s] = 0.f; }
+  for (int t = 0; t < kEmbT; ++t) {
+    const float x = __half2float(fp[(size_t)t * 256]);
+#pragma unroll
+    for (int s = 0; s < kSpeakers; ++s) {
+      const float w = s_w[s][t];
+      v1[s] += w;
+      v2[s] += w * w;
+      sx[s] += x * w;
+    }
+  }
+  float mean[kSpeakers], sd[kSpeakers];
+#pragma unroll
+  for (int s = 0; s < kSpeakers; ++s) {
+    v1[s] += 1e-8f;
+    mean[s] = sx[s] / v1[s];
+    sd[s] = 0.f;
+  }
+  for (int t = 0; t < kEmbT; ++t) {
+    const float x = __half2float(fp[(size_t)t * 256]);
+#pragma unroll
+    for (int s = 0; s < kSpeakers; ++s) {
+      const float d = x - mean[s];
+      sd[s] += d * d * s_w[s][t];
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < kSpeakers; ++s) {
+    const float var = sd[s] / (v1[s] - v2[s] / v1[s] + 1e-8f);
+    float* o = stats + ((size_t)b * kSpeakers + s) * (2 * kStatsDim);
+    o[c * 10 + h] = mean[s];
+    o[kStatsDim + c * 10 + h] = sqrtf(var);
+  }
+}
+
+int stats_pool_forward(const __half* feat, const unsigned char* masks, float* stats, int B, cudaStream_t stream) {
+  dim3 grid(10, B);
+  stats_pool_kernel<<<grid, 256, 0, stream>>>(feat, masks, stats);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+// generic fp32 version (any F, T, S, Tw) used by the known-answer tests of the reference
+__global__ void stats_pool_generic_kernel(const float* __restrict__ seq, const float* __restrict__ w,
+                                          float* __restrict__ out, int B, int F, int T, int S, int Tw) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * S * F) return;
+  const int f = idx % F, s = (idx / F) % S, b = idx / (F * S);
+  const float* x = seq + ((size_t)b * F + f) * T;
+  float mean, sd;
+  if (w == nullptr) {
+    float sum = 0.f;
+    for (int t = 0; t < T; ++t) sum += x[t];
+    mean = sum / T;
+    float acc = 0.f;
+    for (int t = 0; t < T; ++t) acc += (x[t] - mean) * (x[t] - mean);
+    sd = sqrtf(acc / (T - 1));
+  } else {
+    const float* ww = w + ((size_t)b * S + s) * Tw;
+    float v1 = 0.f, v2 = 0.f, sx = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float wt = ww[(int)(((long long)t * Tw) / T)];
+      v1 += wt; v2 += wt * wt; sx += x[t] * wt;
+    }
+    v1 += 1e-8f;
+    mean = sx / v1;
+    float acc = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float wt = ww[(int)(((long long)t * Tw) / T)];
+      acc += (x[t] - mean) * (x[t] - mean) * wt;
+    }
+    sd = sqrtf(acc / (v1 - v2 / v1 + 1e-8f));
+  }
+  float* o = out + ((size_t)b * S + s) * 2 * F;
+  o[f] = mean;
+  o[F + f] = sd;
+}
+
+int stats_pool_generic(const float* seq, const float* w, float* out, int B, int F, int T, int S, int Tw,
+                       cudaStream_t stream) {
+  const int total = B * S * F;
+  stats_pool_generic_kernel<<<ceil_div(total, 128), 128, 0, stream>>>(seq, w, out, B, F, T, S, Tw);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // namespace b200

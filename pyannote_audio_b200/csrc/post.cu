@@ -1,0 +1,148 @@
+// Integer post-processing of the segmentation: powerset -> multilabel, speaker counting (overlap-add),
+// clustered reconstruction + top-count selection, clean-frame statistics for clustering.
+//
+// Reference (paths relative to /root/reference/src/pyannote/audio):
+//   Powerset.to_multilabel            utils/powerset.py:115-140
+//   Inference.aggregate               core/inference.py:498-620   (hamming=False, warm_up=(0,0))
+//   speaker_count                     pipelines/utils/diarization.py:150-185   (np.rint of a float32 ratio)
+//   reconstruct / to_diarization      pipelines/speaker_diarization.py:480-528, utils/diarization.py:221-268
+//   filter_embeddings                 pipelines/clustering.py:77-125
+// Everything here is exact small-integer arithmetic; scatter loops of the reference become per-frame gathers
+// over the (<= 11) chunks that cover a frame.
+#include "common.cuh"
+#include "post.cuh"
+
+namespace b200 {
+
+__constant__ unsigned char kPowersetMap[7][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1},
+                                                 {1, 1, 0}, {1, 0, 1}, {0, 1, 1}};
+
+__global__ void powerset_kernel(const unsigned char* __restrict__ cls, long long n, unsigned char* __restrict__ ml) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = cls[i] < 7 ? cls[i] : 0;
+  ml[i * 3 + 0] = kPowersetMap[c][0];
+  ml[i * 3 + 1] = kPowersetMap[c][1];
+  ml[i * 3 + 2] = kPowersetMap[c][2];
+}
+
+int powerset_to_multilabel(const unsigned char* cls, long long n, unsigned char* ml, cudaStream_t stream) {
+  powerset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(cls, n, ml);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+// first chunk whose window [start, start+589) may contain frame f  (start_frame is non-decreasing)
+__device__ __forceinline__ int first_chunk(const int* __restrict__ sf, int C, int f) {
+  int lo = 0, hi = C;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (sf[mid] + kFrames <= f) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void speaker_count_kernel(const unsigned char* __restrict__ seg, const int* __restrict__ sf, int C, int F,
+                                     unsigned char* __restrict__ count) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  int num = 0, den = 0;
+  for (int c = first_chunk(sf, C, f); c < C && sf[c] <= f; ++c) {
+    const unsigned char* p = seg + ((size_t)c * kFrames + (f - sf[c])) * 3;
+    num += p[0] + p[1] + p[2];
+    den += 1;
+  }
+  float avg = 0.f;                                   // missing = 0.0 where no chunk contributes
+  if (den > 0) avg = __fdiv_rn((float)num, (float)den);
+  count[f] = (unsigned char)rintf(avg);              // np.rint: round half to even
+}
+
+int speaker_count(const unsigned char* seg, const int* sf, int C, int F, unsigned char* count, cudaStream_t stream) {
+  speaker_count_kernel<<<ceil_div(F, 256), 256, 0, stream>>>(seg, sf, C, F, count);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+constexpr int kMaxK = 32;
+
+__global__ void reconstruct_kernel(const unsigned char* __restrict__ seg, const signed char* __restrict__ hard,
+                                   const int* __restrict__ sf, int C, int F, int Kout,
+                                   const unsigned char* __restrict__ count, unsigned char* __restrict__ out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  int act[kMaxK];
+#pragma unroll
+  for (int k = 0; k < kMaxK; ++k) act[k] = 0;
+  for (int c = first_chunk(sf, C, f); c < C && sf[c] <= f; ++c) {
+    const unsigned char* p = seg + ((size_t)c * kFrames + (f - sf[c])) * 3;
+    const signed char* h = hard + c * 3;
+    // per cluster: max over the local speakers mapped to it (values are 0/1 -> OR), then summed over chunks
+    int mk[3];
+    int nm = 0;
+    for (int s = 0; s < 3; ++s) {
+      const int k = h[s];
+      if (k < 0) continue;
+      bool seen = false;
+      for (int j = 0; j < nm; ++j) seen |= (mk[j] == k);
+      if (seen) continue;
+      mk[nm++] = k;
+      int v = 0;
+      for (int s2 = s; s2 < 3; ++s2)
+        if (h[s2] == k) v |= p[s2];
+      act[k] += v;
+    }
+  }
+  const int cnt = count[f];
+  unsigned used = 0;
+  unsigned char* o = out + (size_t)f * Kout;
+  for (int k = 0; k < Kout; ++k) o[k] = 0;
+  for (int i = 0; i < cnt && i < Kout; ++i) {
+    int best = -1, bv = -1;
+    for (int k = 0; k < Kout; ++k)
+      if (!((used >> k) & 1u) && act[k] > bv) { bv = act[k]; best = k; }   // ties -> lowest cluster index
+    used |= 1u << best;
+    o[best] = 1;
+  }
+}
+
+int reconstruct(const unsigned char* seg, const signed char* hard, const int* sf, int C, int F, int Kout,
+                const unsigned char* count, unsigned char* out, cudaStream_t stream) {
+  B200_CHECK(Kout >= 1 && Kout <= kMaxK, B200_ERR_INVALID, "reconstruct: %d clusters unsupported (max %d)", Kout, kMaxK);
+  reconstruct_kernel<<<ceil_div(F, 128), 128, 0, stream>>>(seg, hard, sf, C, F, Kout, count, out);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+__global__ void clean_frames_kernel(const unsigned char* __restrict__ seg, int C, int* __restrict__ clean,
+                                    unsigned char* __restrict__ active) {
+  // one warp per chunk
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= C) return;
+  int cl[3] = {0, 0, 0}, ac[3] = {0, 0, 0};
+  for (int t = lane; t < kFrames; t += 32) {
+    const unsigned char* p = seg + ((size_t)c * kFrames + t) * 3;
+    const int s = p[0] + p[1] + p[2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (s == 1) cl[k] += p[k];
+      ac[k] |= p[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    for (int o = 16; o > 0; o >>= 1) {
+      cl[k] += __shfl_xor_sync(0xffffffffu, cl[k], o);
+      ac[k] |= __shfl_xor_sync(0xffffffffu, ac[k], o);
+    }
+    if (lane == 0) { clean[c * 3 + k] = cl[k]; active[c * 3 + k] = (unsigned char)ac[k]; }
+  }
+}
+
+int clean_frames(const unsigned char* seg, int C, int* clean, unsigned char* active, cudaStream_t stream) {
+  clean_frames_kernel<<<ceil_div(C * 32, 256), 256, 0, stream>>>(seg, C, clean, active);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // namespace b200

@@ -1,0 +1,40 @@
+// Segmentation path (PyanNet: SincNet front-end -> 4x BiLSTM -> Linear x2 -> classifier -> powerset argmax).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct SegWeights {
+  bool loaded = false;
+  int lstm_layers = 4;
+  float wav_w = 1.f, wav_b = 0.f;   // sincnet.wav_norm1d affine
+  float* sinc_f = nullptr;          // [126][80]: half filters (k=0..124) + centre tap (k=125); cos ch 0..39, sin 40..79
+  float* in_gamma[3] = {nullptr, nullptr, nullptr};   // sincnet.norm1d.{0,1,2}.weight
+  float* in_beta[3] = {nullptr, nullptr, nullptr};
+  float* conv_w[2] = {nullptr, nullptr};   // [CIN][5][60]
+  float* conv_b[2] = {nullptr, nullptr};   // [60]
+  // LSTM, per layer: W_ih for both directions [1024][Kpad] with row = dir*512 + unit*4 + gate; bias = b_ih+b_hh
+  float* w_ih[8] = {};
+  float* b_g[8] = {};
+  int k_in[8] = {};                 // padded input size (64, 256, ...)
+  float* w_hh[8] = {};              // [2 dir][2 rank][128 k][256]  (smem image of the recurrent kernel)
+  float* lin_w[2] = {nullptr, nullptr};   // [128][256], [128][128]
+  float* lin_b[2] = {nullptr, nullptr};
+  float* cls_w = nullptr;           // [7][128]
+  float* cls_b = nullptr;           // [7]
+};
+
+int sgemm_nt(const float* A, int lda, const float* Bw, int ldb, float* C, int ldc, const float* bias, int M, int N,
+             int K, int act, cudaStream_t stream);
+
+// SincNet front-end on NB chunks: wav + per-chunk (offset, valid) -> X0 [NB][589][64] fp32 (60 features + 4 zero pad)
+size_t sincnet_workspace_bytes(int NB);
+int sincnet_forward(const SegWeights& W, const float* wav, const long long* chunk_off, const int* chunk_valid, int NB,
+                    void* ws, float* x0, cudaStream_t stream);
+
+// BiLSTM stack + linear head: X0 -> class ids [NB][589] u8 (+ optional log-probs [NB][589][7])
+size_t lstm_workspace_bytes(int NB);
+int lstm_head_forward(const SegWeights& W, const float* x0, int NB, void* ws, unsigned char* cls, float* logp,
+                      int num_sms, cudaStream_t stream);
+
+}  // namespace b200
