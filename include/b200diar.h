@@ -134,6 +134,24 @@ int b200_reconstruct(b200_ctx* ctx, const uint8_t* seg, const int8_t* hard_clust
  * = any frame active (inactive speakers, speaker_diarization.py:681). */
 int b200_clean_frames(b200_ctx* ctx, const uint8_t* seg, int32_t num_chunks, int32_t* clean, uint8_t* active,
                       void* stream);
+/* linkage(X, "centroid", "euclidean") (scipy, called at clustering.py:600-602 and :374-376): x[n][dim] fp64 device;
+ * rows are L2-normalised first when normalize != 0; Z[n-1][4] fp64 device in scipy's format. */
+int b200_linkage_centroid(b200_ctx* ctx, const double* x, int32_t n, int32_t dim, int32_t normalize, double* Z,
+                          void* stream);
+/* fcluster(Z, t, criterion="distance") (clustering.py:604, 385): HOST arrays, labels[n] 1-based like scipy. */
+int b200_fcluster_distance(const double* Z, int32_t n, double t, int32_t* labels);
+/* cdist(a, b, "cosine") (clustering.py:645-655): a[m][dim], b[k][dim] fp64 device -> d[m][k] fp64 device. */
+int b200_cdist_cosine(b200_ctx* ctx, const double* a, int32_t m, const double* b, int32_t k, int32_t dim, double* d,
+                      void* stream);
+/* VBx iterations (utils/vbx.py:98-136 via cluster_vbx :140-155): fea[n][D], phi[D], gamma[n][S] (in: initial
+ * responsibilities, out: final), pi[S] (out), all fp64 device; *iters (host) = iterations run. */
+int b200_vbx(b200_ctx* ctx, const double* fea, const double* phi, int32_t n, int32_t D, int32_t S, double Fa,
+             double Fb, int32_t max_iters, double epsilon, double* gamma, double* pi, int32_t* iters, void* stream);
+/* constrained_argmax / argmax (clustering.py:127-140, 658-665): soft[num_chunks][3][K] fp64 device ->
+ * hard[num_chunks][3] int8 device (-2 = unassigned). */
+int b200_assign(b200_ctx* ctx, const double* soft, int32_t num_chunks, int32_t num_clusters, int32_t constrained,
+                int8_t* hard, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

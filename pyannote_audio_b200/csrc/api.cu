@@ -1,6 +1,7 @@
 // extern "C" surface of libb200diar.so (declared in include/b200diar.h): context, weight ingestion
 // (BN folding, layout transforms, fp16 conversion on the host), and the forward entry points.
 #include "../../include/b200diar.h"
+#include "cluster.cuh"
 #include "common.cuh"
 #include "emb.cuh"
 #include "post.cuh"
@@ -569,6 +570,52 @@ int b200_clean_frames(b200_ctx* ctx, const uint8_t* seg, int32_t num_chunks, int
   DeviceGuard g(ctx->device);
   ctx->launches += 1;
   return clean_frames(seg, num_chunks, clean, active, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------------
+int b200_linkage_centroid(b200_ctx* ctx, const double* x, int32_t n, int32_t dim, int32_t normalize, double* Z,
+                          void* stream) {
+  B200_CHECK(ctx && x && Z && n >= 2 && dim >= 1, B200_ERR_INVALID, "linkage needs at least 2 observations");
+  B200_CHECK(n <= 32768, B200_ERR_INVALID, "linkage: n=%d too large", n);
+  DeviceGuard g(ctx->device);
+  int rc = ensure_ws(ctx, linkage_workspace_bytes(n, dim));
+  if (rc) return rc;
+  ctx->launches += 2 + (normalize ? 1 : 0);
+  return linkage_centroid(x, n, dim, normalize, Z, ctx->ws, (cudaStream_t)stream);
+}
+
+int b200_fcluster_distance(const double* Z, int32_t n, double t, int32_t* labels) {
+  B200_CHECK(Z && labels && n >= 1, B200_ERR_INVALID, "bad arguments");
+  return fcluster_distance(Z, n, t, labels);
+}
+
+int b200_cdist_cosine(b200_ctx* ctx, const double* a, int32_t m, const double* b, int32_t k, int32_t dim, double* d,
+                      void* stream) {
+  B200_CHECK(ctx && a && b && d && m >= 0 && k >= 1 && dim >= 1, B200_ERR_INVALID, "bad arguments");
+  if (m == 0) return B200_OK;
+  DeviceGuard g(ctx->device);
+  ctx->launches += 1;
+  return cdist_cosine(a, m, b, k, dim, d, (cudaStream_t)stream);
+}
+
+int b200_vbx(b200_ctx* ctx, const double* fea, const double* phi, int32_t n, int32_t D, int32_t S, double Fa,
+             double Fb, int32_t max_iters, double epsilon, double* gamma, double* pi, int32_t* iters, void* stream) {
+  B200_CHECK(ctx && fea && phi && gamma && pi && n >= 1 && D >= 1 && S >= 1 && max_iters >= 1, B200_ERR_INVALID,
+             "bad arguments");
+  DeviceGuard g(ctx->device);
+  int rc = ensure_ws(ctx, vbx_workspace_bytes(n, D, S));
+  if (rc) return rc;
+  ctx->launches += 1 + 3 * max_iters;
+  return vbx_run(fea, phi, n, D, S, Fa, Fb, max_iters, epsilon, gamma, pi, iters, ctx->ws, (cudaStream_t)stream);
+}
+
+int b200_assign(b200_ctx* ctx, const double* soft, int32_t num_chunks, int32_t num_clusters, int32_t constrained,
+                int8_t* hard, void* stream) {
+  B200_CHECK(ctx && soft && hard && num_chunks >= 0 && num_clusters >= 1, B200_ERR_INVALID, "bad arguments");
+  if (num_chunks == 0) return B200_OK;
+  DeviceGuard g(ctx->device);
+  ctx->launches += 1;
+  return assign_clusters(soft, num_chunks, num_clusters, constrained, (signed char*)hard, (cudaStream_t)stream);
 }
 
 }  // extern "C"
