@@ -46,6 +46,10 @@ int b200_ctx_destroy(b200_ctx* ctx);
 int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches claim) */
 int64_t b200_ctx_launch_count(const b200_ctx* ctx);
+/* with option "profile" = 1 the library brackets the ResNet trunk ("trunk": conv kernels) and the segmentation
+ * network ("seg") with CUDA events on the caller's stream; this returns and resets the accumulated device time
+ * and the number of units (segments / chunks) processed.  Synchronises the device. */
+int b200_ctx_timer(b200_ctx* ctx, const char* name, double* total_ms, int64_t* units);
 
 /* ---- weights: Model.from_pretrained state_dict (core/model.py:497-655) ------------------------------------ */
 

@@ -50,6 +50,7 @@ _PROTOS = {
     "b200_ctx_destroy": (C.c_int, [C.c_void_p]),
     "b200_ctx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "b200_ctx_launch_count": (C.c_int64, [C.c_void_p]),
+    "b200_ctx_timer": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "b200_seg_load": (C.c_int, [C.c_void_p, C.POINTER(SegWeights)]),
     "b200_emb_load": (C.c_int, [C.c_void_p, C.POINTER(EmbWeights)]),
     "b200_seg_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,

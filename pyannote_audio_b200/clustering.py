@@ -1,0 +1,292 @@
+"""Clustering stage (mirror of /root/reference/src/pyannote/audio/pipelines/clustering.py, core/plda.py, utils/vbx.py).
+
+Same classes / call signatures as the reference (``VBxClustering``, ``AgglomerativeClustering``, ``PLDA``); the
+arithmetic runs in fp64 on the device through libb200diar.so: clean-frame filter, centroid linkage, PLDA transform
+(plain fp64 matmuls), VBx iterations, cosine cdist and the constrained 3xK assignment.  Only the dendrogram cut
+(``fcluster``, a tree walk over (n-1) rows) and the rarely used KMeans fallback stay on the host.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import ops
+from .core import SlidingWindowFeature
+from .models import get_context
+
+
+class PLDA:
+    """core/plda.py:33-63 over utils/vbx.py:181-218.  The one-off setup (matrix inverses + generalised eigh) runs on
+    the host in float64 exactly like the reference; the per-file transform runs on the device."""
+
+    def __init__(self, transform_npz: Union[str, Path, dict], plda_npz: Union[str, Path, dict, None] = None,
+                 lda_dimension: int = 128):
+        from scipy.linalg import eigh
+
+        x = transform_npz if isinstance(transform_npz, dict) else np.load(transform_npz)
+        p = x if plda_npz is None else (plda_npz if isinstance(plda_npz, dict) else np.load(plda_npz))
+        self.mean1, self.mean2, self.lda = (np.asarray(x[k], dtype=np.float64) for k in ("mean1", "mean2", "lda"))
+        mu, tr, psi = (np.asarray(p[k], dtype=np.float64) for k in ("mu", "tr", "psi"))
+        W = np.linalg.inv(tr.T.dot(tr))
+        B = np.linalg.inv((tr.T / psi).dot(tr))
+        acvar, wccn = eigh(B, W)
+        self._plda_psi = acvar[::-1].copy()
+        self._plda_tr = wccn.T[::-1].copy()
+        self._plda_mu = mu
+        self.lda_dimension = lda_dimension
+        self._dev = {}
+
+    @property
+    def phi(self) -> np.ndarray:
+        return self._plda_psi[: self.lda_dimension]
+
+    def _consts(self, device):
+        key = str(device)
+        if key not in self._dev:
+            t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)  # noqa: E731
+            self._dev[key] = dict(mean1=t(self.mean1), mean2=t(self.mean2), lda=t(self.lda), mu=t(self._plda_mu),
+                                  trT=t(self._plda_tr.T[:, : self.lda_dimension]), phi=t(self.phi))
+        return self._dev[key]
+
+    def transform(self, x: torch.Tensor) -> torch.Tensor:
+        """(n, 256) float64 device tensor -> (n, lda_dimension) (vbx.py:211-217)."""
+        c = self._consts(x.device)
+        din, dout = c["lda"].shape
+        y = x - c["mean1"]
+        y = np.sqrt(din) * (y / torch.linalg.norm(y, dim=1, keepdim=True))
+        y = y @ c["lda"] - c["mean2"]
+        y = np.sqrt(dout) * (y / torch.linalg.norm(y, dim=1, keepdim=True))
+        return (y - c["mu"]) @ c["trT"]
+
+    def __call__(self, embeddings) -> np.ndarray:
+        if isinstance(embeddings, torch.Tensor):
+            return self.transform(embeddings.double())
+        dev = torch.device("cuda", torch.cuda.current_device())
+        return self.transform(torch.from_numpy(np.asarray(embeddings, dtype=np.float64)).to(dev)).cpu().numpy()
+
+
+def _seg_tensor(segmentations, ctx) -> torch.Tensor:
+    """(C,589,3) uint8 device tensor from a SlidingWindowFeature / ndarray / tensor of {0,1}."""
+    data = segmentations.data if isinstance(segmentations, SlidingWindowFeature) else segmentations
+    if isinstance(data, torch.Tensor):
+        return data.to(device=ctx.device, dtype=torch.uint8).contiguous()
+    return torch.from_numpy(np.nan_to_num(np.asarray(data), nan=0.0).astype(np.uint8)).to(ctx.device).contiguous()
+
+
+class BaseClustering:
+    def __init__(self, metric: str = "cosine", constrained_assignment: bool = False, device=None):
+        if metric != "cosine":
+            raise NotImplementedError("the device clustering path implements the cosine metric (community-1)")
+        self.metric = metric
+        self.constrained_assignment = constrained_assignment
+        self.device = device
+
+    def _ctx(self, like=None):
+        if isinstance(like, torch.Tensor) and like.is_cuda:
+            return get_context(like.device)
+        return get_context(self.device if self.device is not None else torch.device("cuda", torch.cuda.current_device()))
+
+    def set_num_clusters(self, num_embeddings: int, num_clusters=None, min_clusters=None, max_clusters=None):
+        min_clusters = num_clusters or min_clusters or 1
+        min_clusters = max(1, min(num_embeddings, min_clusters))
+        max_clusters = num_clusters or max_clusters or num_embeddings
+        max_clusters = max(1, min(num_embeddings, max_clusters))
+        if min_clusters > max_clusters:
+            raise ValueError(f"min_clusters must be smaller than (or equal to) max_clusters "
+                             f"(here: min_clusters={min_clusters:g} and max_clusters={max_clusters:g}).")
+        if min_clusters == max_clusters:
+            num_clusters = min_clusters
+        return num_clusters, min_clusters, max_clusters
+
+    def filter_embeddings(self, embeddings, segmentations, min_active_ratio: float = 0.2):
+        """clustering.py:77-125 -> (train (n,256) f64 device, chunk_idx, speaker_idx, active (C,3) bool device)."""
+        ctx = self._ctx(embeddings)
+        seg = _seg_tensor(segmentations, ctx)
+        emb = embeddings if isinstance(embeddings, torch.Tensor) else torch.from_numpy(np.asarray(embeddings))
+        emb = emb.to(ctx.device)
+        num_frames = seg.shape[1]
+        clean, active = ctx.clean_frames(seg)
+        keep = (clean.double() >= min_active_ratio * num_frames) & ~torch.isnan(emb).any(dim=2)
+        chunk_idx, speaker_idx = torch.nonzero(keep, as_tuple=True)
+        return emb[chunk_idx, speaker_idx].double(), chunk_idx, speaker_idx, active.bool()
+
+    def constrained_argmax(self, soft_clusters) -> np.ndarray:
+        ctx = self._ctx(soft_clusters)
+        soft = soft_clusters if isinstance(soft_clusters, torch.Tensor) else torch.from_numpy(soft_clusters)
+        soft = torch.nan_to_num(soft.to(ctx.device).double(), nan=float(torch.nan_to_num(soft, nan=np.inf).min()))
+        return ctx.assign(soft, constrained=True).cpu().numpy()
+
+    def _assign(self, ctx, emb64, centroids, active, constrained):
+        C = emb64.shape[0]
+        K = centroids.shape[0]
+        e2k = ctx.cdist_cosine(emb64.reshape(-1, emb64.shape[-1]), centroids).reshape(C, ops.SPEAKERS, K)
+        soft = 2 - e2k
+        if constrained:
+            const = soft.min() - 1.0
+            soft = torch.where(active[:, :, None], soft, const)
+        hard = ctx.assign(soft, constrained=constrained)
+        return hard, soft
+
+
+class VBxClustering(BaseClustering):
+    expects_num_clusters: bool = False
+
+    def __init__(self, plda: PLDA, metric: str = "cosine", constrained_assignment: bool = True, device=None):
+        super().__init__(metric=metric, constrained_assignment=constrained_assignment, device=device)
+        self.plda = plda
+        self.threshold, self.Fa, self.Fb = 0.6, 0.07, 0.8
+
+    def instantiate(self, params: dict):
+        for k in ("threshold", "Fa", "Fb"):
+            if k in params:
+                setattr(self, k, float(params[k]))
+        return self
+
+    def __call__(self, embeddings, segmentations=None, num_clusters=None, min_clusters=None, max_clusters=None,
+                 return_debug: bool = False, **kwargs):
+        """clustering.py:572-669.  Returns (hard_clusters (C,3) int8, soft_clusters (C,3,K) f64, centroids (K,256))."""
+        constrained = self.constrained_assignment
+        min_clusters = min_clusters if min_clusters is not None else 1
+        max_clusters = max_clusters if max_clusters is not None else np.inf
+        ctx = self._ctx(embeddings)
+        train, _, _, active = self.filter_embeddings(embeddings, segmentations)
+        emb = embeddings if isinstance(embeddings, torch.Tensor) else torch.from_numpy(np.asarray(embeddings))
+        emb64 = emb.to(ctx.device).double()
+        num_chunks, num_speakers, dimension = emb64.shape
+        if train.shape[0] < 2:
+            hard = np.zeros((num_chunks, num_speakers), dtype=np.int8)
+            soft = np.ones((num_chunks, num_speakers, 1))
+            centroids = train.mean(dim=0, keepdim=True).cpu().numpy()
+            return hard, soft, centroids
+        # AHC (centroid linkage on unit vectors) on the device, dendrogram cut on the host
+        Z = ctx.linkage_centroid(train, normalize=True).cpu().numpy()
+        ahc = ops.fcluster_distance(Z, self.threshold) - 1
+        _, ahc = np.unique(ahc, return_inverse=True)
+        # VBx
+        fea = self.plda.transform(train)
+        S = int(ahc.max()) + 1
+        qinit = torch.zeros((len(ahc), S), dtype=torch.float64, device=ctx.device)
+        qinit[torch.arange(len(ahc), device=ctx.device), torch.from_numpy(ahc).to(ctx.device)] = 1.0
+        qinit = torch.softmax(qinit * 7.0, dim=1)
+        q, sp, iters = ctx.vbx(fea, self.plda._consts(ctx.device)["phi"], qinit, self.Fa, self.Fb, max_iters=20)
+        W = q[:, sp > 1e-7]
+        centroids = (W.T @ train) / W.sum(0, keepdim=True).T
+        auto_num = centroids.shape[0]
+        if auto_num < min_clusters:
+            num_clusters = min_clusters
+        elif auto_num > max_clusters:
+            num_clusters = max_clusters
+        if num_clusters and num_clusters != auto_num:
+            from sklearn.cluster import KMeans
+
+            constrained = False
+            normed = (train / torch.linalg.norm(train, dim=1, keepdim=True)).cpu().numpy()
+            km = KMeans(n_clusters=int(num_clusters), n_init=3, random_state=42, copy_x=False).fit_predict(normed)
+            tr = train.cpu().numpy()
+            centroids = torch.from_numpy(np.vstack([np.mean(tr[km == k], axis=0) for k in range(int(num_clusters))]))
+            centroids = centroids.to(ctx.device)
+        hard, soft = self._assign(ctx, emb64, centroids.contiguous(), active, constrained)
+        out = (hard.cpu().numpy().reshape(num_chunks, num_speakers), soft.cpu().numpy(), centroids.cpu().numpy())
+        if return_debug:
+            return out + (dict(ahc=ahc, dendrogram=Z, q=q.cpu().numpy(), sp=sp.cpu().numpy(), iters=iters,
+                               fea=fea.cpu().numpy(), train=train.cpu().numpy(), active=active.cpu().numpy()),)
+        return out
+
+
+class AgglomerativeClustering(BaseClustering):
+    """Legacy (3.1) clustering, clustering.py:293-480.  ``method="centroid"`` runs on the device."""
+
+    expects_num_clusters: bool = False
+
+    def __init__(self, metric: str = "cosine", constrained_assignment: bool = False, device=None):
+        super().__init__(metric=metric, constrained_assignment=constrained_assignment, device=device)
+        self.method, self.threshold, self.min_cluster_size = "centroid", 0.7, 12
+
+    def instantiate(self, params: dict):
+        for k in ("method", "threshold", "min_cluster_size"):
+            if k in params:
+                setattr(self, k, params[k])
+        return self
+
+    def cluster(self, embeddings: np.ndarray, min_clusters: int = 1, max_clusters: Optional[int] = None,
+                num_clusters: Optional[int] = None) -> np.ndarray:
+        if self.method != "centroid":
+            raise NotImplementedError("device linkage implements method='centroid' (the pyannote default)")
+        ctx = self._ctx()
+        embeddings = np.array(embeddings, dtype=np.float64)
+        num_embeddings, _ = embeddings.shape
+        max_clusters = max_clusters if max_clusters is not None else num_embeddings
+        min_cluster_size = min(self.min_cluster_size, max(1, round(0.1 * num_embeddings)))
+        if num_embeddings == 1:
+            return np.zeros((1,), dtype=np.uint8)
+        x = torch.from_numpy(embeddings).to(ctx.device)
+        dendrogram = ctx.linkage_centroid(x, normalize=True).cpu().numpy()
+        with np.errstate(divide="ignore", invalid="ignore"):
+            embeddings /= np.linalg.norm(embeddings, axis=-1, keepdims=True)
+        clusters = ops.fcluster_distance(dendrogram, self.threshold) - 1
+        uniq, counts = np.unique(clusters, return_counts=True)
+        large = uniq[counts >= min_cluster_size]
+        num_large = len(large)
+        if num_large < min_clusters:
+            num_clusters = min_clusters
+        elif num_large > max_clusters:
+            num_clusters = max_clusters
+        if num_clusters is not None and num_large != num_clusters:
+            _d = np.copy(dendrogram)
+            _d[:, 2] = np.arange(num_embeddings - 1)
+            best_iteration, best_num_large = num_embeddings - 1, 1
+            for iteration in np.argsort(np.abs(dendrogram[:, 2] - self.threshold)):
+                if _d[iteration, 3] < min_cluster_size:
+                    continue
+                clusters = ops.fcluster_distance(_d, iteration) - 1
+                uniq, counts = np.unique(clusters, return_counts=True)
+                large = uniq[counts >= min_cluster_size]
+                num_large = len(large)
+                if abs(num_large - num_clusters) < abs(best_num_large - num_clusters):
+                    best_iteration, best_num_large = iteration, num_large
+                if num_large == num_clusters:
+                    break
+            if best_num_large != num_clusters:
+                clusters = ops.fcluster_distance(_d, best_iteration) - 1
+                uniq, counts = np.unique(clusters, return_counts=True)
+                large = uniq[counts >= min_cluster_size]
+                num_large = len(large)
+        if num_large == 0:
+            clusters[:] = 0
+            return clusters
+        small = uniq[counts < min_cluster_size]
+        if len(small) == 0:
+            return clusters
+        large_c = np.vstack([np.mean(embeddings[clusters == k], axis=0) for k in large])
+        small_c = np.vstack([np.mean(embeddings[clusters == k], axis=0) for k in small])
+        d = ctx.cdist_cosine(torch.from_numpy(large_c).to(ctx.device), torch.from_numpy(small_c).to(ctx.device))
+        for sk, lk in enumerate(torch.argmin(d, dim=0).cpu().numpy()):
+            clusters[clusters == small[sk]] = large[lk]
+        _, clusters = np.unique(clusters, return_inverse=True)
+        return clusters
+
+    def __call__(self, embeddings, segmentations=None, num_clusters=None, min_clusters=None, max_clusters=None,
+                 **kwargs):
+        """BaseClustering.__call__ (clustering.py:214-289) + assign_embeddings (:142-212)."""
+        ctx = self._ctx(embeddings)
+        train, chunk_idx, speaker_idx, active = self.filter_embeddings(embeddings, segmentations)
+        emb = embeddings if isinstance(embeddings, torch.Tensor) else torch.from_numpy(np.asarray(embeddings))
+        emb64 = emb.to(ctx.device).double()
+        num_chunks, num_speakers, _ = emb64.shape
+        num_embeddings = train.shape[0]
+        num_clusters, min_clusters, max_clusters = self.set_num_clusters(num_embeddings, num_clusters, min_clusters,
+                                                                         max_clusters)
+        if max_clusters < 2:
+            hard = np.zeros((num_chunks, num_speakers), dtype=np.int8)
+            soft = np.ones((num_chunks, num_speakers, 1))
+            return hard, soft, train.mean(dim=0, keepdim=True).cpu().numpy()
+        train_clusters = self.cluster(train.cpu().numpy(), min_clusters=min_clusters, max_clusters=max_clusters,
+                                      num_clusters=num_clusters)
+        K = int(train_clusters.max()) + 1
+        lab = torch.from_numpy(train_clusters.astype(np.int64)).to(ctx.device)
+        centroids = torch.stack([train[lab == k].mean(dim=0) for k in range(K)])
+        hard, soft = self._assign(ctx, emb64, centroids.contiguous(), active, self.constrained_assignment)
+        return hard.cpu().numpy(), soft.cpu().numpy(), centroids.cpu().numpy()

@@ -181,7 +181,7 @@ class Annotation:
 
     def _sort(self):
         if not self._sorted:
-            self._tracks.sort(key=lambda r: (r[0].start, r[0].end, str(r[1])))
+            self._tracks.sort(key=lambda r: (r[0].start, r[0].end))   # stable: ties keep insertion (track) order
             self._sorted = True
 
     def itertracks(self, yield_label: bool = False):

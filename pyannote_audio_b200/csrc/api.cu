@@ -26,6 +26,11 @@ struct b200_ctx {
   long long* d_off = nullptr;
   int* d_valid = nullptr;
   int meta_cap = 0;
+  // optional CUDA-event timers around the dominant kernels (bench.py's live roofline measurement)
+  int profile = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trunk_events, seg_events;
+  std::vector<cudaEvent_t> event_pool;
+  int64_t trunk_segments = 0, seg_chunks = 0;
 };
 
 namespace {
@@ -45,6 +50,31 @@ int upload(b200_ctx* ctx, const std::vector<T>& h, T** out) {
   *out = reinterpret_cast<T*>(p);
   return B200_OK;
 }
+
+cudaEvent_t take_event(b200_ctx* ctx) {
+  if (!ctx->event_pool.empty()) {
+    cudaEvent_t e = ctx->event_pool.back();
+    ctx->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct ScopedTimer {
+  b200_ctx* ctx;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* sink;
+  cudaStream_t st;
+  cudaEvent_t a = nullptr, b = nullptr;
+  ScopedTimer(b200_ctx* c, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* s, cudaStream_t stream)
+      : ctx(c), sink(s), st(stream) {
+    if (ctx->profile) { a = take_event(ctx); b = take_event(ctx); cudaEventRecord(a, st); }
+  }
+  ~ScopedTimer() {
+    if (ctx->profile) { cudaEventRecord(b, st); sink->push_back({a, b}); }
+  }
+};
 
 int ensure_ws(b200_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->ws_cap) return B200_OK;
@@ -179,6 +209,7 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value) {
   if (k == "conv_impl") ctx->conv_impl = (int)value;
   else if (k == "seg_max_batch") ctx->seg_max_batch = (int)value;
   else if (k == "emb_max_batch") ctx->emb_max_batch = (int)value;
+  else if (k == "profile") ctx->profile = (int)value;
   else B200_CHECK(false, B200_ERR_INVALID, "unknown option '%s'", key);
   B200_CHECK(ctx->seg_max_batch >= 1 && ctx->emb_max_batch >= 1 && ctx->conv_impl >= 0 && ctx->conv_impl <= 2,
              B200_ERR_INVALID, "option '%s' value %lld out of range", key, (long long)value);
@@ -186,6 +217,31 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value) {
 }
 
 int64_t b200_ctx_launch_count(const b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int b200_ctx_timer(b200_ctx* ctx, const char* name, double* total_ms, int64_t* units) {
+  B200_CHECK(ctx && name && total_ms && units, B200_ERR_INVALID, "bad arguments");
+  DeviceGuard g(ctx->device);
+  std::string k(name);
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* v = nullptr;
+  int64_t* u = nullptr;
+  if (k == "trunk") { v = &ctx->trunk_events; u = &ctx->trunk_segments; }
+  else if (k == "seg") { v = &ctx->seg_events; u = &ctx->seg_chunks; }
+  else B200_CHECK(false, B200_ERR_INVALID, "unknown timer '%s'", name);
+  B200_CUDA_OK(cudaDeviceSynchronize());
+  double ms = 0.0;
+  for (auto& pr : *v) {
+    float t = 0.f;
+    B200_CUDA_OK(cudaEventElapsedTime(&t, pr.first, pr.second));
+    ms += t;
+    ctx->event_pool.push_back(pr.first);
+    ctx->event_pool.push_back(pr.second);
+  }
+  v->clear();
+  *total_ms = ms;
+  *units = *u;
+  *u = 0;
+  return B200_OK;
+}
 
 // ------------------------------------------------------------------------------------------------------
 int b200_seg_load(b200_ctx* ctx, const b200_seg_weights* w) {
@@ -336,6 +392,8 @@ static int seg_run(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, co
   void* region = reinterpret_cast<char*>(ctx->ws) + x0_bytes;
   for (int c0 = 0; c0 < n; c0 += nbmax) {
     const int nb = (n - c0) < nbmax ? (n - c0) : nbmax;
+    ScopedTimer timer(ctx, &ctx->seg_events, st);
+    if (ctx->profile) ctx->seg_chunks += nb;
     float* x0_dst = sinc_out ? sinc_out + (size_t)c0 * kFrames * 64 : x0;
     if ((rc = sincnet_forward(ctx->seg, wav, ctx->d_off + c0, ctx->d_valid + c0, nb, region, x0_dst, st))) return rc;
     ctx->launches += 8;
@@ -456,7 +514,11 @@ int b200_emb_forward(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, 
     const int nb = (num_chunks - c0) < nbmax ? (num_chunks - c0) : nbmax;
     if ((rc = fbank_forward(ctx->emb, wav, ctx->d_off + c0, ctx->d_valid + c0, nb, w.fbank, w.fmean, st))) return rc;
     ctx->launches += 2;
-    if ((rc = trunk_run(ctx, w, nb, st))) return rc;
+    {
+      ScopedTimer timer(ctx, &ctx->trunk_events, st);
+      if ((rc = trunk_run(ctx, w, nb, st))) return rc;
+    }
+    if (ctx->profile) ctx->trunk_segments += nb;
     if ((rc = stats_pool_forward(w.A, masks + (size_t)c0 * kSpeakers * kFrames, w.stats, nb, st))) return rc;
     if ((rc = sgemm_nt(w.stats, 2 * kStatsDim, ctx->emb.seg1_w, 2 * kStatsDim, emb + (size_t)c0 * kSpeakers * kEmbDim,
                        kEmbDim, ctx->emb.seg1_b, nb * kSpeakers, kEmbDim, 2 * kStatsDim, 0, st)))

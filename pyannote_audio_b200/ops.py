@@ -95,6 +95,12 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.b200_ctx_launch_count(self._h))
 
+    def timer(self, name: str):
+        """(accumulated device ms, units) of a profiled region ("trunk" | "seg"); needs set_option("profile", 1)."""
+        ms, units = C.c_double(0.0), C.c_int64(0)
+        _lib.check(self.lib.b200_ctx_timer(self._h, name.encode(), C.byref(ms), C.byref(units)))
+        return float(ms.value), int(units.value)
+
     # ---- weights ---------------------------------------------------------------------------------
     def load_segmentation(self, sd: Mapping[str, torch.Tensor]):
         keep = []

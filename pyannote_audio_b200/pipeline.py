@@ -1,0 +1,434 @@
+"""Speaker diarization pipeline (mirror of /root/reference/src/pyannote/audio/pipelines/speaker_diarization.py).
+
+Same constructor arguments, ``apply`` signature, hook protocol and ``DiarizeOutput`` as the reference's
+``SpeakerDiarization``; plus the reference's own optional extension point ``apply_batch(files)``
+(core/pipeline.py:497-508) which is where multi-file batching and multi-GPU sharding plug in.
+
+Data flow per batch of files (everything between the H2D of the waveforms and the D2H of the discrete diarization
+stays on the device):
+  waveforms --H2D--> [PyanNet sliding window] -> powerset classes (C,589) u8 -> multilabel (C,589,3) u8
+     -> speaker count (F,) u8 -> masks (C,3,589) -> [WeSpeaker trunk once per chunk + 3 masked poolings] -> (C,3,256)
+     -> [filter -> centroid linkage -> (host: dendrogram cut) -> PLDA -> VBx -> cosine cdist -> 3xK assignment]
+     -> [clustered overlap-add + top-count selection] -> discrete diarization (F,K) u8 --D2H--> run-length -> Annotation
+"""
+from __future__ import annotations
+
+import math
+import textwrap
+import warnings
+from dataclasses import dataclass
+from typing import Any, Callable, Iterator, List, Mapping, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import ops
+from .audio import Audio, AudioFile
+from .clustering import PLDA, AgglomerativeClustering, VBxClustering
+from .core import Annotation, Segment, SlidingWindow, SlidingWindowFeature
+from .inference import Inference, chunk_layout
+from .models import PyanNet, WeSpeakerResNet34, get_context
+
+
+def set_num_speakers(num_speakers=None, min_speakers=None, max_speakers=None):
+    """pipelines/utils/diarization.py:34-69."""
+    min_speakers = num_speakers or min_speakers or 1
+    max_speakers = num_speakers or max_speakers or np.inf
+    if min_speakers > max_speakers:
+        raise ValueError(f"min_speakers must be smaller than (or equal to) max_speakers "
+                         f"(here: min_speakers={min_speakers:g} and max_speakers={max_speakers:g}).")
+    if min_speakers == max_speakers:
+        num_speakers = min_speakers
+    return num_speakers, min_speakers, max_speakers
+
+
+@dataclass
+class DiarizeOutput:
+    speaker_diarization: Annotation
+    exclusive_speaker_diarization: Annotation
+    speaker_embeddings: Optional[np.ndarray] = None
+
+    def serialize(self) -> dict:
+        def rows(a):
+            return [{"start": round(s.start, 3), "end": round(s.end, 3), "speaker": lab}
+                    for s, _, lab in a.itertracks(yield_label=True)]
+
+        return {"diarization": rows(self.speaker_diarization),
+                "exclusive_diarization": rows(self.exclusive_speaker_diarization)}
+
+
+class PretrainedSpeakerEmbedding:
+    """pipelines/speaker_verification.py:622-716 (PyannoteAudioPretrainedSpeakerEmbedding) over the CUDA model."""
+
+    def __init__(self, embedding: WeSpeakerResNet34, device: Optional[torch.device] = None):
+        self.embedding = embedding
+        self.model_ = embedding
+        self.model_.eval()
+        self.device = device or self.model_.device
+        if self.device.type == "cuda":
+            self.model_.to(self.device)
+
+    def to(self, device: torch.device):
+        if not isinstance(device, torch.device):
+            raise TypeError(f"`device` must be an instance of `torch.device`, got `{type(device).__name__}`")
+        self.model_.to(device)
+        self.device = device
+        return self
+
+    @property
+    def sample_rate(self) -> int:
+        return self.model_.audio.sample_rate
+
+    @property
+    def dimension(self) -> int:
+        return self.model_.dimension
+
+    @property
+    def metric(self) -> str:
+        return "cosine"
+
+    @property
+    def min_num_samples(self) -> int:
+        # smallest input for which kaldi.fbank yields a frame (speaker_verification.py:688-702 finds it by
+        # bisection on exceptions; with a 400-sample analysis window the bisection converges to 400)
+        return 400
+
+    def __call__(self, waveforms: torch.Tensor, masks: Optional[torch.Tensor] = None) -> np.ndarray:
+        return self.model_(waveforms, weights=masks).cpu().numpy()
+
+
+def binarize_frames(discrete: np.ndarray, frames: SlidingWindow, min_duration_off: float = 0.0,
+                    uri: Optional[str] = None) -> Tuple[Annotation, np.ndarray]:
+    """to_annotation (diarization.py:188-218) / Binarize(onset=offset=0.5) (utils/signal.py:254-318), vectorised.
+
+    Returns the Annotation (integer labels) and the (n_segments, 3) int array of (start_frame, end_frame, label).
+    """
+    n, K = discrete.shape
+    ann = Annotation(uri=uri)
+    rows = []
+    if n < 2:
+        return ann, np.zeros((0, 3), dtype=np.int64)
+    act = discrete > 0
+    pad = np.zeros((1, K), dtype=bool)
+    d = np.diff(np.concatenate([pad, act, pad]).astype(np.int8), axis=0)      # (n+1, K)
+    for k in range(K):
+        on = np.nonzero(d[:, k] == 1)[0]
+        off = np.nonzero(d[:, k] == -1)[0]
+        off = np.minimum(off, n - 1)           # still active at the end -> region closes at the last frame
+        for a, b in zip(on, off):
+            rows.append((int(a), int(b), k))
+    rows.sort()
+    track = 0
+    for a, b, k in rows:
+        # timestamps are frames[i].middle, computed like pyannote.core.Segment.middle: 0.5 * (start + end)
+        ann.add(Segment(frames[a].middle, frames[b].middle), track, k)
+        track += 1
+    if min_duration_off > 0.0:
+        ann = ann.support(collar=min_duration_off)
+    return ann, np.asarray(rows, dtype=np.int64).reshape(-1, 3)
+
+
+class SpeakerDiarization:
+    def __init__(self, legacy: bool = False, segmentation: Union[PyanNet, Mapping, None] = None,
+                 segmentation_step: float = 0.1, embedding: Union[WeSpeakerResNet34, Mapping, None] = None,
+                 embedding_exclude_overlap: bool = False, plda: Union[PLDA, Mapping, None] = None,
+                 clustering: str = "VBxClustering", embedding_batch_size: int = 1, segmentation_batch_size: int = 1,
+                 der_variant: Optional[dict] = None, token=None, cache_dir=None,
+                 device: Optional[torch.device] = None):
+        self.legacy = legacy
+        device = device or torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+        self.device = device
+        if isinstance(segmentation, Mapping):
+            model = PyanNet()
+            model.load_state_dict(segmentation)
+            segmentation = model
+        if isinstance(embedding, Mapping):
+            model = WeSpeakerResNet34()
+            model.load_state_dict(embedding)
+            embedding = model
+        if not isinstance(segmentation, PyanNet) or not isinstance(embedding, WeSpeakerResNet34):
+            raise ValueError("`segmentation` / `embedding` must be PyanNet / WeSpeakerResNet34 instances or their "
+                             "state dicts (no network access here: pretrained hub checkpoints cannot be fetched)")
+        self.segmentation_model = segmentation
+        self.segmentation_step = segmentation_step
+        self.embedding = embedding
+        self.embedding_batch_size = embedding_batch_size
+        self.embedding_exclude_overlap = embedding_exclude_overlap
+        self.klustering = clustering
+        self.der_variant = der_variant or {"collar": 0.0, "skip_overlap": False}
+        self._plda = PLDA(plda) if isinstance(plda, Mapping) else plda
+        segmentation.to(device)
+        embedding.to(device)
+        duration = segmentation.specifications.duration
+        self._segmentation = Inference(segmentation, duration=duration, step=self.segmentation_step * duration,
+                                       skip_aggregation=True, batch_size=segmentation_batch_size)
+        self._embedding = PretrainedSpeakerEmbedding(embedding, device=device)
+        self._audio = Audio(sample_rate=self._embedding.sample_rate, mono="downmix")
+        if clustering == "VBxClustering":
+            if self._plda is None:
+                raise ValueError("VBxClustering needs a PLDA model")
+            self.clustering = VBxClustering(self._plda, metric=self._embedding.metric, device=device)
+        elif clustering == "AgglomerativeClustering":
+            self.clustering = AgglomerativeClustering(metric=self._embedding.metric, device=device)
+        else:
+            raise ValueError("clustering must be one of [AgglomerativeClustering, VBxClustering]")
+        self._expects_num_speakers = self.clustering.expects_num_clusters
+        self.min_duration_off = 0.0
+        self.d2h_bytes = 0        # bytes copied device -> host by the last apply/apply_batch (bench.py reports it)
+        self.instantiate(self.default_parameters())
+
+    # ---- pyannote.pipeline-style parameter plumbing -------------------------------------------------------
+    @property
+    def segmentation_batch_size(self) -> int:
+        return self._segmentation.batch_size
+
+    @segmentation_batch_size.setter
+    def segmentation_batch_size(self, batch_size: int):
+        self._segmentation.batch_size = batch_size
+
+    def default_parameters(self):
+        if self.klustering == "VBxClustering":
+            return {"segmentation": {"min_duration_off": 0.0}, "clustering": {"threshold": 0.6, "Fa": 0.07, "Fb": 0.8}}
+        return {"segmentation": {"min_duration_off": 0.0},
+                "clustering": {"method": "centroid", "min_cluster_size": 12, "threshold": 0.7045654963945799}}
+
+    def instantiate(self, params: dict):
+        self.min_duration_off = float(params.get("segmentation", {}).get("min_duration_off", 0.0))
+        self.clustering.instantiate(params.get("clustering", {}))
+        return self
+
+    def to(self, device: torch.device):
+        if not isinstance(device, torch.device):
+            raise TypeError(f"`device` must be an instance of `torch.device`, got `{type(device).__name__}`")
+        self._segmentation.to(device)
+        self._embedding.to(device)
+        self.clustering.device = device
+        self.device = device
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", device if isinstance(device, int) else torch.cuda.current_device()))
+
+    def classes(self):
+        speaker = 0
+        while True:
+            yield f"SPEAKER_{speaker:02d}"
+            speaker += 1
+
+    @staticmethod
+    def setup_hook(file, hook: Optional[Callable] = None) -> Callable:
+        def noop(*args, **kwargs):
+            return
+
+        return (lambda *a, **k: hook(*a, file=file, **k)) if hook is not None else noop
+
+    # ---- stages ---------------------------------------------------------------------------------------------
+    def _frames(self) -> SlidingWindow:
+        return self._segmentation.model.receptive_field
+
+    def _grid(self, num_chunks: int):
+        """Global frame grid of a file: per-chunk start frames and total frame count (inference.py:532-571, 596)."""
+        frames = self._frames()
+        duration, step = self._segmentation.duration, self._segmentation.step
+        fr = SlidingWindow(start=0.0, duration=frames.duration, step=frames.step)
+        sf = fr.closest_frames(np.arange(num_chunks) * step + 0.5 * fr.duration).astype(np.int32)
+        num_frames = fr.closest_frame(0.0 + duration + (num_chunks - 1) * step + 0.5 * fr.duration) + 1
+        return sf, int(num_frames), fr
+
+    def get_segmentations(self, file, hook=None) -> SlidingWindowFeature:
+        if hook is not None:
+            import functools
+
+            hook = functools.partial(hook, "segmentation", None)
+        return self._segmentation(file, hook=hook)
+
+    def speaker_count(self, binarized: SlidingWindowFeature, frames: SlidingWindow,
+                      warm_up: Tuple[float, float] = (0.0, 0.0)) -> SlidingWindowFeature:
+        """diarization.py:150-185 on the device (warm_up must be (0, 0), as the pipeline calls it)."""
+        if tuple(warm_up) != (0.0, 0.0):
+            raise NotImplementedError("device speaker counting implements warm_up=(0.0, 0.0)")
+        ctx = get_context(self.device)
+        seg = torch.from_numpy(np.nan_to_num(binarized.data).astype(np.uint8)).to(ctx.device)
+        sf, F, fr = self._grid(seg.shape[0])
+        count = ctx.speaker_count(seg, sf, F).cpu().numpy()[:, None]
+        return SlidingWindowFeature(count, fr)
+
+    def _masks(self, seg: torch.Tensor) -> torch.Tensor:
+        """(C,589,3) u8 -> StatsPool masks (C,3,589) u8 (speaker_diarization.py:375-423)."""
+        if self.embedding_exclude_overlap:
+            num_frames = seg.shape[1]
+            num_samples = self._segmentation.duration * self._embedding.sample_rate
+            min_num_frames = math.ceil(num_frames * self._embedding.min_num_samples / num_samples)
+            clean = seg * (seg.sum(dim=2, keepdim=True) < 2).to(seg.dtype)
+            use_clean = clean.sum(dim=1, keepdim=True) > min_num_frames
+            seg = torch.where(use_clean, clean, seg)
+        return seg.permute(0, 2, 1).contiguous()
+
+    def get_embeddings(self, file, binary_segmentations: SlidingWindowFeature, exclude_overlap: bool = False,
+                       hook: Optional[Callable] = None) -> np.ndarray:
+        """(C,3,256) float32 embeddings; reference loop speaker_diarization.py:332-478."""
+        ctx = get_context(self.device)
+        waveform, sr = self._audio(file)
+        seg = torch.from_numpy(np.nan_to_num(binary_segmentations.data).astype(np.uint8)).to(ctx.device)
+        off, valid, _, _ = chunk_layout(waveform.shape[1], ops.CHUNK, round(self._segmentation.step * sr))
+        wav_dev = torch.zeros(int(off[-1]) + ops.CHUNK, dtype=torch.float32, device=ctx.device)
+        wav_dev[: waveform.shape[1]] = waveform[0].to(ctx.device)
+        prev = self.embedding_exclude_overlap
+        self.embedding_exclude_overlap = exclude_overlap
+        try:
+            emb = self.embedding.forward_chunks(wav_dev, off, valid, self._masks(seg))
+        finally:
+            self.embedding_exclude_overlap = prev
+        if hook is not None:
+            hook("embeddings", None, total=1, completed=1)
+        return emb.cpu().numpy()
+
+    def reconstruct(self, segmentations: SlidingWindowFeature, hard_clusters: np.ndarray,
+                    count: SlidingWindowFeature) -> SlidingWindowFeature:
+        """speaker_diarization.py:480-528 + to_diarization (diarization.py:221-268) on the device."""
+        ctx = get_context(self.device)
+        seg = torch.from_numpy(np.nan_to_num(segmentations.data).astype(np.uint8)).to(ctx.device)
+        sf, F, fr = self._grid(seg.shape[0])
+        cnt = torch.from_numpy(np.asarray(count.data).reshape(-1).astype(np.uint8)).to(ctx.device)
+        K = int(np.max(hard_clusters)) + 1
+        Kout = max(K, int(cnt.max().item()), 1)
+        d = ctx.reconstruct(seg, hard_clusters, sf, F, K, cnt, Kout)
+        return SlidingWindowFeature(d.cpu().numpy().astype(np.float64), fr)
+
+    def to_annotation(self, discrete: SlidingWindowFeature, min_duration_on: float = 0.0,
+                      min_duration_off: float = 0.0) -> Annotation:
+        ann, _ = binarize_frames(np.asarray(discrete.data), discrete.sliding_window, min_duration_off)
+        return ann
+
+    # ---- apply ---------------------------------------------------------------------------------------------------
+    def apply(self, file: AudioFile, num_speakers: Optional[int] = None, min_speakers: Optional[int] = None,
+              max_speakers: Optional[int] = None, hook: Optional[Callable] = None, **kwargs):
+        if len(kwargs) > 0:
+            warnings.warn(f"Ignoring unexpected keyword arguments: {', '.join(list(kwargs.keys()))}")
+        for _, output in self.apply_batch([file], num_speakers=num_speakers, min_speakers=min_speakers,
+                                          max_speakers=max_speakers, hook=hook):
+            return output
+
+    def __call__(self, file, **kwargs):
+        if isinstance(file, (list, tuple)):
+            return [out for _, out in self.apply_batch(list(file), **kwargs)]
+        return self.apply(file, **kwargs)
+
+    def apply_batch(self, files: Sequence[AudioFile], num_speakers: Optional[int] = None,
+                    min_speakers: Optional[int] = None, max_speakers: Optional[int] = None,
+                    hook: Optional[Callable] = None, progress=None,
+                    return_artifacts: bool = False) -> Iterator[Tuple[Mapping, Any]]:
+        """Batched entry point: segmentation and embedding of ALL files run as two device passes over one resident
+        buffer; clustering / reconstruction then run per file."""
+        resident = self.upload(files)
+        yield from self.run_resident(resident, num_speakers=num_speakers, min_speakers=min_speakers,
+                                     max_speakers=max_speakers, hook=hook, return_artifacts=return_artifacts)
+
+    def upload(self, files: Sequence[AudioFile]) -> dict:
+        """H2D: one device buffer for all files, every chunk window addressable (zero padded tails)."""
+        ctx = get_context(self.device)
+        files = [self._audio.validate_file(f) for f in files]
+        step_size = round(self._segmentation.step * self._embedding.sample_rate)
+        wavs, layouts, base = [], [], 0
+        for f in files:
+            w, sr = self._audio(f)
+            off, valid, _, _ = chunk_layout(w.shape[1], ops.CHUNK, step_size)
+            layouts.append((base, off, valid, w.shape[1]))
+            wavs.append(w)
+            base += int(off[-1]) + ops.CHUNK
+        wav_dev = torch.zeros(base, dtype=torch.float32, device=ctx.device)
+        for (b0, off, valid, T), w in zip(layouts, wavs):
+            wav_dev[b0: b0 + T].copy_(w[0], non_blocking=True)
+        return dict(files=files, wav=wav_dev, layouts=layouts,
+                    off=np.concatenate([b0 + off for b0, off, _, _ in layouts]),
+                    valid=np.concatenate([valid for _, _, valid, _ in layouts]),
+                    bounds=np.cumsum([0] + [len(l[1]) for l in layouts]))
+
+    def run_resident(self, resident: dict, num_speakers: Optional[int] = None, min_speakers: Optional[int] = None,
+                     max_speakers: Optional[int] = None, hook: Optional[Callable] = None,
+                     return_artifacts: bool = False) -> Iterator[Tuple[Mapping, Any]]:
+        num_speakers, min_speakers, max_speakers = set_num_speakers(num_speakers, min_speakers, max_speakers)
+        if self._expects_num_speakers and num_speakers is None:
+            raise ValueError(f"num_speakers must be provided when using {self.klustering} clustering")
+        ctx = get_context(self.device)
+        wav_dev, all_off, all_valid, bounds = resident["wav"], resident["off"], resident["valid"], resident["bounds"]
+        # ---- device passes over all files at once ------------------------------------------------------------
+        cls = self._segmentation.model.forward_chunks(wav_dev, all_off, all_valid)        # (C,589) u8
+        seg = ctx.powerset_to_multilabel(cls)                                              # (C,589,3) u8
+        emb = self.embedding.forward_chunks(wav_dev, all_off, all_valid, self._masks(seg))  # (C,3,256) f32
+        # ---- per-file clustering + reconstruction ------------------------------------------------------------
+        for fi, file in enumerate(resident["files"]):
+            h = self.setup_hook(file, hook)
+            c0, c1 = int(bounds[fi]), int(bounds[fi + 1])
+            out = self._finish_file(ctx, file, seg[c0:c1], emb[c0:c1], num_speakers, min_speakers, max_speakers, h,
+                                    return_artifacts)
+            yield file, out
+
+    def _finish_file(self, ctx, file, seg, emb, num_speakers, min_speakers, max_speakers, hook, return_artifacts):
+        uri = file.get("uri", None)
+        C = seg.shape[0]
+        sf, F, fr = self._grid(C)
+        chunks_sw = SlidingWindow(start=0.0, duration=self._segmentation.duration, step=self._segmentation.step)
+        hook("segmentation", _Lazy(lambda: SlidingWindowFeature(seg.cpu().numpy().astype(np.float32), chunks_sw)))
+        count = ctx.speaker_count(seg, sf, F)
+        hook("speaker_counting", _Lazy(lambda: SlidingWindowFeature(count.cpu().numpy()[:, None], fr)))
+        artifacts = dict(segmentations=seg, count=count, embeddings=emb) if return_artifacts else None
+        if int(count.max().item()) == 0:
+            output = DiarizeOutput(Annotation(uri=uri), Annotation(uri=uri), np.zeros((0, self._embedding.dimension)))
+            output = output.speaker_diarization if self.legacy else output
+            return (output, artifacts) if return_artifacts else output
+        hook("embeddings", _Lazy(lambda: emb.cpu().numpy()))
+        hard, _, centroids = self.clustering(embeddings=emb, segmentations=seg, num_clusters=num_speakers,
+                                             min_clusters=min_speakers, max_clusters=max_speakers)
+        num_different = int(np.max(hard)) + 1
+        if num_different < min_speakers or num_different > max_speakers:
+            warnings.warn(textwrap.dedent(f"""
+                The detected number of speakers ({num_different}) for {uri} is outside
+                the given bounds [{min_speakers}, {max_speakers}]. This can happen if the
+                given audio file is too short to contain {min_speakers} or more speakers.
+                Try to lower the desired minimal number of speakers.
+                """))
+        if np.isfinite(max_speakers):
+            count = torch.clamp(count, max=int(max_speakers))
+        inactive = (seg.sum(dim=1) == 0).cpu().numpy()
+        hard = hard.copy()
+        hard[inactive] = -2
+        K = int(np.max(hard)) + 1
+        Kout = max(K, int(count.max().item()), 1)
+        discrete = ctx.reconstruct(seg, hard, sf, F, K, count, Kout)
+        count1 = torch.clamp(count, max=1)
+        exclusive = ctx.reconstruct(seg, hard, sf, F, K, count1, max(K, 1))
+        discrete_np, exclusive_np = discrete.cpu().numpy(), exclusive.cpu().numpy()
+        self.d2h_bytes += discrete_np.nbytes + exclusive_np.nbytes + hard.nbytes + centroids.nbytes + seg.shape[0] * 3
+        hook("discrete_diarization", _Lazy(lambda: SlidingWindowFeature(discrete_np.astype(np.float64), fr)))
+        diarization, rows = binarize_frames(discrete_np, fr, self.min_duration_off, uri=uri)
+        exclusive_diarization, xrows = binarize_frames(exclusive_np, fr, self.min_duration_off, uri=uri)
+        mapping = {label: expected for label, expected in zip(diarization.labels(), self.classes())}
+        labels_int = diarization.labels()
+        diarization = diarization.rename_labels(mapping)
+        exclusive_diarization = exclusive_diarization.rename_labels(mapping)
+        if len(labels_int) > centroids.shape[0]:
+            centroids = np.pad(centroids, ((0, len(labels_int) - centroids.shape[0]), (0, 0)))
+        inverse = {label: index for index, label in mapping.items()}
+        centroids = centroids[[inverse[label] for label in diarization.labels()]] if len(labels_int) else centroids[:0]
+        output = DiarizeOutput(diarization, exclusive_diarization, centroids)
+        if return_artifacts:
+            artifacts.update(hard_clusters=hard, discrete=discrete_np, exclusive=exclusive_np, segments=rows,
+                             exclusive_segments=xrows, centroids=centroids)
+            return (output.speaker_diarization if self.legacy else output), artifacts
+        return output.speaker_diarization if self.legacy else output
+
+
+class _Lazy:
+    """Hook artefact materialised (D2H) only if a hook actually looks at it."""
+
+    def __init__(self, fn):
+        self._fn, self._v = fn, None
+
+    def get(self):
+        if self._v is None:
+            self._v = self._fn()
+        return self._v
+
+    def __getattr__(self, name):
+        return getattr(self.get(), name)

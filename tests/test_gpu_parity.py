@@ -1,0 +1,325 @@
+"""GPU parity tests (pytest -m gpu): every check goes through the C ABI (pyannote_audio_b200.ops / the public API)
+and compares against the CPU oracle on the same seeded inputs.  Tolerances:
+  * integer / index outputs (classes, counts, discrete diarization, segment frame indices, partitions): bit-exact
+  * segmentation log-probabilities (fp32 both sides, different summation order): 2e-4 absolute
+  * embeddings (fp16 tensor-core trunk vs fp32 oracle): cosine distance <= 1e-3 (BASELINE.json north_star)
+  * fp64 clustering arithmetic: 1e-9
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets, pipeline as P
+from pyannote_audio_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+FRAMES = P.SW(*nets.sincnet_receptive_field())
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ctx(dev):
+    from pyannote_audio_b200.models import get_context
+
+    c = get_context(dev)
+    c.load_segmentation(syn.make_segmentation_state_dict(0))
+    c.load_embedding(syn.make_embedding_state_dict(1))
+    return c
+
+
+@pytest.fixture(scope="module")
+def oracle_models():
+    seg = nets.PyanNet()
+    seg.load_state_dict(syn.make_segmentation_state_dict(0))
+    emb = nets.WeSpeakerResNet34()
+    emb.load_state_dict(syn.make_embedding_state_dict(1))
+    return seg.eval(), emb.eval()
+
+
+def _device_wave(wav, dev):
+    from pyannote_audio_b200.inference import chunk_layout
+
+    T = wav.shape[1]
+    off, valid, _, _ = chunk_layout(T, 160000, 16000)
+    buf = torch.zeros(int(off[-1]) + 160000, dtype=torch.float32, device=dev)
+    buf[:T] = wav[0].to(dev)
+    return buf, off, valid
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_stats_pool_known_answers_cuda(ctx, dev, golden):
+    # /root/reference/tests/test_stats_pool.py:28-131, through b200_stats_pool
+    r4 = lambda t: torch.round(t.cpu(), decimals=4)  # noqa: E731
+    x = torch.tensor([[[2.0, 4.0], [2.0, 4.0]], [[1.0, 1.0], [1.0, 1.0]]], device=dev)
+    assert torch.equal(r4(ctx.stats_pool(x)), torch.Tensor([[3.0, 3.0, 1.4142, 1.4142], [1.0, 1.0, 0.0, 0.0]]))
+    w = torch.tensor([[0.5, 0.01], [0.2, 0.1]], device=dev)
+    assert torch.equal(r4(ctx.stats_pool(x, w)), torch.Tensor([[2.0392, 2.0392, 1.4142, 1.4142], [1.0, 1.0, 0.0, 0.0]]))
+    assert torch.equal(r4(ctx.stats_pool(x, torch.zeros(2, 2, device=dev))), torch.zeros(2, 4))
+    # vectors produced by the reference's pooling.py (incl. nearest interpolation of 5 weights onto 11 frames)
+    xs = torch.from_numpy(golden["sp_x"]).to(dev)
+    np.testing.assert_allclose(ctx.stats_pool(xs).cpu().numpy(), golden["sp_y_none"], atol=2e-6)
+    np.testing.assert_allclose(ctx.stats_pool(xs, torch.from_numpy(golden["sp_w2"]).to(dev)).cpu().numpy(),
+                               golden["sp_y_w2"], atol=2e-6)
+    np.testing.assert_allclose(ctx.stats_pool(xs, torch.from_numpy(golden["sp_w3"]).to(dev)).cpu().numpy(),
+                               golden["sp_y_w3"], atol=2e-6)
+
+
+def test_powerset_cuda(ctx, dev, golden):
+    logits = torch.from_numpy(golden["ps_logits"])
+    cls = logits.argmax(-1).to(torch.uint8).to(dev)
+    assert np.array_equal(ctx.powerset_to_multilabel(cls).cpu().numpy(), golden["ps_multilabel"].astype(np.uint8))
+
+
+def test_segmentation_parity(ctx, dev, oracle_models):
+    seg_model, _ = oracle_models
+    wav = syn.make_conversation(37.3, seed=11)           # ragged: padded tail chunk
+    chunks = P.chunk_waveform(wav)
+    buf, off, valid = _device_wave(wav, dev)
+    assert len(off) == chunks.shape[0] and valid[-1] < 160000
+    with torch.inference_mode():
+        ref_sinc = seg_model.sincnet(chunks).transpose(1, 2).numpy()
+        ref_logp = seg_model(chunks).numpy()
+    sinc = ctx.sincnet_forward(buf, off, valid).cpu().numpy()
+    np.testing.assert_allclose(sinc, ref_sinc, atol=2e-4, rtol=0)
+    cls, logp = ctx.seg_forward(buf, off, valid, return_logp=True)
+    np.testing.assert_allclose(logp.cpu().numpy(), ref_logp, atol=2e-4, rtol=0)
+    ref_cls = ref_logp.argmax(-1)
+    top2 = np.sort(ref_logp, axis=-1)
+    margin = top2[..., -1] - top2[..., -2]
+    mism = cls.cpu().numpy() != ref_cls
+    # bit-identical decisions wherever the oracle's own top-2 margin is above fp32 reordering noise
+    assert not (mism & (margin > 1e-3)).any()
+    assert mism.mean() < 1e-3
+    # a chunk computed inside a batch equals the same chunk computed alone (bitwise: deterministic kernels)
+    alone = ctx.seg_forward(buf, off[5:6], valid[5:6])
+    assert torch.equal(alone[0], cls[5])
+
+
+def test_segmentation_edge_cases(ctx, dev, oracle_models):
+    seg_model, _ = oracle_models
+    for T in (100, 160000, 171234):                       # shorter than a chunk / exactly one / one + ragged tail
+        wav = syn.make_conversation(T / 16000.0, seed=5)[:, :T]
+        chunks = P.chunk_waveform(wav)
+        buf, off, valid = _device_wave(wav, dev)
+        assert chunks.shape[0] == len(off)
+        with torch.inference_mode():
+            ref = seg_model(chunks).numpy()
+        _, logp = ctx.seg_forward(buf, off, valid, return_logp=True)
+        np.testing.assert_allclose(logp.cpu().numpy(), ref, atol=3e-4, rtol=0)
+    with pytest.raises(ValueError):
+        ctx.seg_forward(buf, np.array([0], dtype=np.int64), np.array([160001], dtype=np.int32))
+    assert ctx.seg_forward(buf, np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int32)).shape == (0, 589)
+
+
+def test_embedding_parity(ctx, dev, oracle_models):
+    _, emb_model = oracle_models
+    wav = syn.make_conversation(13.7, seed=21)
+    chunks = P.chunk_waveform(wav)
+    buf, off, valid = _device_wave(wav, dev)
+    n = chunks.shape[0]
+    with torch.inference_mode():
+        ref_fb = emb_model.compute_fbank(chunks)
+        ref_frames = emb_model.resnet.forward_frames(ref_fb)
+    fb = ctx.emb_fbank(buf, off, valid)
+    np.testing.assert_allclose(fb.cpu().numpy(), ref_fb.numpy(), atol=5e-3, rtol=0)
+    # trunk: tensor-core path and CUDA-core path against the fp32 oracle, and against each other
+    out = {}
+    for impl in (0, 1, 2):
+        ctx.set_option("conv_impl", impl)
+        out[impl] = ctx.emb_trunk(ref_fb.to(dev)).cpu().numpy()
+        rel = np.abs(out[impl] - ref_frames.numpy()).max() / np.abs(ref_frames.numpy()).max()
+        assert rel < 2e-2, f"impl {impl}: trunk relative error {rel}"
+    ctx.set_option("conv_impl", 1)
+    assert np.abs(out[1] - out[0]).max() <= 2e-2 * np.abs(out[0]).max()
+    assert np.array_equal(out[1], out[2]) or np.abs(out[1] - out[2]).max() < 1e-2
+    rng = np.random.default_rng(0)
+    masks = (rng.uniform(size=(n, 3, 589)) < 0.5).astype(np.uint8)
+    masks[0, 2] = 0                                        # all-zero weights (test_stats_pool.py:111-131 case)
+    masks[1, 0] = 1
+    with torch.inference_mode():
+        ref = emb_model.forward_embedding(ref_frames, weights=torch.from_numpy(masks.astype(np.float32))).numpy()
+    emb = ctx.emb_forward(buf, off, valid, torch.from_numpy(masks).to(dev)).cpu().numpy()
+    cos = (emb * ref).sum(-1) / (np.linalg.norm(emb, axis=-1) * np.linalg.norm(ref, axis=-1))
+    assert (1 - cos).max() <= 1e-3, f"cosine distance to oracle {1 - cos}"
+    # pairwise cosine-distance matrix
+    a, b = emb.reshape(-1, 256), ref.reshape(-1, 256)
+    da = 1 - (a @ a.T) / np.outer(np.linalg.norm(a, axis=1), np.linalg.norm(a, axis=1))
+    db = 1 - (b @ b.T) / np.outer(np.linalg.norm(b, axis=1), np.linalg.norm(b, axis=1))
+    assert np.abs(da - db).max() <= 1e-3
+
+
+def test_post_processing_bit_exact(ctx, dev):
+    rng = np.random.default_rng(1)
+    for C, p in ((1, 0.5), (7, 0.3), (40, 0.3), (40, 0.02)):
+        seg = (rng.uniform(size=(C, 589, 3)) < p).astype(np.float32)
+        swf = P.SWF(seg, P.SW(0.0, 10.0, 1.0))
+        ref_count = P.speaker_count(swf, FRAMES, (0.0, 0.0))
+        sf = P.chunk_start_frames(C, FRAMES)
+        F = len(ref_count.data)
+        seg_dev = torch.from_numpy(seg.astype(np.uint8)).to(dev)
+        count = ctx.speaker_count(seg_dev, sf, F)
+        assert np.array_equal(count.cpu().numpy(), ref_count.data[:, 0])
+        hard = rng.integers(-1, 5, size=(C, 3)).astype(np.int8)
+        hard[hard == -1] = -2
+        if hard.max() < 0:
+            hard[0, 0] = 0
+        for cap in (3, 1):
+            cnt = P.SWF(np.minimum(ref_count.data, cap).astype(np.int8), ref_count.sw)
+            ref_d = P.reconstruct(swf, hard, cnt)
+            K = int(hard.max()) + 1
+            Kout = max(K, int(cnt.data.max()), 1)
+            d = ctx.reconstruct(seg_dev, hard, sf, F, K, torch.from_numpy(cnt.data[:, 0].astype(np.uint8)).to(dev), Kout)
+            assert np.array_equal(d.cpu().numpy()[:, : ref_d.data.shape[1]], ref_d.data.astype(np.uint8))
+            assert not d.cpu().numpy()[:, ref_d.data.shape[1]:].any()
+        clean, active = ctx.clean_frames(seg_dev)
+        single = seg.sum(2, keepdims=True) == 1
+        assert np.array_equal(clean.cpu().numpy(), (seg * single).sum(1).astype(np.int32))
+        assert np.array_equal(active.cpu().numpy() > 0, seg.sum(1) > 0)
+
+
+def _same_partition(a, b):
+    m = {}
+    for x, y in zip(a, b):
+        if m.setdefault(x, y) != y:
+            return False
+    return len(set(m.values())) == len(m)
+
+
+def test_linkage_parity_with_scipy(ctx, dev):
+    from scipy.cluster.hierarchy import fcluster, linkage
+
+    from pyannote_audio_b200 import ops
+
+    rng = np.random.default_rng(3)
+    # issue-1525 vector of /root/reference/tests/test_clustering.py:6-29 (2 embeddings)
+    e2 = np.array([[1.0, 1.0, 1.0, 1.0], [1.0, 2.0, 1.0, 2.0]])
+    Z = ctx.linkage_centroid(torch.from_numpy(e2).to(dev), normalize=True).cpu().numpy()
+    ref = linkage(e2 / np.linalg.norm(e2, axis=1, keepdims=True), "centroid", "euclidean")
+    np.testing.assert_allclose(Z, ref, rtol=1e-12)
+    for n, dim in ((3, 4), (50, 16), (300, 256), (1000, 256)):
+        centers = rng.standard_normal((5, dim))
+        X = centers[rng.integers(0, 5, n)] + 0.6 * rng.standard_normal((n, dim))
+        Xn = X / np.linalg.norm(X, axis=1, keepdims=True)
+        ref = linkage(Xn, "centroid", "euclidean")
+        Z = ctx.linkage_centroid(torch.from_numpy(X).to(dev), normalize=True).cpu().numpy()
+        np.testing.assert_allclose(np.sort(Z[:, 2]), np.sort(ref[:, 2]), rtol=1e-9, atol=1e-12)
+        for t in (0.3, 0.6, 0.9, 1.2):
+            assert _same_partition(fcluster(ref, t, "distance"), ops.fcluster_distance(Z, t))
+
+
+def test_vbx_cdist_assign_parity(ctx, dev, golden):
+    from scipy.optimize import linear_sum_assignment
+    from scipy.spatial.distance import cdist
+    from scipy.special import softmax
+
+    fea, phi, ahc = golden["vbx_fea"], golden["vbx_phi"], golden["vbx_ahc"]
+    q0 = np.zeros((len(ahc), ahc.max() + 1))
+    q0[range(len(ahc)), ahc] = 1.0
+    q0 = softmax(q0 * 7.0, axis=1)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    gamma, pi, iters = ctx.vbx(t(fea), t(phi), t(q0), 0.07, 0.8, max_iters=20)
+    np.testing.assert_allclose(gamma.cpu().numpy(), golden["vbx_gamma"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(pi.cpu().numpy(), golden["vbx_pi"], rtol=1e-8, atol=1e-10)
+    assert 1 <= iters <= 20
+    rng = np.random.default_rng(4)
+    a, b = rng.standard_normal((37, 256)), rng.standard_normal((6, 256))
+    np.testing.assert_allclose(ctx.cdist_cosine(t(a), t(b)).cpu().numpy(), cdist(a, b, "cosine"), rtol=1e-10, atol=1e-12)
+    for K in (1, 2, 3, 6):
+        soft = rng.standard_normal((50, 3, K))
+        hard = ctx.assign(t(soft), constrained=True).cpu().numpy()
+        for c in range(50):
+            rows, cols = linear_sum_assignment(soft[c], maximize=True)
+            ref = -2 * np.ones(3, dtype=np.int8)
+            ref[rows] = cols
+            assert np.array_equal(hard[c], ref)
+        assert np.array_equal(ctx.assign(t(soft), constrained=False).cpu().numpy(), soft.argmax(-1))
+
+
+@pytest.fixture(scope="module")
+def pipeline(dev):
+    from pyannote_audio_b200.models import PyanNet, WeSpeakerResNet34
+    from pyannote_audio_b200.pipeline import SpeakerDiarization
+
+    seg, emb = PyanNet(), WeSpeakerResNet34()
+    seg.load_state_dict(syn.make_segmentation_state_dict(0), strict=False)
+    emb.load_state_dict(syn.make_embedding_state_dict(1), strict=False)
+    return SpeakerDiarization(segmentation=seg, embedding=emb, plda=syn.make_plda(2), device=dev)
+
+
+def test_pipeline_end_to_end_vs_oracle(pipeline, oracle_models):
+    seg_model, emb_model = oracle_models
+    plda = P.PLDA(**syn.make_plda(2))
+    wav = syn.make_conversation(75.0, seed=1234)
+    file = {"waveform": wav, "sample_rate": 16000, "uri": "synthetic"}
+    seen = []
+    (_, (out, art)), = list(pipeline.apply_batch([file], hook=lambda name, *a, **k: seen.append(name),
+                                                 return_artifacts=True))
+    assert seen[:3] == ["segmentation", "speaker_counting", "embeddings"] and "discrete_diarization" in seen
+    ref = P.apply(seg_model, emb_model, plda, wav)
+    seg = art["segmentations"].cpu().numpy().astype(np.float32)
+    assert seg.shape == ref.segmentations.data.shape
+    mism = (seg != ref.segmentations.data).any(-1).mean()
+    assert mism < 1e-3
+    emb = art["embeddings"].cpu().numpy()
+    cos = (emb * ref.embeddings).sum(-1) / (np.linalg.norm(emb, axis=-1) * np.linalg.norm(ref.embeddings, axis=-1))
+    assert (1 - cos).max() <= 1e-3
+    # downstream of the networks everything is exact: feed the CUDA segmentations/embeddings to the oracle's
+    # clustering + reconstruction and require bit-identical integer outputs
+    ref2 = P.apply(seg_model, emb_model, plda, wav, segmentations=P.SWF(seg, P.SW(0.0, 10.0, 1.0)), embeddings=emb)
+    assert np.array_equal(art["count"].cpu().numpy(), ref2.count.data[:, 0])
+    assert _same_partition(art["hard_clusters"].ravel().tolist(), ref2.hard_clusters.ravel().tolist())
+    assert np.array_equal(art["hard_clusters"], ref2.hard_clusters)
+    assert np.array_equal(art["discrete"][:, : ref2.discrete.data.shape[1]], ref2.discrete.data.astype(np.uint8))
+    assert [tuple(r) for r in art["segments"]] == ref2.segments                  # integer frame boundaries
+    assert [tuple(r) for r in art["exclusive_segments"]] == ref2.exclusive_segments
+    got = [(s.start, s.end, lab) for s, _, lab in out.speaker_diarization.itertracks(yield_label=True)]
+    assert got == ref2.times
+    np.testing.assert_allclose(out.speaker_embeddings, ref2.speaker_embeddings, rtol=1e-6, atol=1e-8)
+    if mism == 0:   # whole pipeline identical to the fully independent oracle run as well
+        assert np.array_equal(art["count"].cpu().numpy(), ref.count.data[:, 0])
+
+
+def test_pipeline_edge_cases(pipeline):
+    silence = {"waveform": torch.zeros(1, 16000 * 12), "sample_rate": 16000, "uri": "silence"}
+    short = {"waveform": syn.make_conversation(3.0, seed=2), "sample_rate": 16000, "uri": "short"}
+    outs = pipeline([silence, short])
+    assert len(outs) == 2
+    for o in outs:
+        assert hasattr(o, "speaker_diarization") and isinstance(o.serialize(), dict)
+    one = pipeline(short, num_speakers=1)
+    assert len(one.speaker_diarization.labels()) <= 1
+
+
+def test_full_size_properties(ctx, dev):
+    """BASELINE.json configs[2]/[3] sizes through size-independent properties (oracle would take hours on CPU)."""
+    wav = syn.make_conversation(3600.0, seed=99)
+    buf, off, valid = _device_wave(wav, dev)
+    assert len(off) == 3591
+    cls = ctx.seg_forward(buf, off, valid)
+    assert cls.shape == (3591, 589) and int(cls.max()) <= 6
+    assert torch.equal(cls, ctx.seg_forward(buf, off, valid))                       # deterministic / idempotent
+    sub = ctx.seg_forward(buf, off[1000:1010], valid[1000:1010])
+    assert torch.equal(sub, cls[1000:1010])                                          # batch invariance
+    seg = ctx.powerset_to_multilabel(cls)
+    sf = P.chunk_start_frames(3591, FRAMES)
+    F = FRAMES.closest_frame(10.0 + 3590 * 1.0 + 0.5 * FRAMES.duration) + 1
+    assert F == 213334
+    count = ctx.speaker_count(seg, sf, F)
+    assert int(count.max()) <= 2                                                     # powerset: at most 2 simultaneous
+    masks = seg.permute(0, 2, 1).contiguous()
+    emb = ctx.emb_forward(buf, off, valid, masks)
+    assert emb.shape == (3591, 3, 256) and bool(torch.isfinite(emb).all())
+    sub = ctx.emb_forward(buf, off[2000:2003], valid[2000:2003], masks[2000:2003])
+    assert torch.equal(sub, emb[2000:2003])
+    # cosine-distance matrix on ~10k embeddings: symmetric, zero diagonal, within [0, 2]
+    x = emb.reshape(-1, 256).double()
+    d = ctx.cdist_cosine(x, x)
+    assert d.shape == (10773, 10773)
+    assert float((d - d.T).abs().max()) < 1e-12 and float(d.diagonal().abs().max()) < 1e-9
+    assert float(d.min()) > -1e-9 and float(d.max()) <= 2.0 + 1e-9

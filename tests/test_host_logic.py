@@ -1,0 +1,168 @@
+"""CPU: host-side logic of the product package (no GPU, no compute calls into the CUDA library)."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets, pipeline as P
+from pyannote_audio_b200 import synthetic as syn
+from pyannote_audio_b200.core import Annotation, Segment, SlidingWindow, SlidingWindowFeature
+from pyannote_audio_b200.inference import Inference, chunk_layout
+from pyannote_audio_b200.models import PyanNet, WeSpeakerResNet34
+from pyannote_audio_b200.pipeline import binarize_frames, set_num_speakers
+
+
+@pytest.mark.parametrize("T", [480000, 160000, 159999, 100, 176000, 176001, 9600000])
+def test_chunk_layout_matches_oracle_chunking(T):
+    off, valid, num_chunks, has_last = chunk_layout(T, 160000, 16000)
+    if T <= 200000:
+        wav = torch.arange(T, dtype=torch.float32)[None]
+        chunks = P.chunk_waveform(wav)
+        assert chunks.shape[0] == len(off)
+        for c in range(len(off)):
+            ref = chunks[c, 0].numpy()
+            got = np.zeros(160000, dtype=np.float32)
+            got[: valid[c]] = wav[0, off[c]: off[c] + valid[c]].numpy()
+            assert np.array_equal(ref, got)
+    assert len(off) == num_chunks + int(has_last)
+    # 30 s -> 21 chunks, 10 min -> 591
+    if T == 480000:
+        assert len(off) == 21
+    if T == 9600000:
+        assert len(off) == 591
+
+
+def test_inference_ctor_validation():
+    # mirrors /root/reference/tests/inference_test.py:51-76
+    model = PyanNet()
+    with pytest.warns(UserWarning):
+        Inference(model, duration=5.0)
+    with pytest.raises(ValueError):
+        Inference(model, step=20.0)
+    with pytest.raises(ValueError):
+        Inference(model, window="hopping")
+    with pytest.warns(UserWarning):
+        Inference(model, window="whole")
+    inf = Inference(model, skip_aggregation=True)
+    assert inf.duration == 10.0 and inf.step == 1.0
+    with pytest.raises(TypeError):
+        inf.to("cuda")
+
+
+def test_models_have_reference_state_dict_keys():
+    seg_sd, emb_sd = syn.make_segmentation_state_dict(0), syn.make_embedding_state_dict(1)
+    m = PyanNet()
+    missing, unexpected = m.load_state_dict(seg_sd, strict=False)
+    assert not unexpected and set(missing) <= {"_dummy"}
+    e = WeSpeakerResNet34()
+    missing, unexpected = e.load_state_dict(emb_sd, strict=False)
+    assert not unexpected and set(missing) <= {"_dummy"}
+    # oracle modules take the very same dicts (same key names as the reference)
+    nets.PyanNet().load_state_dict(seg_sd, strict=True)
+    nets.WeSpeakerResNet34().load_state_dict(emb_sd, strict=True)
+    assert m.num_frames(160000) == 589 and m.receptive_field_size(1) == 991 and m.receptive_field_center(0) == 495
+    rf = m.receptive_field
+    assert (rf.start, rf.duration, rf.step) == (0.0, 991 / 16000, 270 / 16000)
+    assert e.num_frames(160000) == 125
+
+
+def test_models_refuse_cpu_forward():
+    m = PyanNet()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 1, 160000))
+
+
+def test_binarize_frames_matches_oracle():
+    rng = np.random.default_rng(0)
+    frames = SlidingWindow(start=0.0, duration=991 / 16000, step=270 / 16000)
+    for trial in range(5):
+        d = (rng.uniform(size=(400, 3)) < 0.5).astype(np.uint8)
+        d[:, 2] = 0 if trial == 0 else d[:, 2]
+        if trial == 1:
+            d[-5:, 0] = 1
+            d[0, 1] = 1
+        ann, rows = binarize_frames(d, frames)
+        ref_rows, ref_times = P.binarize_to_segments(P.SWF(d.astype(np.float64), P.SW(0.0, 991 / 16000, 270 / 16000)))
+        assert [tuple(r) for r in rows] == ref_rows
+        got = [(s.start, s.end, lab) for s, _, lab in ann.itertracks(yield_label=True)]
+        assert got == ref_times
+
+
+def test_sliding_window_arithmetic_matches_oracle():
+    sw = SlidingWindow(start=0.0, duration=991 / 16000, step=270 / 16000)
+    osw = P.SW(0.0, 991 / 16000, 270 / 16000)
+    for t in [0.0, 0.03, 1.0, 59.0 * 270 / 16000, 10.03096875, 3600.0]:
+        assert sw.closest_frame(t) == osw.closest_frame(t)
+    ts = np.arange(4000) * 1.0 + 0.5 * sw.duration
+    assert np.array_equal(sw.closest_frames(ts), np.array([osw.closest_frame(t) for t in ts]))
+    data = np.zeros((100, 2))
+    swf = SlidingWindowFeature(data, sw)
+    e = swf.extent
+    assert (e.start, e.end) == osw.range_to_segment(0, 100)
+    assert swf.crop(e, return_data=True).shape[0] == 100
+
+
+def test_annotation_and_set_num_speakers():
+    a = Annotation(uri="x")
+    a.add(Segment(1.0, 2.0), 0, 1)
+    a.add(Segment(0.5, 0.7), 1, 0)
+    a.add(Segment(2.1, 3.0), 2, 1)
+    assert a.labels() == [0, 1]
+    assert [s.start for s in a.itersegments()] == [0.5, 1.0, 2.1]
+    b = a.rename_labels({0: "SPEAKER_00", 1: "SPEAKER_01"})
+    assert b.labels() == ["SPEAKER_00", "SPEAKER_01"]
+    assert len(a.support(collar=0.2)) == 2
+    assert "SPEAKER x 1 0.500 0.200" in b.to_rttm()
+    assert set_num_speakers(None, None, None) == (None, 1, np.inf)
+    assert set_num_speakers(3, None, None) == (3, 3, 3)
+    with pytest.raises(ValueError):
+        set_num_speakers(None, 4, 2)
+
+
+def test_fcluster_host_matches_scipy():
+    from scipy.cluster.hierarchy import fcluster, linkage
+
+    from pyannote_audio_b200 import ops
+
+    rng = np.random.default_rng(0)
+    for _ in range(100):
+        n = int(rng.integers(2, 80))
+        X = rng.standard_normal((n, 8))
+        X /= np.linalg.norm(X, axis=1, keepdims=True)
+        Z = linkage(X, "centroid", "euclidean")
+        t = float(rng.uniform(0.2, 1.5))
+        assert np.array_equal(fcluster(Z, t, "distance"), ops.fcluster_distance(Z, t))
+
+
+def test_sinc_filter_bank_matches_oracle():
+    from pyannote_audio_b200.ops import sinc_filter_bank
+
+    sd = syn.make_segmentation_state_dict(0)
+    p = "sincnet.conv1d.0.filterbank."
+    bank = sinc_filter_bank(sd[p + "low_hz_"], sd[p + "band_hz_"], sd[p + "window_"], sd[p + "n_"])
+    fb = nets.ParamSincFB()
+    fb.load_state_dict({k[len(p):]: v for k, v in sd.items() if k.startswith(p)})
+    assert torch.equal(bank, fb.filters()[:, 0, :])
+    # (anti)symmetry the CUDA kernel relies on
+    assert torch.equal(bank[:40], torch.flip(bank[:40], dims=[1]))
+    assert torch.equal(bank[40:], -torch.flip(bank[40:], dims=[1]))
+
+
+def test_product_plda_setup_matches_oracle():
+    from pyannote_audio_b200.clustering import PLDA
+
+    arrays = syn.make_plda(2)
+    a, b = PLDA(arrays), P.PLDA(**arrays)
+    np.testing.assert_allclose(a.phi, b.phi, rtol=1e-12)
+    np.testing.assert_allclose(a._plda_tr, b._tr, rtol=1e-12, atol=1e-14)
+
+
+def test_oracle_not_imported_by_product():
+    import pathlib
+    import re
+
+    root = pathlib.Path(__file__).resolve().parents[1] / "pyannote_audio_b200"
+    for f in root.rglob("*.py"):
+        src = f.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
