@@ -75,8 +75,7 @@ _PROTOS = {
                                     C.c_void_p]),
     "b200_vbx": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double,
                            C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "b200_assign": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
-                              C.c_void_p]),
+    "b200_assign": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 
 # symbols that every build must export (tests/test_abi.py checks the header against the .so)

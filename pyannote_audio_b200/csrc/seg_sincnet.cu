@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(128) sinc_pool_kernel(const float* __restrict_
                                                         const float2* __restrict__ affine,
                                                         const float* __restrict__ filt /*[126][80]*/,
                                                         float* __restrict__ P0 /*[B][80][5325]*/,
-                                                        float2* __restrict__ part /*[B][80][kTiles0]*/) {
+                                                        double2* __restrict__ part /*[B][80][kTiles0]*/) {
   extern __shared__ float sm[];
   float* xs = sm;                    // 2176
   float* fs = sm + 2176;             // 126*80
@@ -144,18 +144,18 @@ __global__ void __launch_bounds__(128) sinc_pool_kernel(const float* __restrict_
   }
   __syncthreads();
   if (tid < 80) {
-    float s = 0.f, ss = 0.f;
+    double s = 0.0, ss = 0.0;
     for (int i = 0; i < kTileP; ++i) {
-      const float v = pt[tid * 65 + i];
+      const double v = pt[tid * 65 + i];
       s += v;
-      ss = fmaf(v, v, ss);
+      ss += v * v;
     }
-    part[((size_t)b * 80 + tid) * kTiles0 + tile] = make_float2(s, ss);
+    part[((size_t)b * 80 + tid) * kTiles0 + tile] = make_double2(s, ss);
   }
 }
 
 // ---- InstanceNorm finalize: partial sums -> per (chunk, channel) affine -------------------------------
-__global__ void in_finalize_kernel(const float2* __restrict__ part, int ntiles, int n, int C,
+__global__ void in_finalize_kernel(const double2* __restrict__ part, int ntiles, int n, int C,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float2* __restrict__ affine, int total) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -163,7 +163,7 @@ __global__ void in_finalize_kernel(const float2* __restrict__ part, int ntiles, 
   const int c = idx % C;
   double s = 0, ss = 0;
   for (int t = 0; t < ntiles; ++t) {
-    const float2 p = part[(size_t)idx * ntiles + t];
+    const double2 p = part[(size_t)idx * ntiles + t];
     s += p.x;
     ss += p.y;
   }
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(192) conv5_pool_kernel(const float* __restrict
                                                          const float* __restrict__ Wc /*[CIN][5][60]*/,
                                                          const float* __restrict__ bias /*[60]*/,
                                                          float* __restrict__ Pout, int Lp, int ntiles,
-                                                         float2* __restrict__ part /*[B][60][ntiles]*/) {
+                                                         double2* __restrict__ part /*[B][60][ntiles]*/) {
   constexpr int TW = 3 * kTileP + 4;   // 196 input positions per tile
   constexpr int CCH = 20;              // input channels per weight stage
   extern __shared__ float sm[];
@@ -248,13 +248,13 @@ __global__ void __launch_bounds__(192) conv5_pool_kernel(const float* __restrict
   }
   __syncthreads();
   if (tid < 60) {
-    float s = 0.f, ss = 0.f;
+    double s = 0.0, ss = 0.0;
     for (int i = 0; i < kTileP; ++i) {
-      const float v = pt[tid * 65 + i];
+      const double v = pt[tid * 65 + i];
       s += v;
-      ss = fmaf(v, v, ss);
+      ss += v * v;
     }
-    part[((size_t)b * 60 + tid) * ntiles + tile] = make_float2(s, ss);
+    part[((size_t)b * 60 + tid) * ntiles + tile] = make_double2(s, ss);
   }
 }
 
@@ -278,7 +278,8 @@ __global__ void in_apply_transpose_kernel(const float* __restrict__ P2, const fl
 
 // ---- host ------------------------------------------------------------------------------------------
 struct SincWs {
-  float2 *af_wav, *af0, *af1, *af2, *part0, *part1, *part2;
+  float2 *af_wav, *af0, *af1, *af2;
+  double2 *part0, *part1, *part2;
   float *P0, *P1, *P2;
 };
 
@@ -295,9 +296,9 @@ static size_t carve(int NB, void* base, SincWs* w) {
   t.af0 = (float2*)take(sizeof(float2) * NB * 80);
   t.af1 = (float2*)take(sizeof(float2) * NB * 60);
   t.af2 = (float2*)take(sizeof(float2) * NB * 60);
-  t.part0 = (float2*)take(sizeof(float2) * (size_t)NB * 80 * kTiles0);
-  t.part1 = (float2*)take(sizeof(float2) * (size_t)NB * 60 * kTiles1);
-  t.part2 = (float2*)take(sizeof(float2) * (size_t)NB * 60 * kTiles2);
+  t.part0 = (double2*)take(sizeof(double2) * (size_t)NB * 80 * kTiles0);
+  t.part1 = (double2*)take(sizeof(double2) * (size_t)NB * 60 * kTiles1);
+  t.part2 = (double2*)take(sizeof(double2) * (size_t)NB * 60 * kTiles2);
   t.P0 = (float*)take(sizeof(float) * (size_t)NB * 80 * kPool0);
   t.P1 = (float*)take(sizeof(float) * (size_t)NB * 60 * kPool1);
   t.P2 = (float*)take(sizeof(float) * (size_t)NB * 60 * kPool2);
