@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--files-per-gpu", type=int, default=12)
     ap.add_argument("--minutes", type=float, default=10.0)
-    ap.add_argument("--cpu-sample-seconds", type=float, default=20.0)
+    ap.add_argument("--cpu-sample-seconds", type=float, default=12.0)
     ap.add_argument("--min-warmup", type=int, default=3, help="lower only when profiling under ncu")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     return ap.parse_args()
@@ -113,7 +113,7 @@ def cpu_pass(seconds, models, seed=4242):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(min(32, os.cpu_count() or 1))   # conv on >32 threads oversubscribes and gets slower
     models = oracle_models()
     secs = args.cpu_sample_seconds
     for _ in range(min(args.warmup, 1)):
@@ -235,7 +235,7 @@ def main():
                 "trunk_ms_per_step": trunk_ms / args.steps, "seg_ms_per_step": seg_ms / args.steps}
     cpu = None
     if args.gpus == 1 and not args.no_cpu_baseline:
-        torch.set_num_threads(os.cpu_count() or 1)
+        torch.set_num_threads(min(32, os.cpu_count() or 1))
         models = oracle_models()
         t = cpu_pass(args.cpu_sample_seconds, models)
         cpu = {"value": (args.cpu_sample_seconds / 3600.0) / t, "unit": "audio-hours/sec",

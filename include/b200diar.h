@@ -42,7 +42,8 @@ int b200_version(void);
 /* Model.to(device) / Inference.to(device)  (core/inference.py:169-180) */
 int b200_ctx_create(b200_ctx** ctx, int device);
 int b200_ctx_destroy(b200_ctx* ctx);
-/* conv_impl: 0 = CUDA-core reference conv, 1 = tcgen05 tensor-core conv (default), 2 = tcgen05 for stride-1 only */
+/* options: "conv_impl" 0 = CUDA-core reference conv, 1 = tcgen05 per-tap conv, 2 = tcgen05 for stride-1 only,
+ * 3..6 = tcgen05 strip-streaming conv (halo reuse) variants; "seg_max_batch", "emb_max_batch", "profile". */
 int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches claim) */
 int64_t b200_ctx_launch_count(const b200_ctx* ctx);

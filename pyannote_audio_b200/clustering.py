@@ -148,14 +148,27 @@ class VBxClustering(BaseClustering):
     def __call__(self, embeddings, segmentations=None, num_clusters=None, min_clusters=None, max_clusters=None,
                  return_debug: bool = False, **kwargs):
         """clustering.py:572-669.  Returns (hard_clusters (C,3) int8, soft_clusters (C,3,K) f64, centroids (K,256))."""
+        import os
+        import time
+
+        timing = bool(os.environ.get("B200_TIMING"))
+        marks = []
+
+        def mark(name):
+            if timing:
+                torch.cuda.synchronize()
+                marks.append((name, time.perf_counter()))
+
         constrained = self.constrained_assignment
         min_clusters = min_clusters if min_clusters is not None else 1
         max_clusters = max_clusters if max_clusters is not None else np.inf
         ctx = self._ctx(embeddings)
+        mark("start")
         train, _, _, active = self.filter_embeddings(embeddings, segmentations)
         emb = embeddings if isinstance(embeddings, torch.Tensor) else torch.from_numpy(np.asarray(embeddings))
         emb64 = emb.to(ctx.device).double()
         num_chunks, num_speakers, dimension = emb64.shape
+        mark("filter")
         if train.shape[0] < 2:
             hard = np.zeros((num_chunks, num_speakers), dtype=np.int8)
             soft = np.ones((num_chunks, num_speakers, 1))
@@ -163,8 +176,10 @@ class VBxClustering(BaseClustering):
             return hard, soft, centroids
         # AHC (centroid linkage on unit vectors) on the device, dendrogram cut on the host
         Z = ctx.linkage_centroid(train, normalize=True).cpu().numpy()
+        mark("linkage")
         ahc = ops.fcluster_distance(Z, self.threshold) - 1
         _, ahc = np.unique(ahc, return_inverse=True)
+        mark("fcluster")
         # VBx
         fea = self.plda.transform(train)
         S = int(ahc.max()) + 1
@@ -172,6 +187,7 @@ class VBxClustering(BaseClustering):
         qinit[torch.arange(len(ahc), device=ctx.device), torch.from_numpy(ahc).to(ctx.device)] = 1.0
         qinit = torch.softmax(qinit * 7.0, dim=1)
         q, sp, iters = ctx.vbx(fea, self.plda._consts(ctx.device)["phi"], qinit, self.Fa, self.Fb, max_iters=20)
+        mark("plda+vbx")
         W = q[:, sp > 1e-7]
         centroids = (W.T @ train) / W.sum(0, keepdim=True).T
         auto_num = centroids.shape[0]
@@ -190,6 +206,18 @@ class VBxClustering(BaseClustering):
             centroids = centroids.to(ctx.device)
         hard, soft = self._assign(ctx, emb64, centroids.contiguous(), active, constrained)
         out = (hard.cpu().numpy().reshape(num_chunks, num_speakers), soft.cpu().numpy(), centroids.cpu().numpy())
+        mark("assign+d2h")
+        if timing:
+            import sys
+
+            acc = getattr(VBxClustering, "_timing_acc", {})
+            for (_, t0), (name, t1) in zip(marks[:-1], marks[1:]):
+                acc[name] = acc.get(name, 0.0) + (t1 - t0)
+            acc["n_train"] = acc.get("n_train", 0) + int(train.shape[0])
+            acc["S"] = acc.get("S", 0) + S
+            VBxClustering._timing_acc = acc
+            print("[b200 timing vbx-cum] " + ", ".join(f"{k}={v * 1e3:.1f}ms" if isinstance(v, float) else f"{k}={v}"
+                                                       for k, v in acc.items()), file=sys.stderr, flush=True)
         if return_debug:
             return out + (dict(ahc=ahc, dendrogram=Z, q=q.cpu().numpy(), sp=sp.cpu().numpy(), iters=iters,
                                fea=fea.cpu().numpy(), train=train.cpu().numpy(), active=active.cpu().numpy()),)

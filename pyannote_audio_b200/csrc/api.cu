@@ -211,7 +211,7 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value) {
   else if (k == "emb_max_batch") ctx->emb_max_batch = (int)value;
   else if (k == "profile") ctx->profile = (int)value;
   else B200_CHECK(false, B200_ERR_INVALID, "unknown option '%s'", key);
-  B200_CHECK(ctx->seg_max_batch >= 1 && ctx->emb_max_batch >= 1 && ctx->conv_impl >= 0 && ctx->conv_impl <= 2,
+  B200_CHECK(ctx->seg_max_batch >= 1 && ctx->emb_max_batch >= 1 && ctx->conv_impl >= 0 && ctx->conv_impl <= 6,
              B200_ERR_INVALID, "option '%s' value %lld out of range", key, (long long)value);
   return B200_OK;
 }
@@ -408,6 +408,7 @@ static int seg_run(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, co
 
 int b200_seg_forward(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, const int32_t* chunk_valid,
                      int32_t num_chunks, uint8_t* classes, float* logp, void* stream) {
+  if (num_chunks == 0) return B200_OK;
   B200_CHECK(classes != nullptr, B200_ERR_INVALID, "classes is NULL");
   return seg_run(ctx, wav, chunk_off, chunk_valid, num_chunks, classes, logp, nullptr, (cudaStream_t)stream);
 }
@@ -480,7 +481,7 @@ static int trunk_run(b200_ctx* ctx, const EmbWs& w, int nb, cudaStream_t st) {
   for (const BlockWeights& B : E.blocks) {
     const int s = B.conv1.stride;
     const int impl1 = (ctx->conv_impl == 2) ? (s == 1 ? 1 : 0) : ctx->conv_impl;
-    const int impl_s1 = ctx->conv_impl == 0 ? 0 : 1;
+    const int impl_s1 = ctx->conv_impl == 2 ? 1 : ctx->conv_impl;
     const int Ho = (H + 2 - 3) / s + 1, Wo = (Wd + 2 - 3) / s + 1;
     if ((rc = conv_forward(B.conv1, w.A, nullptr, w.Bf, nb, H, Wd, 1, impl1, ctx->num_sms, st))) return rc;
     const __half* res = w.A;

@@ -264,6 +264,241 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// conv_tc2_kernel: stride-1 3x3 convolution with shared-memory halo reuse ("strip streaming")
+//
+// A work item is a strip of 128 output columns x R output rows of one image.  The producer streams the R+2 input
+// rows (130 pixels wide: one halo pixel each side, zero filled by TMA at the image border) through a ring of
+// shared-memory slots ONCE; each slot feeds up to 3 output rows (kh) x 3 horizontal taps (kw).  The kw shift is a
+// descriptor trick: the A operand of tap kw starts kw pixel-rows (kw * Ck * 2 bytes) into the slot, with the UMMA
+// descriptor's base_offset field carrying the swizzle phase of the shifted start.  Up to 4 output rows accumulate
+// concurrently in TMEM (4 x N columns).  L2->smem traffic for activations drops 9x against conv_tc_kernel; weights
+// stay resident in shared memory when they fit (C_in * C_out <= 64 x 64), otherwise they stream through a B ring.
+// ------------------------------------------------------------------------------------------------
+struct ConvV2Params {
+  int B, H, W, C_in, C_out;
+  int N, n_halves, Ck, ncc, tiles_w, R, nhseg, num_items, relu;
+  int resident, n_aslots, n_bslots, base_off_mode;
+  const float* bias;
+  const __half* residual;
+  __half* out;
+  uint32_t a_bytes, a_slot_bytes, b_bytes, idesc, swizzle, w_off, a_off, b_off;
+};
+
+__device__ __forceinline__ uint64_t make_kmajor_desc_bo(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type,
+                                                        int base_off_mode) {
+  uint64_t d = make_kmajor_desc(saddr, sbo_bytes, layout_type);
+  if (base_off_mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+  return d;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvV2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  // header: [0,64) a_full  [64,128) a_empty  [128,256) b_full  [256,384) b_empty  [384,416) tfull  [416,448) tempty
+  //         [448,456) wbar  [512,516) tmem slot   [1024,2048) bias
+  const uint32_t bar_afull = base, bar_aempty = base + 64, bar_bfull = base + 128, bar_bempty = base + 256;
+  const uint32_t bar_tfull = base + 384, bar_tempty = base + 416, bar_w = base + 448;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + 512);
+  float* s_bias = reinterpret_cast<float*>(gbase + 1024);
+  const uint32_t w_smem = base + p.w_off, a_smem = base + p.a_off, b_smem = base + p.b_off;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = p.N;
+  for (int i = threadIdx.x; i < p.C_out; i += blockDim.x) s_bias[i] = p.bias[i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.n_aslots; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
+    for (int s = 0; s < p.n_bslots; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
+    for (int a = 0; a < 4; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+    mbar_init(bar_w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int ksteps = p.Ck / 16;
+  const uint32_t rowbytes = p.Ck * 2;
+
+  // item -> (b, wt, hs, nh); nh fastest so that both N halves of a strip run back to back (input rows hit L2)
+  auto decode = [&](int item, int& b, int& wt, int& h0, int& h1, int& nh) {
+    nh = item % p.n_halves;
+    int t = item / p.n_halves;
+    const int hs = t % p.nhseg; t /= p.nhseg;
+    wt = t % p.tiles_w;
+    b = t / p.tiles_w;
+    h0 = hs * p.R;
+    h1 = min(p.H, h0 + p.R);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+      if (p.resident) {
+        mbar_expect_tx(bar_w, 9u * p.ncc * p.b_bytes);
+        for (int tap = 0; tap < 9; ++tap)
+          for (int cc = 0; cc < p.ncc; ++cc)
+            tma_load_3d(&tmB, bar_w, w_smem + (tap * p.ncc + cc) * p.b_bytes, cc * p.Ck, 0, tap);
+      }
+      uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        int b, wt, h0, h1, nh;
+        decode(item, b, wt, h0, h1, nh);
+        const int R = h1 - h0;
+        for (int t = 0; t < R + 2; ++t) {
+          for (int cc = 0; cc < p.ncc; ++cc) {
+            mbar_wait(bar_aempty + 8 * as, aph ^ 1);
+            mbar_expect_tx(bar_afull + 8 * as, p.a_bytes);
+            tma_load_4d(&tmA, bar_afull + 8 * as, a_smem + as * p.a_slot_bytes, cc * p.Ck, wt * kTileM - 1,
+                        h0 - 1 + t, b);
+            if (++as == (uint32_t)p.n_aslots) { as = 0; aph ^= 1; }
+            if (!p.resident) {
+              for (int kh = 0; kh < 3; ++kh) {
+                const int r = t - kh;
+                if (r < 0 || r >= R) continue;
+                for (int kw = 0; kw < 3; ++kw) {
+                  mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
+                  mbar_expect_tx(bar_bfull + 8 * bs, p.b_bytes);
+                  tma_load_3d(&tmB, bar_bfull + 8 * bs, b_smem + bs * p.b_bytes, cc * p.Ck, nh * N, kh * 3 + kw);
+                  if (++bs == (uint32_t)p.n_bslots) { bs = 0; bph ^= 1; }
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t sbo = (p.swizzle == 128) ? 1024u : 512u;
+      const uint32_t ltype = (p.swizzle == 128) ? 2u : 4u;
+      if (p.resident) { mbar_wait(bar_w, 0); tc_fence_after(); }
+      uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+      uint32_t grow = 0;                                  // global output-row counter of this CTA
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        int b, wt, h0, h1, nh;
+        decode(item, b, wt, h0, h1, nh);
+        const int R = h1 - h0;
+        for (int t = 0; t < R + 2; ++t) {
+          for (int cc = 0; cc < p.ncc; ++cc) {
+            mbar_wait(bar_afull + 8 * as, aph);
+            tc_fence_after();
+            const uint32_t sa = a_smem + as * p.a_slot_bytes;
+            for (int kh = 0; kh < 3; ++kh) {
+              const int r = t - kh;
+              if (r < 0 || r >= R) continue;
+              const uint32_t g = grow + (uint32_t)r;
+              const uint32_t acc = g & 3u;
+              if (kh == 0 && cc == 0) {                   // first contribution to output row r
+                mbar_wait(bar_tempty + 8 * acc, ((g >> 2) & 1u) ^ 1u);
+                tc_fence_after();
+              }
+              const uint32_t d_tmem = tmem_base + acc * (uint32_t)N;
+              for (int kw = 0; kw < 3; ++kw) {
+                uint32_t sb;
+                if (p.resident) {
+                  sb = w_smem + ((kh * 3 + kw) * p.ncc + cc) * p.b_bytes;
+                } else {
+                  mbar_wait(bar_bfull + 8 * bs, bph);
+                  tc_fence_after();
+                  sb = b_smem + bs * p.b_bytes;
+                }
+                const uint64_t adesc = make_kmajor_desc_bo(sa + kw * rowbytes, sbo, ltype, p.base_off_mode);
+                const uint64_t bdesc = make_kmajor_desc(sb, sbo, ltype);
+                for (int k = 0; k < ksteps; ++k)
+                  tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kh | cc | kw | k) != 0);
+                if (!p.resident) {
+                  tc_commit(bar_bempty + 8 * bs);
+                  if (++bs == (uint32_t)p.n_bslots) { bs = 0; bph ^= 1; }
+                }
+              }
+              if (kh == 2 && cc == p.ncc - 1) tc_commit(bar_tfull + 8 * acc);   // output row r complete
+            }
+            tc_commit(bar_aempty + 8 * as);
+            if (++as == (uint32_t)p.n_aslots) { as = 0; aph ^= 1; }
+          }
+        }
+        grow += (uint32_t)R;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    uint32_t grow = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int b, wt, h0, h1, nh;
+      decode(item, b, wt, h0, h1, nh);
+      const int R = h1 - h0;
+      const int w = wt * kTileM + q * 32 + lane;
+      const bool valid = w < p.W;
+      for (int r = 0; r < R; ++r) {
+        const uint32_t g = grow + (uint32_t)r;
+        const uint32_t acc = g & 3u;
+        mbar_wait(bar_tfull + 8 * acc, (g >> 2) & 1u);
+        tc_fence_after();
+        const size_t pix = (((size_t)b * p.H + (h0 + r)) * p.W + (valid ? w : 0)) * (size_t)p.C_out + (size_t)nh * N;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)N;
+        for (int n0 = 0; n0 < N; n0 += 32) {
+          uint32_t rr[32];
+          tc_ld32(taddr + n0, rr);
+          if (valid) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) + s_bias[nh * N + n0 + j];
+            if (p.residual) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix + n0);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                uint4 u = __ldg(rp + j4);
+                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 f = __half22float2(h2[e]);
+                  v[j4 * 8 + 2 * e] += f.x;
+                  v[j4 * 8 + 2 * e + 1] += f.y;
+                }
+              }
+            }
+            uint4* op = reinterpret_cast<uint4*>(p.out + pix + n0);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              uint4 u;
+              __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float a = v[j4 * 8 + 2 * e], c = v[j4 * 8 + 2 * e + 1];
+                if (p.relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+                h2[e] = __floats2half2_rn(a, c);
+              }
+              op[j4] = u;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      }
+      grow += (uint32_t)R;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // SIMT reference conv (same math, CUDA cores) -- debugging aid and A/B check for the tensor-core path
 // ------------------------------------------------------------------------------------------------
@@ -400,8 +635,99 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+static int conv2_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H, int W,
+                         int relu, int base_off_mode, int num_sms, cudaStream_t stream) {
+  ConvV2Params p{};
+  p.B = B; p.H = H; p.W = W; p.C_in = L.C_in; p.C_out = L.C_out; p.relu = relu;
+  p.bias = L.bias; p.residual = residual; p.out = out; p.base_off_mode = base_off_mode;
+  p.N = L.C_out < 128 ? L.C_out : 128;
+  p.n_halves = L.C_out / p.N;
+  p.Ck = (L.C_in >= 64) ? 64 : 32;
+  p.ncc = L.C_in / p.Ck;
+  p.swizzle = (p.Ck == 64) ? 128 : 64;
+  p.tiles_w = ceil_div(W, kTileM);
+  // split H when there are too few strips to fill the machine twice
+  const int strips = B * p.tiles_w * p.n_halves;
+  int nhseg = 1;
+  if (strips < 2 * num_sms) nhseg = ceil_div(2 * num_sms, strips);
+  if (nhseg > H / 2) nhseg = H / 2 > 0 ? H / 2 : 1;
+  p.R = ceil_div(H, nhseg);
+  p.nhseg = ceil_div(H, p.R);
+  p.num_items = B * p.tiles_w * p.nhseg * p.n_halves;
+  p.a_bytes = 130u * p.Ck * 2;
+  p.a_slot_bytes = (uint32_t)align_up(p.a_bytes, 1024);
+  p.b_bytes = (uint32_t)p.N * p.Ck * 2;
+  const size_t wbytes = (size_t)9 * p.ncc * p.b_bytes;
+  p.resident = (p.n_halves == 1 && wbytes <= 80 * 1024) ? 1 : 0;
+  p.idesc = (1u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+  uint32_t off = 2048;
+  p.w_off = off;
+  if (p.resident) off += (uint32_t)align_up(wbytes, 1024);
+  const uint32_t budget = 210 * 1024;
+  if (p.resident) {
+    p.n_bslots = 0;
+    p.n_aslots = (int)((budget - off) / p.a_slot_bytes);
+    if (p.n_aslots > 8) p.n_aslots = 8;
+    p.a_off = off;
+    p.b_off = off;
+    off += p.n_aslots * p.a_slot_bytes;
+  } else {
+    p.n_aslots = 3;
+    p.a_off = off;
+    off += p.n_aslots * p.a_slot_bytes;
+    p.n_bslots = (int)((budget - off) / p.b_bytes);
+    if (p.n_bslots > 16) p.n_bslots = 16;
+    p.b_off = off;
+    off += p.n_bslots * p.b_bytes;
+  }
+  B200_CHECK(p.n_aslots >= 2 && (p.resident || p.n_bslots >= 2), B200_ERR_STATE, "conv v2: smem budget too small");
+  PFN_encodeTiled enc = get_encode();
+  B200_CHECK(enc != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)L.C_in, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)L.C_in * 2, (cuuint64_t)W * L.C_in * 2, (cuuint64_t)H * W * L.C_in * 2};
+    cuuint32_t box[4] = {(cuuint32_t)p.Ck, 130, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(in), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     p.swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(A, v2) failed: %d", (int)r);
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)L.C_in, (cuuint64_t)L.C_out, 9};
+    cuuint64_t strides[2] = {(cuuint64_t)L.C_in * 2, (cuuint64_t)L.C_out * L.C_in * 2};
+    cuuint32_t box[3] = {(cuuint32_t)p.Ck, (cuuint32_t)p.N, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(L.w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     p.swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(B, v2) failed: %d", (int)r);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const size_t smem = 1024 + off;
+  int grid = p.num_items < num_sms ? p.num_items : num_sms;
+  conv_tc2_kernel<<<grid, kTcThreads, smem, stream>>>(tmA, tmB, p);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
 int conv_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H_in, int W_in,
                  int relu, int impl, int num_sms, cudaStream_t stream) {
+  if (impl >= 3) {
+    // 3: v2 for C_in >= 64 (128B swizzle), base_offset set; 4: v2 also for C_in = 32 (64B swizzle);
+    // 5 / 6: same as 3 / 4 with base_offset left at 0 (hardware-semantics A/B)
+    const bool small_ok = (impl == 4 || impl == 6);
+    if (L.ksize == 3 && L.stride == 1 && (L.C_in >= 64 || small_ok))
+      return conv2_forward(L, in, residual, out, B, H_in, W_in, relu, (impl == 3 || impl == 4) ? 1 : 0, num_sms, stream);
+    impl = 1;
+  }
   ConvParams p{};
   p.B = B; p.H_in = H_in; p.W_in = W_in; p.C_in = L.C_in; p.C_out = L.C_out;
   p.taps_h = L.ksize; p.taps_w = L.ksize; p.stride = L.stride; p.pad = L.ksize / 2;

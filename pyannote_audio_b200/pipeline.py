@@ -353,9 +353,13 @@ class SpeakerDiarization:
         ctx = get_context(self.device)
         wav_dev, all_off, all_valid, bounds = resident["wav"], resident["off"], resident["valid"], resident["bounds"]
         # ---- device passes over all files at once ------------------------------------------------------------
+        self._timer = _StageTimer(ctx.device)
+        self._timer.start()
         cls = self._segmentation.model.forward_chunks(wav_dev, all_off, all_valid)        # (C,589) u8
         seg = ctx.powerset_to_multilabel(cls)                                              # (C,589,3) u8
+        self._timer.mark("segmentation")
         emb = self.embedding.forward_chunks(wav_dev, all_off, all_valid, self._masks(seg))  # (C,3,256) f32
+        self._timer.mark("embedding")
         # ---- per-file clustering + reconstruction ------------------------------------------------------------
         for fi, file in enumerate(resident["files"]):
             h = self.setup_hook(file, hook)
@@ -363,6 +367,7 @@ class SpeakerDiarization:
             out = self._finish_file(ctx, file, seg[c0:c1], emb[c0:c1], num_speakers, min_speakers, max_speakers, h,
                                     return_artifacts)
             yield file, out
+        self._timer.report()
 
     def _finish_file(self, ctx, file, seg, emb, num_speakers, min_speakers, max_speakers, hook, return_artifacts):
         uri = file.get("uri", None)
@@ -370,6 +375,7 @@ class SpeakerDiarization:
         sf, F, fr = self._grid(C)
         chunks_sw = SlidingWindow(start=0.0, duration=self._segmentation.duration, step=self._segmentation.step)
         hook("segmentation", _Lazy(lambda: SlidingWindowFeature(seg.cpu().numpy().astype(np.float32), chunks_sw)))
+        tm = getattr(self, "_timer", None) or _StageTimer(ctx.device)
         count = ctx.speaker_count(seg, sf, F)
         hook("speaker_counting", _Lazy(lambda: SlidingWindowFeature(count.cpu().numpy()[:, None], fr)))
         artifacts = dict(segmentations=seg, count=count, embeddings=emb) if return_artifacts else None
@@ -380,6 +386,7 @@ class SpeakerDiarization:
         hook("embeddings", _Lazy(lambda: emb.cpu().numpy()))
         hard, _, centroids = self.clustering(embeddings=emb, segmentations=seg, num_clusters=num_speakers,
                                              min_clusters=min_speakers, max_clusters=max_speakers)
+        tm.mark("count+clustering")
         num_different = int(np.max(hard)) + 1
         if num_different < min_speakers or num_different > max_speakers:
             warnings.warn(textwrap.dedent(f"""
@@ -399,6 +406,7 @@ class SpeakerDiarization:
         count1 = torch.clamp(count, max=1)
         exclusive = ctx.reconstruct(seg, hard, sf, F, K, count1, max(K, 1))
         discrete_np, exclusive_np = discrete.cpu().numpy(), exclusive.cpu().numpy()
+        tm.mark("reconstruct+d2h")
         self.d2h_bytes += discrete_np.nbytes + exclusive_np.nbytes + hard.nbytes + centroids.nbytes + seg.shape[0] * 3
         hook("discrete_diarization", _Lazy(lambda: SlidingWindowFeature(discrete_np.astype(np.float64), fr)))
         diarization, rows = binarize_frames(discrete_np, fr, self.min_duration_off, uri=uri)
@@ -412,11 +420,46 @@ class SpeakerDiarization:
         inverse = {label: index for index, label in mapping.items()}
         centroids = centroids[[inverse[label] for label in diarization.labels()]] if len(labels_int) else centroids[:0]
         output = DiarizeOutput(diarization, exclusive_diarization, centroids)
+        tm.mark("annotation")
         if return_artifacts:
             artifacts.update(hard_clusters=hard, discrete=discrete_np, exclusive=exclusive_np, segments=rows,
                              exclusive_segments=xrows, centroids=centroids)
             return (output.speaker_diarization if self.legacy else output), artifacts
         return output.speaker_diarization if self.legacy else output
+
+
+class _StageTimer:
+    """Opt-in (B200_TIMING=1) wall-clock breakdown of the per-file stages, with a device sync at every mark."""
+
+    def __init__(self, device):
+        import os
+
+        self.on = bool(os.environ.get("B200_TIMING"))
+        self.device, self.acc, self.t = device, {}, None
+
+    def start(self):
+        if self.on:
+            torch.cuda.synchronize(self.device)
+            import time
+
+            self.t = time.perf_counter()
+
+    def mark(self, name):
+        if self.on:
+            import time
+
+            torch.cuda.synchronize(self.device)
+            now = time.perf_counter()
+            self.acc[name] = self.acc.get(name, 0.0) + (now - self.t)
+            self.t = now
+
+    def report(self):
+        if self.on and self.acc:
+            import sys
+
+            tot = sum(self.acc.values())
+            print("[b200 timing] " + ", ".join(f"{k}={v * 1e3:.1f}ms" for k, v in self.acc.items())
+                  + f", total={tot * 1e3:.1f}ms", file=sys.stderr, flush=True)
 
 
 class _Lazy:

@@ -15,6 +15,7 @@ from pyannote_audio_b200 import ops, synthetic as syn  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--stage", default="seg")
 ap.add_argument("--seconds", type=float, default=25.0)
+ap.add_argument("--impl", type=int, default=1)
 args = ap.parse_args()
 torch.set_num_threads(max(1, torch.get_num_threads()))
 dev = torch.device("cuda:0")
@@ -85,6 +86,25 @@ if args.stage.startswith("emb"):
     report("embeddings (n,3,256)", emb, ref_emb)
     cos = (emb * ref_emb).sum(-1) / (np.linalg.norm(emb, axis=-1) * np.linalg.norm(ref_emb, axis=-1))
     print("  cosine distance to oracle:", np.round(1 - cos, 6).ravel())
+
+if args.stage == "conv_ab":
+    # A/B of a tensor-core conv variant against the CUDA-core reference conv (same fp16 inputs/weights)
+    ctx.load_embedding(emb_sd)
+    n = min(C, 6)
+    fb = ctx.emb_fbank(wav_dev, off[:n], valid[:n])
+    ctx.set_option("conv_impl", 0)
+    ref = ctx.emb_trunk(fb).cpu().numpy()
+    ctx.set_option("conv_impl", args.impl)
+    got = ctx.emb_trunk(fb)
+    torch.cuda.synchronize()
+    report(f"trunk impl={args.impl} vs SIMT", got.cpu().numpy(), ref)
+    big = fb.repeat(43, 1, 1)[:256].contiguous()
+    for impl in (1, args.impl):
+        ctx.set_option("conv_impl", impl)
+        ctx.emb_trunk(big); torch.cuda.synchronize()
+        t0 = time.time(); ctx.emb_trunk(big); torch.cuda.synchronize()
+        dt = time.time() - t0
+        print(f"  impl={impl}: 256 segments trunk {dt*1e3:.1f} ms -> {256*45.18e9/dt/1e12:.0f} TFLOP/s", flush=True)
 
 if args.stage == "post":
     x = torch.tensor([[[2.0, 4.0], [2.0, 4.0]], [[1.0, 1.0], [1.0, 1.0]]], device=dev)

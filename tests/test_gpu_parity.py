@@ -137,7 +137,7 @@ def test_embedding_parity(ctx, dev, oracle_models):
         assert rel < 2e-2, f"impl {impl}: trunk relative error {rel}"
     ctx.set_option("conv_impl", 1)
     assert np.abs(out[1] - out[0]).max() <= 2e-2 * np.abs(out[0]).max()
-    assert np.array_equal(out[1], out[2]) or np.abs(out[1] - out[2]).max() < 1e-2
+    assert np.abs(out[1] - out[2]).max() <= 2e-2 * np.abs(out[0]).max()
     rng = np.random.default_rng(0)
     masks = (rng.uniform(size=(n, 3, 589)) < 0.5).astype(np.uint8)
     masks[0, 2] = 0                                        # all-zero weights (test_stats_pool.py:111-131 case)
