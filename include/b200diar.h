@@ -124,15 +124,17 @@ int b200_stats_pool(b200_ctx* ctx, const float* seq, const float* weights, float
                     int32_t S, int32_t Tw, void* stream);
 
 /* ---- overlap-add / reconstruction (core/inference.py:498-620, pipelines/utils/diarization.py:150-268,
- * pipelines/speaker_diarization.py:480-528).  seg[num_chunks][589][3] u8 in {0,1}; start_frame[num_chunks] HOST
- * array with the global frame index of each chunk's first frame; num_frames = size of the global grid. */
+ * pipelines/speaker_diarization.py:480-528).  seg[num_chunks][589][3] u8 in {0,1}; start_frame[num_chunks] DEVICE
+ * int32 array with the global frame index of each chunk's first frame (non-decreasing; computed on the host as
+ * inference.py:596 does); num_frames = size of the global grid. */
 int b200_speaker_count(b200_ctx* ctx, const uint8_t* seg, const int32_t* start_frame, int32_t num_chunks,
                        int32_t num_frames, uint8_t* count, void* stream);
-/* hard_clusters[num_chunks][3] int8 (-2 = inactive) HOST; count[num_frames] u8 device (already capped);
- * out: discrete[num_frames][num_clusters_out] u8, num_clusters_out = max(K, max(count)). */
+/* hard_clusters[num_chunks][3] int8 DEVICE (-2 = inactive/unassigned, values >= num_clusters_out are ignored);
+ * count[num_frames] u8 device (already capped); out: discrete[num_frames][num_clusters_out] u8 with
+ * num_clusters_out >= max(K, max(count)), at most 32. */
 int b200_reconstruct(b200_ctx* ctx, const uint8_t* seg, const int8_t* hard_clusters, const int32_t* start_frame,
-                     int32_t num_chunks, int32_t num_frames, int32_t num_clusters, const uint8_t* count,
-                     int32_t num_clusters_out, uint8_t* discrete, void* stream);
+                     int32_t num_chunks, int32_t num_frames, const uint8_t* count, int32_t num_clusters_out,
+                     uint8_t* discrete, void* stream);
 
 /* ---- clustering (pipelines/clustering.py:77-140, 572-669; utils/vbx.py; scipy linkage/fcluster) --------------- */
 /* filter_embeddings: clean-frame counts per (chunk, speaker): out[num_chunks][3] int32, plus active[num_chunks][3] u8
@@ -143,6 +145,11 @@ int b200_clean_frames(b200_ctx* ctx, const uint8_t* seg, int32_t num_chunks, int
  * rows are L2-normalised first when normalize != 0; Z[n-1][4] fp64 device in scipy's format. */
 int b200_linkage_centroid(b200_ctx* ctx, const double* x, int32_t n, int32_t dim, int32_t normalize, double* Z,
                           void* stream);
+/* the same for num_problems independent problems in ONE launch (one CTA each): rows of problem f are
+ * x[row_offsets[f] .. row_offsets[f+1]) (row_offsets: HOST int32[num_problems+1]); Z rows are concatenated, problem
+ * f contributing max(n_f - 1, 0) rows. */
+int b200_linkage_centroid_batched(b200_ctx* ctx, const double* x, const int32_t* row_offsets, int32_t num_problems,
+                                  int32_t dim, int32_t normalize, double* Z, void* stream);
 /* fcluster(Z, t, criterion="distance") (clustering.py:604, 385): HOST arrays, labels[n] 1-based like scipy. */
 int b200_fcluster_distance(const double* Z, int32_t n, double t, int32_t* labels);
 /* cdist(a, b, "cosine") (clustering.py:645-655): a[m][dim], b[k][dim] fp64 device -> d[m][k] fp64 device. */
@@ -152,6 +159,11 @@ int b200_cdist_cosine(b200_ctx* ctx, const double* a, int32_t m, const double* b
  * responsibilities, out: final), pi[S] (out), all fp64 device; *iters (host) = iterations run. */
 int b200_vbx(b200_ctx* ctx, const double* fea, const double* phi, int32_t n, int32_t D, int32_t S, double Fa,
              double Fb, int32_t max_iters, double epsilon, double* gamma, double* pi, int32_t* iters, void* stream);
+/* batched: problem f has n[f] frames (consecutive rows of fea) and S[f] speakers; gamma / pi are the per-problem
+ * arrays concatenated; n, S, iters (nullable) are HOST int32[num_problems].  One persistent CTA per problem. */
+int b200_vbx_batched(b200_ctx* ctx, const double* fea, const double* phi, const int32_t* n, const int32_t* S,
+                     int32_t num_problems, int32_t D, double Fa, double Fb, int32_t max_iters, double epsilon,
+                     double* gamma, double* pi, int32_t* iters, void* stream);
 /* constrained_argmax / argmax (clustering.py:127-140, 658-665): soft[num_chunks][3][K] fp64 device ->
  * hard[num_chunks][3] int8 device (-2 = unassigned). */
 int b200_assign(b200_ctx* ctx, const double* soft, int32_t num_chunks, int32_t num_clusters, int32_t constrained,

@@ -65,11 +65,16 @@ _PROTOS = {
     "b200_stats_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_int32, C.c_void_p]),
     "b200_speaker_count": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
-    "b200_reconstruct": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
-                                   C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "b200_reconstruct": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                   C.c_int32, C.c_void_p, C.c_void_p]),
     "b200_clean_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200_linkage_centroid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                         C.c_void_p]),
+    "b200_linkage_centroid_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                                C.c_void_p, C.c_void_p]),
+    "b200_vbx_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                   C.c_double, C.c_double, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
     "b200_fcluster_distance": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p]),
     "b200_cdist_cosine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                     C.c_void_p]),

@@ -145,82 +145,127 @@ class VBxClustering(BaseClustering):
                 setattr(self, k, float(params[k]))
         return self
 
+    def cluster_batch(self, emb_all: torch.Tensor, seg_all: torch.Tensor, bounds, num_clusters=None,
+                      min_clusters=None, max_clusters=None, skip=None):
+        """VBx clustering of several files at once (clustering.py:572-669 per file).
+
+        emb_all (Ctot,3,256) f32 and seg_all (Ctot,589,3) u8 are device tensors holding the files back to back,
+        ``bounds`` the chunk boundaries (F+1,).  Device work is batched across files (one linkage launch, one VBx
+        launch, ...); host work is the dendrogram cut per file.  Returns a list of dicts with device tensors:
+        hard (C,3) int8, soft (C,3,K) f64, centroids (K,256) f64, active (C,3) bool (+ debug entries).
+        """
+        ctx = self._ctx(emb_all)
+        dev = ctx.device
+        min_clusters = min_clusters if min_clusters is not None else 1
+        max_clusters = max_clusters if max_clusters is not None else np.inf
+        F = len(bounds) - 1
+        skip = skip if skip is not None else [False] * F
+        num_frames = seg_all.shape[1]
+        dim = emb_all.shape[-1]
+        clean, active_all = ctx.clean_frames(seg_all)
+        keep = (clean.double() >= 0.2 * num_frames) & ~torch.isnan(emb_all).any(dim=2)          # (Ctot,3)
+        flat_idx = torch.nonzero(keep.reshape(-1)).reshape(-1)                                    # row-major = np.where
+        csum = torch.cumsum(keep.sum(dim=1), dim=0)
+        bnd = torch.as_tensor(np.asarray(bounds[1:], dtype=np.int64) - 1, device=dev)
+        ends = csum[bnd].cpu().numpy().astype(np.int64)                                           # sync: train counts
+        row_off = np.concatenate([[0], ends]).astype(np.int32)
+        n_f = np.diff(row_off)
+        train_all = emb_all.reshape(-1, dim)[flat_idx].double()
+        emb64_all = emb_all.double()
+        active_all = active_all.bool()
+        results = [None] * F
+        todo = []
+        for f in range(F):
+            c0, c1 = int(bounds[f]), int(bounds[f + 1])
+            if skip[f]:
+                continue
+            if n_f[f] < 2:
+                tr = train_all[row_off[f]: row_off[f + 1]]
+                results[f] = dict(hard=torch.zeros((c1 - c0, ops.SPEAKERS), dtype=torch.int8, device=dev),
+                                  soft=torch.ones((c1 - c0, ops.SPEAKERS, 1), dtype=torch.float64, device=dev),
+                                  centroids=tr.mean(dim=0, keepdim=True), active=active_all[c0:c1], trivial=True)
+            else:
+                todo.append(f)
+        if not todo:
+            return results
+        # ---- AHC: one batched linkage launch, dendrogram cut on the host ------------------------------------
+        lro = np.array(row_off, copy=True)
+        lro_n = np.where(np.isin(np.arange(F), todo), n_f, 0)           # problems not in `todo` get n = 0
+        sub_off = np.concatenate([[0], np.cumsum(lro_n)]).astype(np.int32)
+        if len(todo) == F and not any(skip):
+            x_link, link_off = train_all, row_off
+        else:
+            x_link = torch.cat([train_all[row_off[f]: row_off[f + 1]] for f in todo])
+            link_off = sub_off
+        Z_all = ctx.linkage_centroid_batched(x_link, link_off, normalize=True).cpu().numpy()   # sync
+        ahcs, S_f, zpos = {}, {}, 0
+        for f in todo:
+            n = int(n_f[f])
+            Z = Z_all[zpos: zpos + n - 1]
+            zpos += n - 1
+            ahc = ops.fcluster_distance(Z, self.threshold) - 1
+            _, ahc = np.unique(ahc, return_inverse=True)
+            ahcs[f], S_f[f] = ahc, int(ahc.max()) + 1
+            results[f] = dict(dendrogram=Z, ahc=ahc)
+        # ---- VBx: PLDA transform of all rows, initial responsibilities built on the host, one launch ----------
+        fea = self.plda.transform(x_link)
+        hot_blocks = []
+        for f in todo:
+            n, S = int(n_f[f]), S_f[f]
+            # softmax(7 * one_hot) (vbx.py:142-144) has two distinct values per row
+            tot = 1.0 + (S - 1) * np.exp(-7.0)
+            g = np.full((n, S), np.exp(-7.0) / tot)
+            g[np.arange(n), ahcs[f]] = 1.0 / tot
+            hot_blocks.append(g.reshape(-1))
+        gamma0 = torch.from_numpy(np.concatenate(hot_blocks)).to(dev)
+        phi = self.plda._consts(dev)["phi"]
+        n_list = [int(n_f[f]) for f in todo]
+        S_list = [S_f[f] for f in todo]
+        gamma, pi, _ = ctx.vbx_batched(fea, phi, gamma0, n_list, S_list, self.Fa, self.Fb, max_iters=20)
+        pi_host = pi.cpu().numpy()                                                                 # sync
+        gpos = spos = rpos = 0
+        for f, n, S in zip(todo, n_list, S_list):
+            c0, c1 = int(bounds[f]), int(bounds[f + 1])
+            q = gamma[gpos: gpos + n * S].reshape(n, S)
+            sp = pi_host[spos: spos + S]
+            train = x_link[rpos: rpos + n]
+            gpos, spos, rpos = gpos + n * S, spos + S, rpos + n
+            kept = np.nonzero(sp > 1e-7)[0]
+            W = q[:, torch.as_tensor(kept, device=dev)]
+            centroids = (W.T @ train) / W.sum(0, keepdim=True).T
+            constrained = self.constrained_assignment
+            auto_num = centroids.shape[0]
+            nc = num_clusters
+            if auto_num < min_clusters:
+                nc = min_clusters
+            elif auto_num > max_clusters:
+                nc = max_clusters
+            if nc and nc != auto_num:
+                from sklearn.cluster import KMeans
+
+                constrained = False
+                normed = (train / torch.linalg.norm(train, dim=1, keepdim=True)).cpu().numpy()
+                km = KMeans(n_clusters=int(nc), n_init=3, random_state=42, copy_x=False).fit_predict(normed)
+                tr = train.cpu().numpy()
+                centroids = torch.from_numpy(np.vstack([np.mean(tr[km == k], axis=0) for k in range(int(nc))])).to(dev)
+            hard, soft = self._assign(ctx, emb64_all[c0:c1], centroids.contiguous(), active_all[c0:c1], constrained)
+            results[f].update(hard=hard, soft=soft, centroids=centroids, active=active_all[c0:c1], q=q, sp=sp,
+                              train=train, fea=fea[rpos - n: rpos], trivial=False)
+        return results
+
     def __call__(self, embeddings, segmentations=None, num_clusters=None, min_clusters=None, max_clusters=None,
                  return_debug: bool = False, **kwargs):
         """clustering.py:572-669.  Returns (hard_clusters (C,3) int8, soft_clusters (C,3,K) f64, centroids (K,256))."""
-        import os
-        import time
-
-        timing = bool(os.environ.get("B200_TIMING"))
-        marks = []
-
-        def mark(name):
-            if timing:
-                torch.cuda.synchronize()
-                marks.append((name, time.perf_counter()))
-
-        constrained = self.constrained_assignment
-        min_clusters = min_clusters if min_clusters is not None else 1
-        max_clusters = max_clusters if max_clusters is not None else np.inf
         ctx = self._ctx(embeddings)
-        mark("start")
-        train, _, _, active = self.filter_embeddings(embeddings, segmentations)
         emb = embeddings if isinstance(embeddings, torch.Tensor) else torch.from_numpy(np.asarray(embeddings))
-        emb64 = emb.to(ctx.device).double()
-        num_chunks, num_speakers, dimension = emb64.shape
-        mark("filter")
-        if train.shape[0] < 2:
-            hard = np.zeros((num_chunks, num_speakers), dtype=np.int8)
-            soft = np.ones((num_chunks, num_speakers, 1))
-            centroids = train.mean(dim=0, keepdim=True).cpu().numpy()
-            return hard, soft, centroids
-        # AHC (centroid linkage on unit vectors) on the device, dendrogram cut on the host
-        Z = ctx.linkage_centroid(train, normalize=True).cpu().numpy()
-        mark("linkage")
-        ahc = ops.fcluster_distance(Z, self.threshold) - 1
-        _, ahc = np.unique(ahc, return_inverse=True)
-        mark("fcluster")
-        # VBx
-        fea = self.plda.transform(train)
-        S = int(ahc.max()) + 1
-        qinit = torch.zeros((len(ahc), S), dtype=torch.float64, device=ctx.device)
-        qinit[torch.arange(len(ahc), device=ctx.device), torch.from_numpy(ahc).to(ctx.device)] = 1.0
-        qinit = torch.softmax(qinit * 7.0, dim=1)
-        q, sp, iters = ctx.vbx(fea, self.plda._consts(ctx.device)["phi"], qinit, self.Fa, self.Fb, max_iters=20)
-        mark("plda+vbx")
-        W = q[:, sp > 1e-7]
-        centroids = (W.T @ train) / W.sum(0, keepdim=True).T
-        auto_num = centroids.shape[0]
-        if auto_num < min_clusters:
-            num_clusters = min_clusters
-        elif auto_num > max_clusters:
-            num_clusters = max_clusters
-        if num_clusters and num_clusters != auto_num:
-            from sklearn.cluster import KMeans
-
-            constrained = False
-            normed = (train / torch.linalg.norm(train, dim=1, keepdim=True)).cpu().numpy()
-            km = KMeans(n_clusters=int(num_clusters), n_init=3, random_state=42, copy_x=False).fit_predict(normed)
-            tr = train.cpu().numpy()
-            centroids = torch.from_numpy(np.vstack([np.mean(tr[km == k], axis=0) for k in range(int(num_clusters))]))
-            centroids = centroids.to(ctx.device)
-        hard, soft = self._assign(ctx, emb64, centroids.contiguous(), active, constrained)
-        out = (hard.cpu().numpy().reshape(num_chunks, num_speakers), soft.cpu().numpy(), centroids.cpu().numpy())
-        mark("assign+d2h")
-        if timing:
-            import sys
-
-            acc = getattr(VBxClustering, "_timing_acc", {})
-            for (_, t0), (name, t1) in zip(marks[:-1], marks[1:]):
-                acc[name] = acc.get(name, 0.0) + (t1 - t0)
-            acc["n_train"] = acc.get("n_train", 0) + int(train.shape[0])
-            acc["S"] = acc.get("S", 0) + S
-            VBxClustering._timing_acc = acc
-            print("[b200 timing vbx-cum] " + ", ".join(f"{k}={v * 1e3:.1f}ms" if isinstance(v, float) else f"{k}={v}"
-                                                       for k, v in acc.items()), file=sys.stderr, flush=True)
+        emb = emb.to(ctx.device).float().contiguous()
+        seg = _seg_tensor(segmentations, ctx)
+        r = self.cluster_batch(emb, seg, [0, emb.shape[0]], num_clusters, min_clusters, max_clusters)[0]
+        out = (r["hard"].cpu().numpy(), r["soft"].cpu().numpy(), r["centroids"].cpu().numpy())
         if return_debug:
-            return out + (dict(ahc=ahc, dendrogram=Z, q=q.cpu().numpy(), sp=sp.cpu().numpy(), iters=iters,
-                               fea=fea.cpu().numpy(), train=train.cpu().numpy(), active=active.cpu().numpy()),)
+            dbg = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in r.items()
+                   if k in ("ahc", "dendrogram", "q", "sp", "fea", "train", "active")}
+            return out + (dbg,)
         return out
 
 

@@ -163,23 +163,44 @@ class SlidingWindowFeature:
 
 
 class Annotation:
-    """Ordered collection of (segment, track, label); just what DiarizeOutput / RTTM writing need."""
+    """Ordered collection of (segment, track, label); just what DiarizeOutput / RTTM writing need.
+
+    Bulk-constructed annotations (``from_rows``) keep numpy arrays and only build ``Segment`` objects when iterated.
+    """
 
     def __init__(self, uri: Optional[str] = None):
         self.uri = uri
-        self._tracks: List[Tuple[Segment, str, object]] = []
+        self._tracks: Optional[List[Tuple[Segment, object, object]]] = []
         self._sorted = True
+        self._rows = None      # (starts f64, ends f64, labels object array), already in itertracks order
+
+    @classmethod
+    def from_rows(cls, starts: np.ndarray, ends: np.ndarray, labels, uri: Optional[str] = None) -> "Annotation":
+        """Rows must already be sorted by (start, end, track)."""
+        a = cls(uri=uri)
+        a._rows = (np.asarray(starts, dtype=np.float64), np.asarray(ends, dtype=np.float64),
+                   np.asarray(labels, dtype=object))
+        a._tracks = None
+        return a
+
+    def _materialise(self):
+        if self._tracks is None:
+            st, en, lab = self._rows
+            self._tracks = [(Segment(float(a), float(b)), i, l) for i, (a, b, l) in enumerate(zip(st, en, lab))]
+            self._sorted = True
+            self._rows = None
 
     def __setitem__(self, key, label):
         segment, track = key
-        self._tracks.append((segment, track, label))
-        self._sorted = False
+        self.add(segment, track, label)
 
     def add(self, segment: Segment, track, label):
+        self._materialise()
         self._tracks.append((segment, track, label))
         self._sorted = False
 
     def _sort(self):
+        self._materialise()
         if not self._sorted:
             self._tracks.sort(key=lambda r: (r[0].start, r[0].end))   # stable: ties keep insertion (track) order
             self._sorted = True
@@ -194,9 +215,15 @@ class Annotation:
             yield segment
 
     def labels(self):
+        if self._tracks is None:
+            return sorted(set(self._rows[2].tolist()), key=lambda v: (str(type(v)), v))
         return sorted({label for _, _, label in self._tracks}, key=lambda v: (str(type(v)), v))
 
     def rename_labels(self, mapping: dict) -> "Annotation":
+        if self._tracks is None:
+            st, en, lab = self._rows
+            new = np.array([mapping.get(l, l) for l in lab.tolist()], dtype=object) if len(lab) else lab
+            return Annotation.from_rows(st, en, new, uri=self.uri)
         out = Annotation(uri=self.uri)
         out._tracks = [(s, t, mapping.get(lab, lab)) for s, t, lab in self._tracks]
         out._sorted = self._sorted
@@ -224,10 +251,10 @@ class Annotation:
         return out
 
     def __len__(self):
-        return len(self._tracks)
+        return len(self._rows[0]) if self._tracks is None else len(self._tracks)
 
     def __bool__(self):
-        return len(self._tracks) > 0
+        return len(self) > 0
 
     def to_rttm(self) -> str:
         uri = self.uri if self.uri else "<NA>"

@@ -578,52 +578,23 @@ int b200_stats_pool(b200_ctx* ctx, const float* seq, const float* weights, float
 }
 
 // ------------------------------------------------------------------------------------------------------
-static int push_ints(b200_ctx* ctx, const void* host, size_t bytes, void** dev, cudaStream_t st) {
-  // small per-call host arrays (start frames, hard clusters) ride in the tail of the meta buffers' allocation
-  void* p = nullptr;
-  B200_CUDA_OK(cudaMallocAsync(&p, bytes + 16, st));
-  B200_CUDA_OK(cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, st));
-  *dev = p;
-  return B200_OK;
-}
-
 int b200_speaker_count(b200_ctx* ctx, const uint8_t* seg, const int32_t* start_frame, int32_t num_chunks,
                        int32_t num_frames, uint8_t* count, void* stream) {
   B200_CHECK(ctx && seg && start_frame && count && num_chunks > 0 && num_frames > 0, B200_ERR_INVALID, "bad arguments");
-  for (int c = 1; c < num_chunks; ++c)
-    B200_CHECK(start_frame[c] >= start_frame[c - 1], B200_ERR_INVALID, "start_frame must be non-decreasing");
   DeviceGuard g(ctx->device);
-  cudaStream_t st = (cudaStream_t)stream;
-  void* d_sf = nullptr;
-  int rc = push_ints(ctx, start_frame, sizeof(int) * num_chunks, &d_sf, st);
-  if (rc) return rc;
-  rc = speaker_count(seg, (const int*)d_sf, num_chunks, num_frames, count, st);
-  cudaFreeAsync(d_sf, st);
   ctx->launches += 1;
-  return rc;
+  return speaker_count(seg, start_frame, num_chunks, num_frames, count, (cudaStream_t)stream);
 }
 
 int b200_reconstruct(b200_ctx* ctx, const uint8_t* seg, const int8_t* hard_clusters, const int32_t* start_frame,
-                     int32_t num_chunks, int32_t num_frames, int32_t num_clusters, const uint8_t* count,
-                     int32_t num_clusters_out, uint8_t* discrete, void* stream) {
+                     int32_t num_chunks, int32_t num_frames, const uint8_t* count, int32_t num_clusters_out,
+                     uint8_t* discrete, void* stream) {
   B200_CHECK(ctx && seg && hard_clusters && start_frame && count && discrete && num_chunks > 0 && num_frames > 0,
              B200_ERR_INVALID, "bad arguments");
-  B200_CHECK(num_clusters_out >= num_clusters && num_clusters >= 0, B200_ERR_INVALID, "num_clusters_out < num_clusters");
-  for (int i = 0; i < num_chunks * 3; ++i)
-    B200_CHECK(hard_clusters[i] < num_clusters, B200_ERR_INVALID, "hard cluster %d >= %d", (int)hard_clusters[i],
-               num_clusters);
   DeviceGuard g(ctx->device);
-  cudaStream_t st = (cudaStream_t)stream;
-  void *d_sf = nullptr, *d_h = nullptr;
-  int rc = push_ints(ctx, start_frame, sizeof(int) * num_chunks, &d_sf, st);
-  if (rc) return rc;
-  if ((rc = push_ints(ctx, hard_clusters, (size_t)num_chunks * 3, &d_h, st))) return rc;
-  rc = reconstruct(seg, (const signed char*)d_h, (const int*)d_sf, num_chunks, num_frames, num_clusters_out, count,
-                   discrete, st);
-  cudaFreeAsync(d_sf, st);
-  cudaFreeAsync(d_h, st);
   ctx->launches += 1;
-  return rc;
+  return reconstruct(seg, (const signed char*)hard_clusters, start_frame, num_chunks, num_frames, num_clusters_out,
+                     count, discrete, (cudaStream_t)stream);
 }
 
 int b200_clean_frames(b200_ctx* ctx, const uint8_t* seg, int32_t num_chunks, int32_t* clean, uint8_t* active,
@@ -636,15 +607,24 @@ int b200_clean_frames(b200_ctx* ctx, const uint8_t* seg, int32_t num_chunks, int
 }
 
 // ------------------------------------------------------------------------------------------------------
+int b200_linkage_centroid_batched(b200_ctx* ctx, const double* x, const int32_t* row_offsets, int32_t num_problems,
+                                  int32_t dim, int32_t normalize, double* Z, void* stream) {
+  B200_CHECK(ctx && x && row_offsets && Z && num_problems >= 1 && dim >= 1, B200_ERR_INVALID, "bad arguments");
+  for (int f = 0; f < num_problems; ++f)
+    B200_CHECK(row_offsets[f + 1] >= row_offsets[f] && row_offsets[f + 1] - row_offsets[f] <= 32768, B200_ERR_INVALID,
+               "linkage: bad row offsets / problem too large");
+  DeviceGuard g(ctx->device);
+  int rc = ensure_ws(ctx, linkage_workspace_bytes_batched(row_offsets, num_problems, dim));
+  if (rc) return rc;
+  ctx->launches += 2 + num_problems;
+  return linkage_centroid_batched(x, row_offsets, num_problems, dim, normalize, Z, ctx->ws, (cudaStream_t)stream);
+}
+
 int b200_linkage_centroid(b200_ctx* ctx, const double* x, int32_t n, int32_t dim, int32_t normalize, double* Z,
                           void* stream) {
-  B200_CHECK(ctx && x && Z && n >= 2 && dim >= 1, B200_ERR_INVALID, "linkage needs at least 2 observations");
-  B200_CHECK(n <= 32768, B200_ERR_INVALID, "linkage: n=%d too large", n);
-  DeviceGuard g(ctx->device);
-  int rc = ensure_ws(ctx, linkage_workspace_bytes(n, dim));
-  if (rc) return rc;
-  ctx->launches += 2 + (normalize ? 1 : 0);
-  return linkage_centroid(x, n, dim, normalize, Z, ctx->ws, (cudaStream_t)stream);
+  B200_CHECK(n >= 2, B200_ERR_INVALID, "linkage needs at least 2 observations");
+  const int32_t offs[2] = {0, n};
+  return b200_linkage_centroid_batched(ctx, x, offs, 1, dim, normalize, Z, stream);
 }
 
 int b200_fcluster_distance(const double* Z, int32_t n, double t, int32_t* labels) {
@@ -661,15 +641,24 @@ int b200_cdist_cosine(b200_ctx* ctx, const double* a, int32_t m, const double* b
   return cdist_cosine(a, m, b, k, dim, d, (cudaStream_t)stream);
 }
 
+int b200_vbx_batched(b200_ctx* ctx, const double* fea, const double* phi, const int32_t* n, const int32_t* S,
+                     int32_t num_problems, int32_t D, double Fa, double Fb, int32_t max_iters, double epsilon,
+                     double* gamma, double* pi, int32_t* iters, void* stream) {
+  B200_CHECK(ctx && fea && phi && n && S && gamma && pi && num_problems >= 1 && D >= 1 && max_iters >= 1,
+             B200_ERR_INVALID, "bad arguments");
+  for (int f = 0; f < num_problems; ++f) B200_CHECK(n[f] >= 0 && S[f] >= 0, B200_ERR_INVALID, "negative problem size");
+  DeviceGuard g(ctx->device);
+  int rc = ensure_ws(ctx, vbx_workspace_bytes_batched(n, S, num_problems, D));
+  if (rc) return rc;
+  ctx->launches += 1;
+  return vbx_run_batched(fea, phi, n, S, num_problems, D, Fa, Fb, max_iters, epsilon, gamma, pi, iters, ctx->ws,
+                         (cudaStream_t)stream);
+}
+
 int b200_vbx(b200_ctx* ctx, const double* fea, const double* phi, int32_t n, int32_t D, int32_t S, double Fa,
              double Fb, int32_t max_iters, double epsilon, double* gamma, double* pi, int32_t* iters, void* stream) {
-  B200_CHECK(ctx && fea && phi && gamma && pi && n >= 1 && D >= 1 && S >= 1 && max_iters >= 1, B200_ERR_INVALID,
-             "bad arguments");
-  DeviceGuard g(ctx->device);
-  int rc = ensure_ws(ctx, vbx_workspace_bytes(n, D, S));
-  if (rc) return rc;
-  ctx->launches += 1 + 3 * max_iters;
-  return vbx_run(fea, phi, n, D, S, Fa, Fb, max_iters, epsilon, gamma, pi, iters, ctx->ws, (cudaStream_t)stream);
+  B200_CHECK(n >= 1 && S >= 1, B200_ERR_INVALID, "bad arguments");
+  return b200_vbx_batched(ctx, fea, phi, &n, &S, 1, D, Fa, Fb, max_iters, epsilon, gamma, pi, iters, stream);
 }
 
 int b200_assign(b200_ctx* ctx, const double* soft, int32_t num_chunks, int32_t num_clusters, int32_t constrained,

@@ -101,11 +101,33 @@ __device__ __forceinline__ void row_nn(const double* __restrict__ D, const unsig
   if (lane == 0) { nn_d[k] = m.v; nn_i[k] = m.i; }
 }
 
-__global__ void __launch_bounds__(1024) linkage_centroid_kernel(double* __restrict__ D, int n, double* __restrict__ Z,
-                                                                double* __restrict__ nn_d, int* __restrict__ nn_i,
-                                                                int* __restrict__ size, int* __restrict__ id,
-                                                                unsigned char* __restrict__ alive,
-                                                                int* __restrict__ todo) {
+struct LinkJob {
+  int n;
+  int row_off;        // offset of this problem in the per-row arrays
+  int z_off;          // row offset into Z
+  int pad;
+  long long d_off;    // element offset of this problem's n x n distance matrix
+};
+
+// one CTA per clustering problem (file): problems are independent, so a batch of files fills the machine
+__global__ void __launch_bounds__(1024) linkage_centroid_kernel(const LinkJob* __restrict__ jobs,
+                                                                double* __restrict__ Dall, double* __restrict__ Zall,
+                                                                double* __restrict__ nn_d_all,
+                                                                int* __restrict__ nn_i_all, int* __restrict__ size_all,
+                                                                int* __restrict__ id_all,
+                                                                unsigned char* __restrict__ alive_all,
+                                                                int* __restrict__ todo_all) {
+  const LinkJob job = jobs[blockIdx.x];
+  const int n = job.n;
+  if (n < 2) return;
+  double* __restrict__ D = Dall + job.d_off;
+  double* __restrict__ Z = Zall + (size_t)job.z_off * 4;
+  double* __restrict__ nn_d = nn_d_all + job.row_off;
+  int* __restrict__ nn_i = nn_i_all + job.row_off;
+  int* __restrict__ size = size_all + job.row_off;
+  int* __restrict__ id = id_all + job.row_off;
+  unsigned char* __restrict__ alive = alive_all + job.row_off;
+  int* __restrict__ todo = todo_all + job.row_off + blockIdx.x;     // n + 1 entries per problem
   __shared__ MinPair s_red[32];
   __shared__ int s_x, s_y, s_ntodo;
   __shared__ double s_dxy;
@@ -196,137 +218,140 @@ __global__ void cdist_cosine_kernel(const double* __restrict__ a, int m, const d
 }
 
 // ------------------------------------------------------------------------------------------------------
-// VBx
+// VBx: one persistent CTA per clustering problem runs all iterations (utils/vbx.py:98-136)
 // ------------------------------------------------------------------------------------------------------
-struct VbxBuf {
-  double *rho, *G, *Ng, *alpha, *invL, *cst, *lpx, *elbo;   // elbo[0]=prev, [1]=cur, [2]=done flag (as double)
-  int* iters;
+struct VbxJob {
+  int n, S;
+  int fea_off;        // row offset into fea / rho / G / lpx
+  int pad;
+  long long gam_off;  // element offset into gamma
+  int pi_off;         // element offset into pi / Ng / cst
+  int mod_off;        // row offset (in units of D) into alpha / invL  (= pi_off)
 };
 
-__global__ void vbx_prep_kernel(const double* __restrict__ X, const double* __restrict__ phi, int n, int D,
-                                double* __restrict__ rho, double* __restrict__ G) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double s = 0.0;
-  for (int d = 0; d < D; ++d) {
-    const double x = X[(size_t)i * D + d];
-    s += x * x;
-    rho[(size_t)i * D + d] = x * sqrt(phi[d]);
+__device__ __forceinline__ double block_sum_1024(double v, double* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x < 32) {
+    t = red[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) red[32] = t;
   }
-  G[i] = -0.5 * (s + D * log(2.0 * M_PI));
+  __syncthreads();
+  return red[32];
 }
 
-// speaker models: Ng[s] = sum_n gamma[n][s];  alpha[s][d] = FaFb * invL * sum_n gamma[n][s] rho[n][d]
-__global__ void vbx_model_kernel(const double* __restrict__ gamma, const double* __restrict__ rho,
-                                 const double* __restrict__ phi, int n, int D, int S, double FaFb,
-                                 double* __restrict__ alpha, double* __restrict__ invL, double* __restrict__ cst,
-                                 const double* __restrict__ elbo) {
-  if (elbo[2] != 0.0) return;
-  const int s = blockIdx.x;                 // one block per speaker, threads over d
-  __shared__ double s_ng;
-  __shared__ double red[8];
-  double ng = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) ng += gamma[(size_t)i * S + s];
-  for (int o = 16; o > 0; o >>= 1) ng += __shfl_xor_sync(0xffffffffu, ng, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ng;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0;
-    for (int w = 0; w < blockDim.x / 32; ++w) t += red[w];
-    s_ng = t;
-  }
-  __syncthreads();
-  double c_part = 0.0;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    double acc = 0.0;
-    for (int i = 0; i < n; ++i) acc += gamma[(size_t)i * S + s] * rho[(size_t)i * D + d];
-    const double il = 1.0 / (1.0 + FaFb * s_ng * phi[d]);
-    const double al = FaFb * il * acc;
-    invL[s * D + d] = il;
-    alpha[s * D + d] = al;
-    c_part += (il + al * al) * phi[d];
-  }
-  __syncthreads();
-  for (int o = 16; o > 0; o >>= 1) c_part += __shfl_xor_sync(0xffffffffu, c_part, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c_part;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0;
-    for (int w = 0; w < blockDim.x / 32; ++w) t += red[w];
-    cst[s] = -0.5 * t;
-  }
-}
+__global__ void __launch_bounds__(1024) vbx_kernel(const VbxJob* __restrict__ jobs, const double* __restrict__ fea_all,
+                                                   const double* __restrict__ phi, int D, double Fa, double Fb,
+                                                   int max_iters, double epsilon, double* __restrict__ gamma_all,
+                                                   double* __restrict__ pi_all, double* __restrict__ rho_all,
+                                                   double* __restrict__ G_all, double* __restrict__ lpx_all,
+                                                   double* __restrict__ alpha_all, double* __restrict__ invL_all,
+                                                   double* __restrict__ cst_all, int* __restrict__ iters_all) {
+  const VbxJob job = jobs[blockIdx.x];
+  const int n = job.n, S = job.S;
+  if (n <= 0 || S <= 0) return;
+  const double* X = fea_all + (size_t)job.fea_off * D;
+  double* rho = rho_all + (size_t)job.fea_off * D;
+  double* G = G_all + job.fea_off;
+  double* lpx = lpx_all + job.fea_off;
+  double* gamma = gamma_all + job.gam_off;
+  double* pi = pi_all + job.pi_off;
+  double* cst = cst_all + job.pi_off;
+  double* alpha = alpha_all + (size_t)job.mod_off * D;
+  double* invL = invL_all + (size_t)job.mod_off * D;
+  __shared__ double red[33];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double FaFb = Fa / Fb;
 
-// responsibilities: one warp per frame n
-__global__ void vbx_resp_kernel(const double* __restrict__ rho, const double* __restrict__ G,
-                                const double* __restrict__ alpha, const double* __restrict__ cst,
-                                const double* __restrict__ pi, int n, int D, int S, double Fa,
-                                double* __restrict__ gamma, double* __restrict__ lpx, const double* __restrict__ elbo) {
-  if (elbo[2] != 0.0) return;
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (i >= n) return;
-  double mx = -DBL_MAX;
-  for (int s = lane; s < S; s += 32) {
-    double dot = 0.0;
-    for (int d = 0; d < D; ++d) dot += rho[(size_t)i * D + d] * alpha[s * D + d];
-    const double v = Fa * (dot + cst[s] + G[i]) + log(pi[s] + 1e-8);
-    gamma[(size_t)i * S + s] = v;
-    mx = fmax(mx, v);
+  // rho = X * sqrt(phi);  G = -0.5 * (|x|^2 + D log(2 pi))    (one warp per frame)
+  for (int i = warp; i < n; i += 32) {
+    double s = 0.0;
+    for (int d = lane; d < D; d += 32) {
+      const double x = X[(size_t)i * D + d];
+      s += x * x;
+      rho[(size_t)i * D + d] = x * sqrt(phi[d]);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) G[i] = -0.5 * (s + D * log(2.0 * M_PI));
   }
-  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  double se = 0.0;
-  for (int s = lane; s < S; s += 32) se += exp(gamma[(size_t)i * S + s] - mx);
-  for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
-  const double lse = log(se) + mx;
-  for (int s = lane; s < S; s += 32) gamma[(size_t)i * S + s] = exp(gamma[(size_t)i * S + s] - lse);
-  if (lane == 0) lpx[i] = lse;
-}
+  for (int s = tid; s < S; s += 1024) pi[s] = 1.0 / S;
+  __syncthreads();
 
-// priors, ELBO, convergence (single block)
-__global__ void vbx_finish_kernel(const double* __restrict__ gamma, const double* __restrict__ lpx,
-                                  const double* __restrict__ alpha, const double* __restrict__ invL, int n, int D,
-                                  int S, double Fb, double epsilon, int it, double* __restrict__ pi,
-                                  double* __restrict__ elbo, int* __restrict__ iters) {
-  if (elbo[2] != 0.0) return;
-  __shared__ double red[32];
-  __shared__ double s_tot;
-  auto block_sum = [&](double v) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = 0;
-    if (threadIdx.x == 0) {
-      for (int w = 0; w < blockDim.x / 32; ++w) t += red[w];
-      s_tot = t;
+  double prev = 0.0;
+  int it = 0;
+  for (; it < max_iters; ++it) {
+    // speaker models: one (s, d) pair per thread
+    for (int e = tid; e < S * D; e += 1024) {
+      const int s = e / D, d = e - s * D;
+      double ng = 0.0, acc = 0.0;
+      for (int i = 0; i < n; ++i) {
+        const double g = gamma[(size_t)i * S + s];
+        ng += g;
+        acc += g * rho[(size_t)i * D + d];
+      }
+      const double il = 1.0 / (1.0 + FaFb * ng * phi[d]);
+      invL[e] = il;
+      alpha[e] = FaFb * il * acc;
     }
     __syncthreads();
-    return s_tot;
-  };
-  double tot = 0.0;
-  for (int s = 0; s < S; ++s) {
-    double c = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) c += gamma[(size_t)i * S + s];
-    c = block_sum(c);
-    if (threadIdx.x == 0) pi[s] = c;
-    tot += c;
-  }
-  __syncthreads();
-  for (int s = threadIdx.x; s < S; s += blockDim.x) pi[s] = pi[s] / tot;
-  double l = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) l += lpx[i];
-  l = block_sum(l);
-  double r = 0.0;
-  for (int e = threadIdx.x; e < S * D; e += blockDim.x) r += log(invL[e]) - invL[e] - alpha[e] * alpha[e] + 1.0;
-  r = block_sum(r);
-  if (threadIdx.x == 0) {
+    for (int s = warp; s < S; s += 32) {
+      double c = 0.0;
+      for (int d = lane; d < D; d += 32) {
+        const double al = alpha[s * D + d];
+        c += (invL[s * D + d] + al * al) * phi[d];
+      }
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (lane == 0) cst[s] = -0.5 * c;
+    }
+    __syncthreads();
+    // responsibilities: one warp per frame
+    for (int i = warp; i < n; i += 32) {
+      double mx = -DBL_MAX;
+      for (int s = 0; s < S; ++s) {
+        double dot = 0.0;
+        for (int d = lane; d < D; d += 32) dot += rho[(size_t)i * D + d] * alpha[s * D + d];
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        const double v = Fa * (dot + cst[s] + G[i]) + log(pi[s] + 1e-8);
+        if (lane == 0) gamma[(size_t)i * S + s] = v;
+        mx = fmax(mx, v);
+      }
+      __syncwarp();
+      double se = 0.0;
+      for (int s = lane; s < S; s += 32) se += exp(gamma[(size_t)i * S + s] - mx);
+      for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+      const double lse = log(se) + mx;
+      for (int s = lane; s < S; s += 32) gamma[(size_t)i * S + s] = exp(gamma[(size_t)i * S + s] - lse);
+      if (lane == 0) lpx[i] = lse;
+    }
+    __syncthreads();
+    // priors
+    double tot = 0.0;
+    for (int s = 0; s < S; ++s) {
+      double c = 0.0;
+      for (int i = tid; i < n; i += 1024) c += gamma[(size_t)i * S + s];
+      c = block_sum_1024(c, red);
+      if (tid == 0) pi[s] = c;
+      tot += c;
+    }
+    __syncthreads();
+    for (int s = tid; s < S; s += 1024) pi[s] = pi[s] / tot;
+    // ELBO (vbx.py:130)
+    double l = 0.0;
+    for (int i = tid; i < n; i += 1024) l += lpx[i];
+    l = block_sum_1024(l, red);
+    double r = 0.0;
+    for (int e = tid; e < S * D; e += 1024) r += log(invL[e]) - invL[e] - alpha[e] * alpha[e] + 1.0;
+    r = block_sum_1024(r, red);
     const double E = l + Fb * 0.5 * r;
-    const double prev = elbo[1];
-    elbo[0] = prev;
-    elbo[1] = E;
-    *iters = it + 1;
-    if (it > 0 && E - prev < epsilon) elbo[2] = 1.0;
+    __syncthreads();
+    if (it > 0 && E - prev < epsilon) { ++it; break; }
+    prev = E;
   }
+  if (tid == 0) iters_all[blockIdx.x] = it;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -378,28 +403,56 @@ __global__ void assign_kernel(const double* __restrict__ soft, int C, int K, int
 // ------------------------------------------------------------------------------------------------------
 // host wrappers
 // ------------------------------------------------------------------------------------------------------
-size_t linkage_workspace_bytes(int n, int dim) {
-  return align_up((size_t)n * n * 8, 256) + align_up((size_t)n * dim * 8, 256) + (size_t)n * 64 + 4096;
+size_t linkage_workspace_bytes_batched(const int* row_offsets, int nfiles, int dim) {
+  size_t d = 0;
+  const int ntot = row_offsets[nfiles];
+  for (int f = 0; f < nfiles; ++f) {
+    const size_t n = row_offsets[f + 1] - row_offsets[f];
+    d += n * n;
+  }
+  return align_up(d * 8, 256) + align_up((size_t)ntot * dim * 8, 256) + (size_t)(ntot + nfiles + 64) * 40 +
+         (size_t)nfiles * sizeof(LinkJob) + 8192;
 }
 
-int linkage_centroid(const double* x, int n, int dim, int normalize, double* Z, void* ws, cudaStream_t st) {
+int linkage_centroid_batched(const double* x, const int* row_offsets, int nfiles, int dim, int normalize, double* Z,
+                             void* ws, cudaStream_t st) {
+  const int ntot = row_offsets[nfiles];
+  std::vector<LinkJob> jobs(nfiles);
+  size_t d = 0;
+  int z = 0;
+  for (int f = 0; f < nfiles; ++f) {
+    const int n = row_offsets[f + 1] - row_offsets[f];
+    jobs[f].n = n;
+    jobs[f].row_off = row_offsets[f];
+    jobs[f].z_off = z;
+    jobs[f].pad = 0;
+    jobs[f].d_off = (long long)d;
+    d += (size_t)n * n;
+    z += n > 1 ? n - 1 : 0;
+  }
   char* p = (char*)ws;
-  double* D = (double*)p; p += align_up((size_t)n * n * 8, 256);
-  double* xn = (double*)p; p += align_up((size_t)n * dim * 8, 256);
-  double* nn_d = (double*)p; p += align_up((size_t)n * 8, 256);
-  int* nn_i = (int*)p; p += align_up((size_t)n * 4, 256);
-  int* size = (int*)p; p += align_up((size_t)n * 4, 256);
-  int* id = (int*)p; p += align_up((size_t)n * 4, 256);
-  int* todo = (int*)p; p += align_up((size_t)n * 4 + 4, 256);
-  unsigned char* alive = (unsigned char*)p;
+  double* D = (double*)p; p += align_up(d * 8, 256);
+  double* xn = (double*)p; p += align_up((size_t)ntot * dim * 8, 256);
+  double* nn_d = (double*)p; p += align_up((size_t)ntot * 8, 256);
+  int* nn_i = (int*)p; p += align_up((size_t)ntot * 4, 256);
+  int* size = (int*)p; p += align_up((size_t)ntot * 4, 256);
+  int* id = (int*)p; p += align_up((size_t)ntot * 4, 256);
+  int* todo = (int*)p; p += align_up((size_t)(ntot + nfiles + 1) * 4, 256);
+  unsigned char* alive = (unsigned char*)p; p += align_up((size_t)ntot, 256);
+  LinkJob* djobs = (LinkJob*)p;
+  B200_CUDA_OK(cudaMemcpyAsync(djobs, jobs.data(), sizeof(LinkJob) * nfiles, cudaMemcpyHostToDevice, st));
   const double* src = x;
-  if (normalize) {
-    normalize_rows_kernel<<<n, 128, 0, st>>>(x, xn, n, dim);
+  if (normalize && ntot > 0) {
+    normalize_rows_kernel<<<ntot, 128, 0, st>>>(x, xn, ntot, dim);
     src = xn;
   }
-  dim3 grid(ceil_div(n, 16), ceil_div(n, 16));
-  pdist_kernel<<<grid, dim3(16, 16), 0, st>>>(src, D, n, dim);
-  linkage_centroid_kernel<<<1, 1024, 0, st>>>(D, n, Z, nn_d, nn_i, size, id, alive, todo);
+  for (int f = 0; f < nfiles; ++f) {
+    const int n = jobs[f].n;
+    if (n < 2) continue;
+    dim3 grid(ceil_div(n, 16), ceil_div(n, 16));
+    pdist_kernel<<<grid, dim3(16, 16), 0, st>>>(src + (size_t)jobs[f].row_off * dim, D + jobs[f].d_off, n, dim);
+  }
+  linkage_centroid_kernel<<<nfiles, 1024, 0, st>>>(djobs, D, Z, nn_d, nn_i, size, id, alive, todo);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }
@@ -410,35 +463,38 @@ int cdist_cosine(const double* a, int m, const double* b, int k, int dim, double
   return B200_OK;
 }
 
-size_t vbx_workspace_bytes(int n, int D, int S) {
-  return ((size_t)n * D + n + S + 2 * (size_t)S * D + S + n + 8) * 8 + 4096 + 64;
+size_t vbx_workspace_bytes_batched(const int* n, const int* S, int nfiles, int D) {
+  size_t ntot = 0, stot = 0;
+  for (int f = 0; f < nfiles; ++f) { ntot += n[f]; stot += S[f]; }
+  return (ntot * D + 2 * ntot + 2 * stot * D + stot + 64) * 8 + (size_t)nfiles * (sizeof(VbxJob) + 4) + 8192;
 }
 
-int vbx_run(const double* fea, const double* phi, int n, int D, int S, double Fa, double Fb, int max_iters,
-            double epsilon, double* gamma, double* pi, int* iters_host, void* ws, cudaStream_t st) {
-  double* p = (double*)ws;
-  double* rho = p; p += (size_t)n * D;
-  double* G = p; p += n;
-  double* alpha = p; p += (size_t)S * D;
-  double* invL = p; p += (size_t)S * D;
-  double* cst = p; p += S;
-  double* lpx = p; p += n;
-  double* elbo = p; p += 4;
-  int* iters = (int*)p;
-  B200_CUDA_OK(cudaMemsetAsync(elbo, 0, 4 * 8 + 8, st));
-  vbx_prep_kernel<<<ceil_div(n, 128), 128, 0, st>>>(fea, phi, n, D, rho, G);
-  // pi init = 1/S (utils/vbx.py:93-94)
-  std::vector<double> pi0(S, 1.0 / S);
-  B200_CUDA_OK(cudaMemcpyAsync(pi, pi0.data(), S * 8, cudaMemcpyHostToDevice, st));
-  B200_CUDA_OK(cudaStreamSynchronize(st));   // pi0 is a stack-lifetime host buffer
-  for (int it = 0; it < max_iters; ++it) {
-    vbx_model_kernel<<<S, 128, 0, st>>>(gamma, rho, phi, n, D, S, Fa / Fb, alpha, invL, cst, elbo);
-    vbx_resp_kernel<<<ceil_div(n * 32, 256), 256, 0, st>>>(rho, G, alpha, cst, pi, n, D, S, Fa, gamma, lpx, elbo);
-    vbx_finish_kernel<<<1, 1024, 0, st>>>(gamma, lpx, alpha, invL, n, D, S, Fb, epsilon, it, pi, elbo, iters);
+// fea [sum n][D], gamma concatenated per problem ([n_f][S_f] row-major), pi concatenated ([S_f])
+int vbx_run_batched(const double* fea, const double* phi, const int* n, const int* S, int nfiles, int D, double Fa,
+                    double Fb, int max_iters, double epsilon, double* gamma, double* pi, int* iters_host, void* ws,
+                    cudaStream_t st) {
+  std::vector<VbxJob> jobs(nfiles);
+  size_t ntot = 0, stot = 0, gtot = 0;
+  for (int f = 0; f < nfiles; ++f) {
+    jobs[f].n = n[f]; jobs[f].S = S[f]; jobs[f].fea_off = (int)ntot; jobs[f].pad = 0;
+    jobs[f].gam_off = (long long)gtot; jobs[f].pi_off = (int)stot; jobs[f].mod_off = (int)stot;
+    ntot += n[f]; stot += S[f]; gtot += (size_t)n[f] * S[f];
   }
+  double* p = (double*)ws;
+  double* rho = p; p += ntot * D;
+  double* G = p; p += ntot;
+  double* lpx = p; p += ntot;
+  double* alpha = p; p += stot * D;
+  double* invL = p; p += stot * D;
+  double* cst = p; p += stot + 8;
+  VbxJob* djobs = (VbxJob*)p;
+  int* iters = (int*)(djobs + nfiles);
+  B200_CUDA_OK(cudaMemcpyAsync(djobs, jobs.data(), sizeof(VbxJob) * nfiles, cudaMemcpyHostToDevice, st));
+  vbx_kernel<<<nfiles, 1024, 0, st>>>(djobs, fea, phi, D, Fa, Fb, max_iters, epsilon, gamma, pi, rho, G, lpx, alpha,
+                                      invL, cst, iters);
   B200_CUDA_OK(cudaGetLastError());
   if (iters_host) {
-    B200_CUDA_OK(cudaMemcpyAsync(iters_host, iters, sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CUDA_OK(cudaMemcpyAsync(iters_host, iters, sizeof(int) * nfiles, cudaMemcpyDeviceToHost, st));
     B200_CUDA_OK(cudaStreamSynchronize(st));
   }
   return B200_OK;

@@ -87,6 +87,31 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// One lane of the (converged) warp; the tcgen05 / TMA instructions take warp-uniform operands, so the role loops are
+// executed by the whole warp and only the issue itself is predicated on the elected lane.  (A single-lane divergent
+// loop makes the compiler emit ELECT/BRA.U.ANY "for each active lane" sequences around every such instruction:
+// ncu showed the MMA warp issue-bound at ~550 cycles per k-block.)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+
+// 64-bit UMMA descriptor from its constant high word and a low word (start address >> 4 | LBO field)
+__device__ __forceinline__ uint64_t desc_from(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return (sbo_bytes >> 4) | (1u << 14) | (layout_type << 29);
+}
+
 // UMMA shared-memory descriptor, K-major, hardware swizzle (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 //   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout type
 __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
@@ -151,54 +176,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int ksteps = p.Ck / 16;
 
   if (warp == 0) {
-    if (lane == 0) {
+    const bool leader = elect_one_sync();
+    if (leader) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int wt = tile % p.tiles_w;
-        const int bh = tile / p.tiles_w;
-        const int h = bh % p.H_out;
-        const int b = bh / p.H_out;
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          const int tap = kb / cchunks, cc = kb - tap * cchunks;
-          const int kh = tap / p.taps_w, kw = tap - kh * p.taps_w;
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+    }
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int wt = tile % p.tiles_w;
+      const int bh = tile / p.tiles_w;
+      const int h = bh % p.H_out;
+      const int b = bh / p.H_out;
+      const int w_base = wt * kTileM * p.stride - p.pad, h_base = h * p.stride - p.pad;
+      int tap = 0, cc = 0, kh = 0, kw = 0;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (leader) {
           mbar_expect_tx(bar_full + 8 * stage, stage_bytes);
           const uint32_t sa = stage0 + stage * stage_bytes;
-          tma_load_4d(&tmA, bar_full + 8 * stage, sa, cc * p.Ck, wt * kTileM * p.stride + kw - p.pad,
-                      h * p.stride + kh - p.pad, b);
+          tma_load_4d(&tmA, bar_full + 8 * stage, sa, cc * p.Ck, w_base + kw, h_base + kh, b);
           tma_load_3d(&tmB, bar_full + 8 * stage, sa + p.a_bytes, cc * p.Ck, 0, tap);
-          if (++stage == p.nstages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+        if (++cc == cchunks) { cc = 0; ++tap; if (++kw == p.taps_w) { kw = 0; ++kh; } }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      const uint32_t sbo = (p.swizzle == 128) ? 1024u : 512u;
-      const uint32_t ltype = (p.swizzle == 128) ? 2u : 4u;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+    const bool leader = elect_one_sync();
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    const uint32_t dhi = desc_hi((p.swizzle == 128) ? 1024u : 512u, (p.swizzle == 128) ? 2u : 4u);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * (uint32_t)N;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (uint32_t)N;
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          tc_fence_after();
+        if (leader) {
           const uint32_t sa = stage0 + stage * stage_bytes;
-          const uint64_t adesc = make_kmajor_desc(sa, sbo, ltype);
-          const uint64_t bdesc = make_kmajor_desc(sa + p.a_bytes, sbo, ltype);
-          for (int k = 0; k < ksteps; ++k) {
-            // +32 B per K=16 step inside the swizzle row: start-address field is in 16 B units
-            tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb | k) != 0);
+          const uint32_t alo = desc_lo(sa), blo = desc_lo(sa + p.a_bytes);
+          // +32 B per K=16 step inside the swizzle row: the start-address field is in 16 B units
+          tc_mma_f16(d_tmem, desc_from(dhi, alo), desc_from(dhi, blo), p.idesc, kb != 0);
+          tc_mma_f16(d_tmem, desc_from(dhi, alo + 2), desc_from(dhi, blo + 2), p.idesc, 1);
+          if (ksteps == 4) {
+            tc_mma_f16(d_tmem, desc_from(dhi, alo + 4), desc_from(dhi, blo + 4), p.idesc, 1);
+            tc_mma_f16(d_tmem, desc_from(dhi, alo + 6), desc_from(dhi, blo + 6), p.idesc, 1);
           }
           tc_commit(bar_empty + 8 * stage);   // frees the smem stage once these MMAs have read it
-          if (++stage == p.nstages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(bar_tfull + 8 * acc);       // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == p.nstages) { stage = 0; phase ^= 1; }
       }
+      if (leader) tc_commit(bar_tfull + 8 * acc);   // accumulator complete -> epilogue
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     const int q = warp & 3;                   // TMEM lane quadrant this warp may access
@@ -341,7 +374,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    const bool leader = elect_one_sync();
+    if (leader) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
       if (p.resident) {
@@ -350,28 +384,35 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int cc = 0; cc < p.ncc; ++cc)
             tma_load_3d(&tmB, bar_w, w_smem + (tap * p.ncc + cc) * p.b_bytes, cc * p.Ck, 0, tap);
       }
-      uint32_t as = 0, aph = 0, bs = 0, bph = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        int b, wt, h0, h1, nh;
-        decode(item, b, wt, h0, h1, nh);
-        const int R = h1 - h0;
-        for (int t = 0; t < R + 2; ++t) {
-          for (int cc = 0; cc < p.ncc; ++cc) {
-            mbar_wait(bar_aempty + 8 * as, aph ^ 1);
+    }
+    __syncwarp();
+    uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int b, wt, h0, h1, nh;
+      decode(item, b, wt, h0, h1, nh);
+      const int R = h1 - h0;
+      const int w_in = wt * kTileM - 1;
+      for (int t = 0; t < R + 2; ++t) {
+        for (int cc = 0; cc < p.ncc; ++cc) {
+          mbar_wait(bar_aempty + 8 * as, aph ^ 1);
+          if (leader) {
             mbar_expect_tx(bar_afull + 8 * as, p.a_bytes);
-            tma_load_4d(&tmA, bar_afull + 8 * as, a_smem + as * p.a_slot_bytes, cc * p.Ck, wt * kTileM - 1,
-                        h0 - 1 + t, b);
-            if (++as == (uint32_t)p.n_aslots) { as = 0; aph ^= 1; }
-            if (!p.resident) {
-              for (int kh = 0; kh < 3; ++kh) {
-                const int r = t - kh;
-                if (r < 0 || r >= R) continue;
-                for (int kw = 0; kw < 3; ++kw) {
-                  mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
+            tma_load_4d(&tmA, bar_afull + 8 * as, a_smem + as * p.a_slot_bytes, cc * p.Ck, w_in, h0 - 1 + t, b);
+          }
+          __syncwarp();
+          if (++as == (uint32_t)p.n_aslots) { as = 0; aph ^= 1; }
+          if (!p.resident) {
+            for (int kh = 0; kh < 3; ++kh) {
+              const int r = t - kh;
+              if (r < 0 || r >= R) continue;
+              for (int kw = 0; kw < 3; ++kw) {
+                mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
+                if (leader) {
                   mbar_expect_tx(bar_bfull + 8 * bs, p.b_bytes);
                   tma_load_3d(&tmB, bar_bfull + 8 * bs, b_smem + bs * p.b_bytes, cc * p.Ck, nh * N, kh * 3 + kw);
-                  if (++bs == (uint32_t)p.n_bslots) { bs = 0; bph ^= 1; }
                 }
+                __syncwarp();
+                if (++bs == (uint32_t)p.n_bslots) { bs = 0; bph ^= 1; }
               }
             }
           }
@@ -379,57 +420,67 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t sbo = (p.swizzle == 128) ? 1024u : 512u;
-      const uint32_t ltype = (p.swizzle == 128) ? 2u : 4u;
-      if (p.resident) { mbar_wait(bar_w, 0); tc_fence_after(); }
-      uint32_t as = 0, aph = 0, bs = 0, bph = 0;
-      uint32_t grow = 0;                                  // global output-row counter of this CTA
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        int b, wt, h0, h1, nh;
-        decode(item, b, wt, h0, h1, nh);
-        const int R = h1 - h0;
-        for (int t = 0; t < R + 2; ++t) {
-          for (int cc = 0; cc < p.ncc; ++cc) {
-            mbar_wait(bar_afull + 8 * as, aph);
-            tc_fence_after();
-            const uint32_t sa = a_smem + as * p.a_slot_bytes;
-            for (int kh = 0; kh < 3; ++kh) {
-              const int r = t - kh;
-              if (r < 0 || r >= R) continue;
-              const uint32_t g = grow + (uint32_t)r;
-              const uint32_t acc = g & 3u;
-              if (kh == 0 && cc == 0) {                   // first contribution to output row r
-                mbar_wait(bar_tempty + 8 * acc, ((g >> 2) & 1u) ^ 1u);
-                tc_fence_after();
-              }
-              const uint32_t d_tmem = tmem_base + acc * (uint32_t)N;
-              for (int kw = 0; kw < 3; ++kw) {
-                uint32_t sb;
-                if (p.resident) {
-                  sb = w_smem + ((kh * 3 + kw) * p.ncc + cc) * p.b_bytes;
-                } else {
-                  mbar_wait(bar_bfull + 8 * bs, bph);
-                  tc_fence_after();
-                  sb = b_smem + bs * p.b_bytes;
-                }
-                const uint64_t adesc = make_kmajor_desc_bo(sa + kw * rowbytes, sbo, ltype, p.base_off_mode);
-                const uint64_t bdesc = make_kmajor_desc(sb, sbo, ltype);
-                for (int k = 0; k < ksteps; ++k)
-                  tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kh | cc | kw | k) != 0);
-                if (!p.resident) {
-                  tc_commit(bar_bempty + 8 * bs);
-                  if (++bs == (uint32_t)p.n_bslots) { bs = 0; bph ^= 1; }
-                }
-              }
-              if (kh == 2 && cc == p.ncc - 1) tc_commit(bar_tfull + 8 * acc);   // output row r complete
+    const bool leader = elect_one_sync();
+    const uint32_t dhi = desc_hi((p.swizzle == 128) ? 1024u : 512u, (p.swizzle == 128) ? 2u : 4u);
+    const uint32_t row_units = rowbytes >> 4;             // one pixel row of the slot, in 16 B descriptor units
+    if (p.resident) { mbar_wait(bar_w, 0); tc_fence_after(); }
+    uint32_t as = 0, aph = 0, bs = 0, bph = 0;
+    uint32_t grow = 0;                                    // global output-row counter of this CTA
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int b, wt, h0, h1, nh;
+      decode(item, b, wt, h0, h1, nh);
+      const int R = h1 - h0;
+      for (int t = 0; t < R + 2; ++t) {
+        for (int cc = 0; cc < p.ncc; ++cc) {
+          mbar_wait(bar_afull + 8 * as, aph);
+          tc_fence_after();
+          const uint32_t alo0 = desc_lo(a_smem + as * p.a_slot_bytes);
+          for (int kh = 0; kh < 3; ++kh) {
+            const int r = t - kh;
+            if (r < 0 || r >= R) continue;
+            const uint32_t g = grow + (uint32_t)r;
+            const uint32_t acc = g & 3u;
+            if (kh == 0 && cc == 0) {                     // first contribution to output row r
+              mbar_wait(bar_tempty + 8 * acc, ((g >> 2) & 1u) ^ 1u);
+              tc_fence_after();
             }
-            tc_commit(bar_aempty + 8 * as);
-            if (++as == (uint32_t)p.n_aslots) { as = 0; aph ^= 1; }
+            const uint32_t d_tmem = tmem_base + acc * (uint32_t)N;
+            for (int kw = 0; kw < 3; ++kw) {
+              uint32_t blo;
+              if (p.resident) {
+                blo = desc_lo(w_smem + ((kh * 3 + kw) * p.ncc + cc) * p.b_bytes);
+              } else {
+                mbar_wait(bar_bfull + 8 * bs, bph);
+                tc_fence_after();
+                blo = desc_lo(b_smem + bs * p.b_bytes);
+              }
+              if (leader) {
+                // tap kw = same slot, kw pixel rows further (absolute-address swizzle: base_offset stays 0)
+                const uint32_t alo = alo0 + kw * row_units;
+                tc_mma_f16(d_tmem, desc_from(dhi, alo), desc_from(dhi, blo), p.idesc, (kh | cc | kw) != 0);
+                tc_mma_f16(d_tmem, desc_from(dhi, alo + 2), desc_from(dhi, blo + 2), p.idesc, 1);
+                if (ksteps == 4) {
+                  tc_mma_f16(d_tmem, desc_from(dhi, alo + 4), desc_from(dhi, blo + 4), p.idesc, 1);
+                  tc_mma_f16(d_tmem, desc_from(dhi, alo + 6), desc_from(dhi, blo + 6), p.idesc, 1);
+                }
+                if (!p.resident) tc_commit(bar_bempty + 8 * bs);
+              }
+              __syncwarp();
+              if (!p.resident) {
+                if (++bs == (uint32_t)p.n_bslots) { bs = 0; bph ^= 1; }
+              }
+            }
+            if (kh == 2 && cc == p.ncc - 1) {             // output row r complete
+              if (leader) tc_commit(bar_tfull + 8 * acc);
+              __syncwarp();
+            }
           }
+          if (leader) tc_commit(bar_aempty + 8 * as);
+          __syncwarp();
+          if (++as == (uint32_t)p.n_aslots) { as = 0; aph ^= 1; }
         }
-        grow += (uint32_t)R;
       }
+      grow += (uint32_t)R;
     }
   } else {
     const int q = warp & 3;

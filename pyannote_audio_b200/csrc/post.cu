@@ -65,50 +65,53 @@ int speaker_count(const unsigned char* seg, const int* sf, int C, int F, unsigne
 
 constexpr int kMaxK = 32;
 
-__global__ void reconstruct_kernel(const unsigned char* __restrict__ seg, const signed char* __restrict__ hard,
-                                   const int* __restrict__ sf, int C, int F, int Kout,
-                                   const unsigned char* __restrict__ count, unsigned char* __restrict__ out) {
+// KMAX is a compile-time bound so that the per-frame activation counters stay in registers (static indexing).
+template <int KMAX>
+__global__ void __launch_bounds__(128) reconstruct_kernel(const unsigned char* __restrict__ seg,
+                                                          const signed char* __restrict__ hard,
+                                                          const int* __restrict__ sf, int C, int F, int Kout,
+                                                          const unsigned char* __restrict__ count,
+                                                          unsigned char* __restrict__ out) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
-  int act[kMaxK];
+  int act[KMAX];
 #pragma unroll
-  for (int k = 0; k < kMaxK; ++k) act[k] = 0;
+  for (int k = 0; k < KMAX; ++k) act[k] = 0;
   for (int c = first_chunk(sf, C, f); c < C && sf[c] <= f; ++c) {
     const unsigned char* p = seg + ((size_t)c * kFrames + (f - sf[c])) * 3;
-    const signed char* h = hard + c * 3;
-    // per cluster: max over the local speakers mapped to it (values are 0/1 -> OR), then summed over chunks
-    int mk[3];
-    int nm = 0;
-    for (int s = 0; s < 3; ++s) {
-      const int k = h[s];
-      if (k < 0) continue;
-      bool seen = false;
-      for (int j = 0; j < nm; ++j) seen |= (mk[j] == k);
-      if (seen) continue;
-      mk[nm++] = k;
-      int v = 0;
-      for (int s2 = s; s2 < 3; ++s2)
-        if (h[s2] == k) v |= p[s2];
+    const int h0 = hard[c * 3 + 0], h1 = hard[c * 3 + 1], h2 = hard[c * 3 + 2];
+    const int p0 = p[0], p1 = p[1], p2 = p[2];
+    // per cluster: max over the local speakers mapped to it (0/1 values -> OR), summed over chunks
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int v = ((h0 == k) ? p0 : 0) | ((h1 == k) ? p1 : 0) | ((h2 == k) ? p2 : 0);
       act[k] += v;
     }
   }
   const int cnt = count[f];
-  unsigned used = 0;
-  unsigned char* o = out + (size_t)f * Kout;
-  for (int k = 0; k < Kout; ++k) o[k] = 0;
+  unsigned used = 0, sel = 0;
   for (int i = 0; i < cnt && i < Kout; ++i) {
-    int best = -1, bv = -1;
-    for (int k = 0; k < Kout; ++k)
-      if (!((used >> k) & 1u) && act[k] > bv) { bv = act[k]; best = k; }   // ties -> lowest cluster index
+    int best = 0, bv = -1;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const bool ok = (k < Kout) && !((used >> k) & 1u) && act[k] > bv;   // ties -> lowest cluster index
+      bv = ok ? act[k] : bv;
+      best = ok ? k : best;
+    }
     used |= 1u << best;
-    o[best] = 1;
+    sel |= 1u << best;
   }
+  unsigned char* o = out + (size_t)f * Kout;
+  for (int k = 0; k < Kout; ++k) o[k] = (sel >> k) & 1u;
 }
 
 int reconstruct(const unsigned char* seg, const signed char* hard, const int* sf, int C, int F, int Kout,
                 const unsigned char* count, unsigned char* out, cudaStream_t stream) {
   B200_CHECK(Kout >= 1 && Kout <= kMaxK, B200_ERR_INVALID, "reconstruct: %d clusters unsupported (max %d)", Kout, kMaxK);
-  reconstruct_kernel<<<ceil_div(F, 128), 128, 0, stream>>>(seg, hard, sf, C, F, Kout, count, out);
+  const int grid = ceil_div(F, 128);
+  if (Kout <= 8) reconstruct_kernel<8><<<grid, 128, 0, stream>>>(seg, hard, sf, C, F, Kout, count, out);
+  else if (Kout <= 16) reconstruct_kernel<16><<<grid, 128, 0, stream>>>(seg, hard, sf, C, F, Kout, count, out);
+  else reconstruct_kernel<32><<<grid, 128, 0, stream>>>(seg, hard, sf, C, F, Kout, count, out);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }

@@ -262,23 +262,41 @@ class Context:
         return out.squeeze(1) if squeeze else out
 
     # ---- overlap-add / reconstruction ----------------------------------------------------------------
-    def speaker_count(self, seg: torch.Tensor, start_frame: Sequence[int], num_frames: int):
+    def start_frames(self, start_frame) -> torch.Tensor:
+        """Device copy of the per-chunk start frames (cached per distinct array)."""
+        if isinstance(start_frame, torch.Tensor):
+            return start_frame
         sf = np.ascontiguousarray(start_frame, dtype=np.int32)
+        if len(sf) > 1 and not bool((np.diff(sf) >= 0).all()):
+            raise ValueError("start_frame must be non-decreasing")
+        key = (len(sf), int(sf[0]) if len(sf) else 0, int(sf[-1]) if len(sf) else 0)
+        cache = self.__dict__.setdefault("_sf_cache", {})
+        hit = cache.get(key)
+        if hit is None or not np.array_equal(hit[0], sf):
+            hit = (sf, torch.from_numpy(sf).to(self.device))
+            if len(cache) > 64:
+                cache.clear()
+            cache[key] = hit
+        return hit[1]
+
+    def speaker_count(self, seg: torch.Tensor, start_frame, num_frames: int):
+        sf = self.start_frames(start_frame)
         count = torch.empty((num_frames,), dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.b200_speaker_count(self._h, _ptr(seg), sf.ctypes.data, len(sf), num_frames, _ptr(count),
+            _lib.check(self.lib.b200_speaker_count(self._h, _ptr(seg), _ptr(sf), sf.numel(), num_frames, _ptr(count),
                                                    _stream(self.device)))
         return count
 
-    def reconstruct(self, seg: torch.Tensor, hard_clusters: np.ndarray, start_frame, num_frames: int,
-                    num_clusters: int, count: torch.Tensor, num_clusters_out: int):
-        sf = np.ascontiguousarray(start_frame, dtype=np.int32)
-        hc = np.ascontiguousarray(hard_clusters, dtype=np.int8)
+    def reconstruct(self, seg: torch.Tensor, hard_clusters, start_frame, num_frames: int, count: torch.Tensor,
+                    num_clusters_out: int):
+        sf = self.start_frames(start_frame)
+        if not isinstance(hard_clusters, torch.Tensor):
+            hard_clusters = torch.from_numpy(np.ascontiguousarray(hard_clusters, dtype=np.int8)).to(self.device)
+        hc = hard_clusters.to(torch.int8).contiguous()
         out = torch.empty((num_frames, num_clusters_out), dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.b200_reconstruct(self._h, _ptr(seg), hc.ctypes.data, sf.ctypes.data, len(sf), num_frames,
-                                                 num_clusters, _ptr(count), num_clusters_out, _ptr(out),
-                                                 _stream(self.device)))
+            _lib.check(self.lib.b200_reconstruct(self._h, _ptr(seg), _ptr(hc), _ptr(sf), sf.numel(), num_frames,
+                                                 _ptr(count), num_clusters_out, _ptr(out), _stream(self.device)))
         return out
 
     def clean_frames(self, seg: torch.Tensor):
@@ -354,3 +372,34 @@ def assign(self, soft: torch.Tensor, constrained: bool = True) -> torch.Tensor:
     with torch.cuda.device(self.device):
         _lib.check(self.lib.b200_assign(self._h, _ptr(soft), c, k, int(constrained), _ptr(hard), _stream(self.device)))
     return hard
+
+
+@_ctx_method
+def linkage_centroid_batched(self, x: torch.Tensor, row_offsets, normalize: bool = True) -> torch.Tensor:
+    """x (sum n_f, dim) f64; row_offsets host int array (F+1,) -> concatenated Z ((sum max(n_f-1,0)), 4) f64."""
+    x = x.contiguous()
+    ro = np.ascontiguousarray(row_offsets, dtype=np.int32)
+    nz = int(np.maximum(np.diff(ro) - 1, 0).sum())
+    Z = torch.empty((nz, 4), dtype=torch.float64, device=self.device)
+    with torch.cuda.device(self.device):
+        _lib.check(self.lib.b200_linkage_centroid_batched(self._h, _ptr(x), ro.ctypes.data, len(ro) - 1, x.shape[1],
+                                                          int(normalize), _ptr(Z), _stream(self.device)))
+    return Z
+
+
+@_ctx_method
+def vbx_batched(self, fea: torch.Tensor, phi: torch.Tensor, gamma0: torch.Tensor, n, S, Fa: float, Fb: float,
+                max_iters: int = 20, epsilon: float = 1e-4, want_iters: bool = False):
+    """fea (sum n_f, D); gamma0 flat concatenation of the per-problem (n_f, S_f) initial responsibilities."""
+    fea, phi = fea.contiguous(), phi.contiguous()
+    gamma = gamma0.contiguous().clone()
+    n = np.ascontiguousarray(n, dtype=np.int32)
+    S = np.ascontiguousarray(S, dtype=np.int32)
+    pi = torch.empty((int(S.sum()),), dtype=torch.float64, device=self.device)
+    iters = np.zeros(len(n), dtype=np.int32)
+    with torch.cuda.device(self.device):
+        _lib.check(self.lib.b200_vbx_batched(self._h, _ptr(fea), _ptr(phi), n.ctypes.data, S.ctypes.data, len(n),
+                                             fea.shape[1], C.c_double(Fa), C.c_double(Fb), max_iters,
+                                             C.c_double(epsilon), _ptr(gamma), _ptr(pi),
+                                             iters.ctypes.data if want_iters else None, _stream(self.device)))
+    return gamma, pi, iters

@@ -101,31 +101,30 @@ def binarize_frames(discrete: np.ndarray, frames: SlidingWindow, min_duration_of
                     uri: Optional[str] = None) -> Tuple[Annotation, np.ndarray]:
     """to_annotation (diarization.py:188-218) / Binarize(onset=offset=0.5) (utils/signal.py:254-318), vectorised.
 
-    Returns the Annotation (integer labels) and the (n_segments, 3) int array of (start_frame, end_frame, label).
+    A region switched on at frame a and off at frame b is [middle(a), middle(b)]; a region still active at the last
+    frame n-1 closes at middle(n-1).  Returns the Annotation (integer labels) and the (n_segments, 3) int array of
+    (start_frame, end_frame, label), both in Annotation.itertracks() order: by (start, end), then speaker column.
     """
     n, K = discrete.shape
-    ann = Annotation(uri=uri)
-    rows = []
-    if n < 2:
-        return ann, np.zeros((0, 3), dtype=np.int64)
-    act = discrete > 0
-    pad = np.zeros((1, K), dtype=bool)
-    d = np.diff(np.concatenate([pad, act, pad]).astype(np.int8), axis=0)      # (n+1, K)
-    for k in range(K):
-        on = np.nonzero(d[:, k] == 1)[0]
-        off = np.nonzero(d[:, k] == -1)[0]
-        off = np.minimum(off, n - 1)           # still active at the end -> region closes at the last frame
-        for a, b in zip(on, off):
-            rows.append((int(a), int(b), k))
-    rows.sort()
-    track = 0
-    for a, b, k in rows:
-        # timestamps are frames[i].middle, computed like pyannote.core.Segment.middle: 0.5 * (start + end)
-        ann.add(Segment(frames[a].middle, frames[b].middle), track, k)
-        track += 1
+    if n < 2 or K == 0:
+        return Annotation(uri=uri), np.zeros((0, 3), dtype=np.int64)
+    act = np.zeros((n + 2, K), dtype=np.int8)
+    act[1:-1] = discrete > 0
+    d = np.diff(act, axis=0)                                   # (n+1, K): +1 at onsets, -1 at offsets
+    on_t, on_k = np.nonzero(d.T == 1)[::-1]                    # column-major scan: grouped by k, ascending t
+    off_t, off_k = np.nonzero(d.T == -1)[::-1]
+    off_t = np.minimum(off_t, n - 1)                           # still active at the end -> last frame
+    order = np.lexsort((on_k, off_t, on_t))                    # sort by (start, end, k)
+    rows = np.stack([on_t[order], off_t[order], on_k[order]], axis=1).astype(np.int64)
+    # timestamps = frames[i].middle computed like pyannote.core: start_i = start + i*step; 0.5*(start_i + (start_i+dur))
+    s0 = frames.start + rows[:, 0] * frames.step
+    s1 = frames.start + rows[:, 1] * frames.step
+    starts = 0.5 * (s0 + (s0 + frames.duration))
+    ends = 0.5 * (s1 + (s1 + frames.duration))
+    ann = Annotation.from_rows(starts, ends, rows[:, 2].tolist(), uri=uri)
     if min_duration_off > 0.0:
         ann = ann.support(collar=min_duration_off)
-    return ann, np.asarray(rows, dtype=np.int64).reshape(-1, 3)
+    return ann, rows
 
 
 class SpeakerDiarization:
@@ -292,7 +291,7 @@ class SpeakerDiarization:
         cnt = torch.from_numpy(np.asarray(count.data).reshape(-1).astype(np.uint8)).to(ctx.device)
         K = int(np.max(hard_clusters)) + 1
         Kout = max(K, int(cnt.max().item()), 1)
-        d = ctx.reconstruct(seg, hard_clusters, sf, F, K, cnt, Kout)
+        d = ctx.reconstruct(seg, hard_clusters, sf, F, cnt, Kout)
         return SlidingWindowFeature(d.cpu().numpy().astype(np.float64), fr)
 
     def to_annotation(self, discrete: SlidingWindowFeature, min_duration_on: float = 0.0,
@@ -360,72 +359,126 @@ class SpeakerDiarization:
         self._timer.mark("segmentation")
         emb = self.embedding.forward_chunks(wav_dev, all_off, all_valid, self._masks(seg))  # (C,3,256) f32
         self._timer.mark("embedding")
-        # ---- per-file clustering + reconstruction ------------------------------------------------------------
-        for fi, file in enumerate(resident["files"]):
-            h = self.setup_hook(file, hook)
-            c0, c1 = int(bounds[fi]), int(bounds[fi + 1])
-            out = self._finish_file(ctx, file, seg[c0:c1], emb[c0:c1], num_speakers, min_speakers, max_speakers, h,
-                                    return_artifacts)
-            yield file, out
+        # ---- clustering + reconstruction, batched across files -------------------------------------------------
+        outs = self._finish_files(ctx, resident["files"], seg, emb, bounds, num_speakers, min_speakers, max_speakers,
+                                  hook, return_artifacts)
         self._timer.report()
+        for file, out in zip(resident["files"], outs):
+            yield file, out
 
     def _finish_file(self, ctx, file, seg, emb, num_speakers, min_speakers, max_speakers, hook, return_artifacts):
-        uri = file.get("uri", None)
-        C = seg.shape[0]
-        sf, F, fr = self._grid(C)
+        if not hasattr(self, "_timer"):
+            self._timer = _StageTimer(ctx.device)
+        return self._finish_files(ctx, [file], seg, emb, [0, seg.shape[0]], num_speakers, min_speakers, max_speakers,
+                                  None, return_artifacts)[0]
+
+    def _finish_files(self, ctx, files, seg, emb, bounds, num_speakers, min_speakers, max_speakers, hook,
+                      return_artifacts):
+        tm = self._timer
+        F = len(files)
         chunks_sw = SlidingWindow(start=0.0, duration=self._segmentation.duration, step=self._segmentation.step)
-        hook("segmentation", _Lazy(lambda: SlidingWindowFeature(seg.cpu().numpy().astype(np.float32), chunks_sw)))
-        tm = getattr(self, "_timer", None) or _StageTimer(ctx.device)
-        count = ctx.speaker_count(seg, sf, F)
-        hook("speaker_counting", _Lazy(lambda: SlidingWindowFeature(count.cpu().numpy()[:, None], fr)))
-        artifacts = dict(segmentations=seg, count=count, embeddings=emb) if return_artifacts else None
-        if int(count.max().item()) == 0:
-            output = DiarizeOutput(Annotation(uri=uri), Annotation(uri=uri), np.zeros((0, self._embedding.dimension)))
-            output = output.speaker_diarization if self.legacy else output
-            return (output, artifacts) if return_artifacts else output
-        hook("embeddings", _Lazy(lambda: emb.cpu().numpy()))
-        hard, _, centroids = self.clustering(embeddings=emb, segmentations=seg, num_clusters=num_speakers,
-                                             min_clusters=min_speakers, max_clusters=max_speakers)
-        tm.mark("count+clustering")
-        num_different = int(np.max(hard)) + 1
-        if num_different < min_speakers or num_different > max_speakers:
-            warnings.warn(textwrap.dedent(f"""
-                The detected number of speakers ({num_different}) for {uri} is outside
-                the given bounds [{min_speakers}, {max_speakers}]. This can happen if the
-                given audio file is too short to contain {min_speakers} or more speakers.
-                Try to lower the desired minimal number of speakers.
-                """))
-        if np.isfinite(max_speakers):
-            count = torch.clamp(count, max=int(max_speakers))
-        inactive = (seg.sum(dim=1) == 0).cpu().numpy()
-        hard = hard.copy()
-        hard[inactive] = -2
-        K = int(np.max(hard)) + 1
-        Kout = max(K, int(count.max().item()), 1)
-        discrete = ctx.reconstruct(seg, hard, sf, F, K, count, Kout)
-        count1 = torch.clamp(count, max=1)
-        exclusive = ctx.reconstruct(seg, hard, sf, F, K, count1, max(K, 1))
-        discrete_np, exclusive_np = discrete.cpu().numpy(), exclusive.cpu().numpy()
-        tm.mark("reconstruct+d2h")
-        self.d2h_bytes += discrete_np.nbytes + exclusive_np.nbytes + hard.nbytes + centroids.nbytes + seg.shape[0] * 3
-        hook("discrete_diarization", _Lazy(lambda: SlidingWindowFeature(discrete_np.astype(np.float64), fr)))
-        diarization, rows = binarize_frames(discrete_np, fr, self.min_duration_off, uri=uri)
-        exclusive_diarization, xrows = binarize_frames(exclusive_np, fr, self.min_duration_off, uri=uri)
-        mapping = {label: expected for label, expected in zip(diarization.labels(), self.classes())}
-        labels_int = diarization.labels()
-        diarization = diarization.rename_labels(mapping)
-        exclusive_diarization = exclusive_diarization.rename_labels(mapping)
-        if len(labels_int) > centroids.shape[0]:
-            centroids = np.pad(centroids, ((0, len(labels_int) - centroids.shape[0]), (0, 0)))
-        inverse = {label: index for index, label in mapping.items()}
-        centroids = centroids[[inverse[label] for label in diarization.labels()]] if len(labels_int) else centroids[:0]
-        output = DiarizeOutput(diarization, exclusive_diarization, centroids)
-        tm.mark("annotation")
-        if return_artifacts:
-            artifacts.update(hard_clusters=hard, discrete=discrete_np, exclusive=exclusive_np, segments=rows,
-                             exclusive_segments=xrows, centroids=centroids)
-            return (output.speaker_diarization if self.legacy else output), artifacts
-        return output.speaker_diarization if self.legacy else output
+        hooks = [self.setup_hook(f, hook) for f in files]
+        grids, counts = [], []
+        for fi in range(F):
+            c0, c1 = int(bounds[fi]), int(bounds[fi + 1])
+            sf, nF, fr = self._grid(c1 - c0)
+            grids.append((sf, nF, fr))
+            sfile = seg[c0:c1]
+            hooks[fi]("segmentation", _Lazy(lambda sfile=sfile: SlidingWindowFeature(
+                sfile.cpu().numpy().astype(np.float32), chunks_sw)))
+            counts.append(ctx.speaker_count(sfile, sf, nF))
+            hooks[fi]("speaker_counting", _Lazy(lambda c=counts[-1], fr=fr: SlidingWindowFeature(
+                c.cpu().numpy()[:, None], fr)))
+        count_max = torch.stack([c.max() for c in counts]).cpu().numpy().astype(np.int64)        # sync
+        tm.mark("speaker_count")
+        silent = [int(m) == 0 for m in count_max]
+        for fi in range(F):
+            if not silent[fi]:
+                efile = emb[int(bounds[fi]): int(bounds[fi + 1])]
+                hooks[fi]("embeddings", _Lazy(lambda efile=efile: efile.cpu().numpy()))
+        if isinstance(self.clustering, VBxClustering):
+            results = self.clustering.cluster_batch(emb, seg, bounds, num_clusters=num_speakers,
+                                                    min_clusters=min_speakers, max_clusters=max_speakers, skip=silent)
+        else:
+            results = []
+            for fi in range(F):
+                if silent[fi]:
+                    results.append(None)
+                    continue
+                c0, c1 = int(bounds[fi]), int(bounds[fi + 1])
+                h, s_, c = self.clustering(embeddings=emb[c0:c1], segmentations=seg[c0:c1], num_clusters=num_speakers,
+                                           min_clusters=min_speakers, max_clusters=max_speakers)
+                results.append(dict(hard=torch.from_numpy(h.astype(np.int8)).to(ctx.device),
+                                    centroids=torch.from_numpy(c).to(ctx.device),
+                                    active=seg[c0:c1].sum(dim=1) > 0))
+        tm.mark("clustering")
+        pending = []
+        for fi in range(F):
+            if silent[fi]:
+                pending.append(None)
+                continue
+            c0, c1 = int(bounds[fi]), int(bounds[fi + 1])
+            sf, nF, fr = grids[fi]
+            r = results[fi]
+            count = counts[fi]
+            if np.isfinite(max_speakers):
+                count = torch.clamp(count, max=int(max_speakers))
+            hard = torch.where(r["active"], r["hard"], torch.full_like(r["hard"], -2))     # inactive -> -2
+            K = int(r["centroids"].shape[0])
+            Kout = max(K, 3)        # columns beyond max(K, max count) stay all-zero and are trimmed on the host
+            discrete = ctx.reconstruct(seg[c0:c1], hard, sf, nF, count, Kout)
+            exclusive = ctx.reconstruct(seg[c0:c1], hard, sf, nF, torch.clamp(count, max=1), Kout)
+            pending.append((discrete, exclusive, hard, r["centroids"], K))
+        tm.mark("reconstruct")
+        outs = []
+        for fi, file in enumerate(files):
+            uri = file.get("uri", None)
+            artifacts = None
+            if return_artifacts:
+                c0, c1 = int(bounds[fi]), int(bounds[fi + 1])
+                artifacts = dict(segmentations=seg[c0:c1], count=counts[fi], embeddings=emb[c0:c1])
+            if silent[fi]:
+                output = DiarizeOutput(Annotation(uri=uri), Annotation(uri=uri),
+                                       np.zeros((0, self._embedding.dimension)))
+                output = output.speaker_diarization if self.legacy else output
+                outs.append((output, artifacts) if return_artifacts else output)
+                continue
+            discrete, exclusive, hard, centroids, K = pending[fi]
+            _, nF, fr = grids[fi]
+            discrete_np, exclusive_np = discrete.cpu().numpy(), exclusive.cpu().numpy()          # D2H of the result
+            centroids = centroids.cpu().numpy()
+            cmax = int(count_max[fi]) if not np.isfinite(max_speakers) else min(int(count_max[fi]), int(max_speakers))
+            discrete_np = discrete_np[:, : max(K, cmax)]
+            exclusive_np = exclusive_np[:, : max(K, min(cmax, 1))]
+            self.d2h_bytes += discrete.numel() + exclusive.numel() + centroids.nbytes + 8
+            if K < min_speakers or K > max_speakers:
+                warnings.warn(textwrap.dedent(f"""
+                    The detected number of speakers ({K}) for {uri} is outside
+                    the given bounds [{min_speakers}, {max_speakers}]. This can happen if the
+                    given audio file is too short to contain {min_speakers} or more speakers.
+                    Try to lower the desired minimal number of speakers.
+                    """))
+            hooks[fi]("discrete_diarization", _Lazy(lambda d=discrete_np, fr=fr: SlidingWindowFeature(
+                d.astype(np.float64), fr)))
+            diarization, rows = binarize_frames(discrete_np, fr, self.min_duration_off, uri=uri)
+            exclusive_diarization, xrows = binarize_frames(exclusive_np, fr, self.min_duration_off, uri=uri)
+            labels_int = diarization.labels()
+            mapping = {label: expected for label, expected in zip(labels_int, self.classes())}
+            diarization = diarization.rename_labels(mapping)
+            exclusive_diarization = exclusive_diarization.rename_labels(mapping)
+            if len(labels_int) > centroids.shape[0]:
+                centroids = np.pad(centroids, ((0, len(labels_int) - centroids.shape[0]), (0, 0)))
+            inverse = {label: index for index, label in mapping.items()}
+            centroids = centroids[[inverse[l] for l in diarization.labels()]] if len(labels_int) else centroids[:0]
+            output = DiarizeOutput(diarization, exclusive_diarization, centroids)
+            if return_artifacts:
+                artifacts.update(hard_clusters=hard.cpu().numpy(), discrete=discrete_np, exclusive=exclusive_np,
+                                 segments=rows, exclusive_segments=xrows, centroids=centroids)
+                outs.append(((output.speaker_diarization if self.legacy else output), artifacts))
+            else:
+                outs.append(output.speaker_diarization if self.legacy else output)
+        tm.mark("d2h+annotation")
+        return outs
 
 
 class _StageTimer:

@@ -128,7 +128,7 @@ if args.stage == "post":
     ref_d = P.reconstruct(swf, hard, cnt)
     K = int(hard.max()) + 1
     Kout = max(K, int(cnt.data.max()))
-    d = ctx.reconstruct(seg_dev, hard, sf, F, K, torch.from_numpy(cnt.data[:, 0].astype(np.uint8)).to(dev), Kout)
+    d = ctx.reconstruct(seg_dev, hard, sf, F, torch.from_numpy(cnt.data[:, 0].astype(np.uint8)).to(dev), Kout)
     print("  reconstruct equal:", np.array_equal(d.cpu().numpy(), ref_d.data.astype(np.uint8)), ref_d.data.shape)
     clean, active = ctx.clean_frames(seg_dev)
     single = (seg.sum(2, keepdims=True) == 1)

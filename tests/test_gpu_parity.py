@@ -174,7 +174,7 @@ def test_post_processing_bit_exact(ctx, dev):
             ref_d = P.reconstruct(swf, hard, cnt)
             K = int(hard.max()) + 1
             Kout = max(K, int(cnt.data.max()), 1)
-            d = ctx.reconstruct(seg_dev, hard, sf, F, K, torch.from_numpy(cnt.data[:, 0].astype(np.uint8)).to(dev), Kout)
+            d = ctx.reconstruct(seg_dev, hard, sf, F, torch.from_numpy(cnt.data[:, 0].astype(np.uint8)).to(dev), Kout)
             assert np.array_equal(d.cpu().numpy()[:, : ref_d.data.shape[1]], ref_d.data.astype(np.uint8))
             assert not d.cpu().numpy()[:, ref_d.data.shape[1]:].any()
         clean, active = ctx.clean_frames(seg_dev)
