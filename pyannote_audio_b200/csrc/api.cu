@@ -14,7 +14,7 @@ using namespace b200;
 struct b200_ctx {
   int device = 0;
   int num_sms = 148;
-  int conv_impl = 1;
+  int conv_impl = 6;   // strip-streaming tcgen05 conv for stride-1 3x3, per-tap tcgen05 conv otherwise
   int seg_max_batch = 2368;     // chunks per segmentation sub-batch (37 LSTM tiles of 64 sequences x 2 directions)
   int emb_max_batch = 256;      // chunks per embedding sub-batch
   int64_t launches = 0;
