@@ -14,6 +14,7 @@ using namespace b200;
 struct b200_ctx {
   int device = 0;
   int num_sms = 148;
+  int seg_gemm_impl = 1;   // 1 = split-fp16 tcgen05 GEMMs for the LSTM input projections / linear layers, 0 = fp32 SIMT
   int conv_impl = 6;   // strip-streaming tcgen05 conv for stride-1 3x3, per-tap tcgen05 conv otherwise
   int seg_max_batch = 2368;     // chunks per segmentation sub-batch (37 LSTM tiles of 64 sequences x 2 directions)
   int emb_max_batch = 256;      // chunks per embedding sub-batch
@@ -210,6 +211,7 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value) {
   else if (k == "seg_max_batch") ctx->seg_max_batch = (int)value;
   else if (k == "emb_max_batch") ctx->emb_max_batch = (int)value;
   else if (k == "profile") ctx->profile = (int)value;
+  else if (k == "seg_gemm_impl") ctx->seg_gemm_impl = (int)value;
   else B200_CHECK(false, B200_ERR_INVALID, "unknown option '%s'", key);
   B200_CHECK(ctx->seg_max_batch >= 1 && ctx->emb_max_batch >= 1 && ctx->conv_impl >= 0 && ctx->conv_impl <= 6,
              B200_ERR_INVALID, "option '%s' value %lld out of range", key, (long long)value);
@@ -313,6 +315,15 @@ int b200_seg_load(b200_ctx* ctx, const b200_seg_weights* w) {
                 whh[(((size_t)(d * 2 + r) * 128 + k) * 256) + p * 128 + tx * 4 + gt] = Wh[(size_t)(gt * 128 + unit) * 128 + k];
               }
     }
+    {
+      std::vector<__half> hi(wih.size()), lo(wih.size());
+      for (size_t i = 0; i < wih.size(); ++i) {
+        hi[i] = __float2half(wih[i]);
+        lo[i] = __float2half(wih[i] - __half2float(hi[i]));
+      }
+      if ((rc = upload(ctx, hi, &S.w_ih_hi[l]))) return rc;
+      if ((rc = upload(ctx, lo, &S.w_ih_lo[l]))) return rc;
+    }
     if ((rc = upload(ctx, wih, &S.w_ih[l]))) return rc;
     if ((rc = upload(ctx, bg, &S.b_g[l]))) return rc;
     if ((rc = upload(ctx, whh, &S.w_hh[l]))) return rc;
@@ -321,6 +332,15 @@ int b200_seg_load(b200_ctx* ctx, const b200_seg_weights* w) {
   for (int i = 0; i < 2; ++i) {
     B200_CHECK(w->linear_weight[i] && w->linear_bias[i], B200_ERR_INVALID, "linear.%d missing", i);
     std::vector<float> lw(w->linear_weight[i], w->linear_weight[i] + 128 * lin_in[i]), lb(w->linear_bias[i], w->linear_bias[i] + 128);
+    {
+      std::vector<__half> hi(lw.size()), lo(lw.size());
+      for (size_t j = 0; j < lw.size(); ++j) {
+        hi[j] = __float2half(lw[j]);
+        lo[j] = __float2half(lw[j] - __half2float(hi[j]));
+      }
+      if ((rc = upload(ctx, hi, &S.lin_w_hi[i]))) return rc;
+      if ((rc = upload(ctx, lo, &S.lin_w_lo[i]))) return rc;
+    }
     if ((rc = upload(ctx, lw, &S.lin_w[i]))) return rc;
     if ((rc = upload(ctx, lb, &S.lin_b[i]))) return rc;
   }
@@ -399,7 +419,8 @@ static int seg_run(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, co
     ctx->launches += 8;
     if (sinc_out) continue;
     if ((rc = lstm_head_forward(ctx->seg, x0, nb, region, classes + (size_t)c0 * kFrames,
-                                logp ? logp + (size_t)c0 * kFrames * kClasses : nullptr, ctx->num_sms, st)))
+                                logp ? logp + (size_t)c0 * kFrames * kClasses : nullptr, ctx->num_sms,
+                                ctx->seg_gemm_impl, st)))
       return rc;
     ctx->launches += 2 * ctx->seg.lstm_layers + 3;
   }

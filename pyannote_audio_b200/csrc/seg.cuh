@@ -18,6 +18,11 @@ struct SegWeights {
   float* b_g[8] = {};
   int k_in[8] = {};                 // padded input size (64, 256, ...)
   float* w_hh[8] = {};              // [2 dir][2 rank][128 k][256]  (smem image of the recurrent kernel)
+  // fp16 (hi, lo) splits of the GEMM weights for the tensor-core path (gemm_tc.cu)
+  __half* w_ih_hi[8] = {};
+  __half* w_ih_lo[8] = {};
+  __half* lin_w_hi[2] = {nullptr, nullptr};
+  __half* lin_w_lo[2] = {nullptr, nullptr};
   float* lin_w[2] = {nullptr, nullptr};   // [128][256], [128][128]
   float* lin_b[2] = {nullptr, nullptr};
   float* cls_w = nullptr;           // [7][128]
@@ -27,6 +32,12 @@ struct SegWeights {
 int sgemm_nt(const float* A, int lda, const float* Bw, int ldb, float* C, int ldc, const float* bias, int M, int N,
              int K, int act, cudaStream_t stream);
 
+// split-precision tensor-core GEMM (gemm_tc.cu): C = act(A B^T + bias), A/B as fp16 (hi, lo) pairs
+int gemm_tc_split(const __half* A_hi, const __half* A_lo, int lda, const __half* B_hi, const __half* B_lo, int ldb,
+                  float* C, int ldc, __half* C_hi, __half* C_lo, int ldc_h, const float* bias, int M, int N, int K,
+                  int act, int num_sms, cudaStream_t stream);
+int split_f16(const float* x, __half* hi, __half* lo, size_t n, cudaStream_t st);
+
 // SincNet front-end on NB chunks: wav + per-chunk (offset, valid) -> X0 [NB][589][64] fp32 (60 features + 4 zero pad)
 size_t sincnet_workspace_bytes(int NB);
 int sincnet_forward(const SegWeights& W, const float* wav, const long long* chunk_off, const int* chunk_valid, int NB,
@@ -35,6 +46,6 @@ int sincnet_forward(const SegWeights& W, const float* wav, const long long* chun
 // BiLSTM stack + linear head: X0 -> class ids [NB][589] u8 (+ optional log-probs [NB][589][7])
 size_t lstm_workspace_bytes(int NB);
 int lstm_head_forward(const SegWeights& W, const float* x0, int NB, void* ws, unsigned char* cls, float* logp,
-                      int num_sms, cudaStream_t stream);
+                      int num_sms, int gemm_impl, cudaStream_t stream);
 
 }  // namespace b200

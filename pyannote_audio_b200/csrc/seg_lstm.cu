@@ -25,7 +25,8 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 template <int RB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 lstm_rec_kernel(const float* __restrict__ Gx /*[NB][589][1024]*/, const float* __restrict__ Whh /*[2][2][128][256]*/,
-                float* __restrict__ Y /*[NB][589][256]*/, int NB, int ntiles) {
+                float* __restrict__ Y /*[NB][589][256] or null*/, __half* __restrict__ Yh, __half* __restrict__ Yl,
+                int NB, int ntiles) {
   constexpr int NBT = 8 * RB;
   extern __shared__ float sm[];
   float* Ws = sm;                         // [128][256]
@@ -122,9 +123,15 @@ lstm_rec_kernel(const float* __restrict__ Gx /*[NB][589][1024]*/, const float* _
         hnext_peer[unit * NBT + ty * RB + r] = hn[p];
       }
       const int b = b0 + r;
-      if (b < NB)
-        *reinterpret_cast<float2*>(Y + ((size_t)b * kFrames + t) * 256 + dir * 128 + rank * 64 + 2 * tx) =
-            make_float2(hn[0], hn[1]);
+      if (b < NB) {
+        const size_t o = ((size_t)b * kFrames + t) * 256 + dir * 128 + rank * 64 + 2 * tx;
+        if (Y) *reinterpret_cast<float2*>(Y + o) = make_float2(hn[0], hn[1]);
+        if (Yh) {   // fp16 (hi, lo) split consumed by the tensor-core GEMM of the next layer
+          const __half h0 = __float2half_rn(hn[0]), h1 = __float2half_rn(hn[1]);
+          *reinterpret_cast<__half2*>(Yh + o) = __halves2half2(h0, h1);
+          *reinterpret_cast<__half2*>(Yl + o) = __floats2half2_rn(hn[0] - __half2float(h0), hn[1] - __half2float(h1));
+        }
+      }
     }
     cluster.sync();
   }
@@ -179,6 +186,7 @@ __global__ void __launch_bounds__(256) classifier_kernel(const float* __restrict
 // ---- host ------------------------------------------------------------------------------------------
 struct LstmWs {
   float *Gx, *Ya, *Yb, *Z1, *Z2;
+  __half *Xh, *Xl, *Yah, *Yal, *Ybh, *Ybl, *Z1h, *Z1l;
 };
 static size_t carve_lstm(int NB, void* base, LstmWs* w) {
   size_t off = 0;
@@ -195,45 +203,75 @@ static size_t carve_lstm(int NB, void* base, LstmWs* w) {
   t.Yb = (float*)take(M * 256 * sizeof(float));
   t.Z1 = (float*)take(M * 128 * sizeof(float));
   t.Z2 = (float*)take(M * 128 * sizeof(float));
+  t.Xh = (__half*)take(M * 64 * sizeof(__half));
+  t.Xl = (__half*)take(M * 64 * sizeof(__half));
+  t.Yah = (__half*)take(M * 256 * sizeof(__half));
+  t.Yal = (__half*)take(M * 256 * sizeof(__half));
+  t.Ybh = (__half*)take(M * 256 * sizeof(__half));
+  t.Ybl = (__half*)take(M * 256 * sizeof(__half));
+  t.Z1h = (__half*)take(M * 128 * sizeof(__half));
+  t.Z1l = (__half*)take(M * 128 * sizeof(__half));
   if (w) *w = t;
   return align_up(off, 256);
 }
 size_t lstm_workspace_bytes(int NB) { return carve_lstm(NB, nullptr, nullptr); }
 
 template <int RB>
-static int launch_rec(const float* Gx, const float* Whh, float* Y, int NB, cudaStream_t stream) {
+static int launch_rec(const float* Gx, const float* Whh, float* Y, __half* Yh, __half* Yl, int NB,
+                      cudaStream_t stream) {
   constexpr int NBT = 8 * RB;
   const int ntiles = ceil_div(NB, NBT);
   const size_t smem = (128 * 256 + 2 * 128 * NBT) * sizeof(float);
   B200_CUDA_OK(cudaFuncSetAttribute(lstm_rec_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  lstm_rec_kernel<RB><<<2 * 2 * ntiles, 256, smem, stream>>>(Gx, Whh, Y, NB, ntiles);
+  lstm_rec_kernel<RB><<<2 * 2 * ntiles, 256, smem, stream>>>(Gx, Whh, Y, Yh, Yl, NB, ntiles);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }
 
 int lstm_head_forward(const SegWeights& W, const float* x0, int NB, void* ws, unsigned char* cls, float* logp,
-                      int num_sms, cudaStream_t stream) {
+                      int num_sms, int gemm_impl, cudaStream_t stream) {
   LstmWs w;
   carve_lstm(NB, ws, &w);
   const int M = NB * kFrames;
-  const float* in = x0;
-  float* outs[2] = {w.Ya, w.Yb};
   const int clusters = num_sms / 2;
+  const bool tc = gemm_impl != 0;
+  int rc;
+  const float* in = x0;
+  const __half *in_h = w.Xh, *in_l = w.Xl;
+  if (tc && (rc = split_f16(x0, w.Xh, w.Xl, (size_t)M * 64, stream))) return rc;
+  float* outs[2] = {w.Ya, w.Yb};
+  __half* outs_h[2] = {w.Yah, w.Ybh};
+  __half* outs_l[2] = {w.Yal, w.Ybl};
   for (int l = 0; l < W.lstm_layers; ++l) {
-    int rc = sgemm_nt(in, W.k_in[l], W.w_ih[l], W.k_in[l], w.Gx, 1024, W.b_g[l], M, 1024, W.k_in[l], 0, stream);
+    if (tc)
+      rc = gemm_tc_split(in_h, in_l, W.k_in[l], W.w_ih_hi[l], W.w_ih_lo[l], W.k_in[l], w.Gx, 1024, nullptr, nullptr, 0,
+                         W.b_g[l], M, 1024, W.k_in[l], 0, num_sms, stream);
+    else
+      rc = sgemm_nt(in, W.k_in[l], W.w_ih[l], W.k_in[l], w.Gx, 1024, W.b_g[l], M, 1024, W.k_in[l], 0, stream);
     if (rc) return rc;
-    float* y = outs[l & 1];
+    float* y = tc ? nullptr : outs[l & 1];
+    __half* yh = tc ? outs_h[l & 1] : nullptr;
+    __half* yl = tc ? outs_l[l & 1] : nullptr;
     // largest batch tile that still fills the machine with 2-CTA clusters
-    if (2 * ceil_div(NB, 64) >= clusters) rc = launch_rec<8>(w.Gx, W.w_hh[l], y, NB, stream);
-    else if (2 * ceil_div(NB, 32) >= clusters) rc = launch_rec<4>(w.Gx, W.w_hh[l], y, NB, stream);
-    else rc = launch_rec<2>(w.Gx, W.w_hh[l], y, NB, stream);
+    if (2 * ceil_div(NB, 64) >= clusters) rc = launch_rec<8>(w.Gx, W.w_hh[l], y, yh, yl, NB, stream);
+    else if (2 * ceil_div(NB, 32) >= clusters) rc = launch_rec<4>(w.Gx, W.w_hh[l], y, yh, yl, NB, stream);
+    else rc = launch_rec<2>(w.Gx, W.w_hh[l], y, yh, yl, NB, stream);
     if (rc) return rc;
-    in = y;
+    in = y; in_h = yh; in_l = yl;
   }
-  int rc = sgemm_nt(in, 256, W.lin_w[0], 256, w.Z1, 128, W.lin_b[0], M, 128, 256, 1, stream);
-  if (rc) return rc;
-  rc = sgemm_nt(w.Z1, 128, W.lin_w[1], 128, w.Z2, 128, W.lin_b[1], M, 128, 128, 1, stream);
-  if (rc) return rc;
+  if (tc) {
+    rc = gemm_tc_split(in_h, in_l, 256, W.lin_w_hi[0], W.lin_w_lo[0], 256, nullptr, 0, w.Z1h, w.Z1l, 128, W.lin_b[0], M,
+                       128, 256, 1, num_sms, stream);
+    if (rc) return rc;
+    rc = gemm_tc_split(w.Z1h, w.Z1l, 128, W.lin_w_hi[1], W.lin_w_lo[1], 128, w.Z2, 128, nullptr, nullptr, 0,
+                       W.lin_b[1], M, 128, 128, 1, num_sms, stream);
+    if (rc) return rc;
+  } else {
+    rc = sgemm_nt(in, 256, W.lin_w[0], 256, w.Z1, 128, W.lin_b[0], M, 128, 256, 1, stream);
+    if (rc) return rc;
+    rc = sgemm_nt(w.Z1, 128, W.lin_w[1], 128, w.Z2, 128, W.lin_b[1], M, 128, 128, 1, stream);
+    if (rc) return rc;
+  }
   classifier_kernel<<<ceil_div(M, 8), 256, 0, stream>>>(w.Z2, W.cls_w, W.cls_b, cls, logp, M);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;

@@ -99,6 +99,13 @@ def test_segmentation_parity(ctx, dev, oracle_models):
     # a chunk computed inside a batch equals the same chunk computed alone (bitwise: deterministic kernels)
     alone = ctx.seg_forward(buf, off[5:6], valid[5:6])
     assert torch.equal(alone[0], cls[5])
+    # split-fp16 tensor-core GEMMs (default) against the fp32 CUDA-core GEMMs: fp32-level agreement
+    ctx.set_option("seg_gemm_impl", 0)
+    cls0, logp0 = ctx.seg_forward(buf, off, valid, return_logp=True)
+    ctx.set_option("seg_gemm_impl", 1)
+    np.testing.assert_allclose(logp0.cpu().numpy(), ref_logp, atol=2e-4, rtol=0)
+    assert float((logp0 - logp).abs().max()) < 1e-4
+    assert float((cls0 != cls).float().mean()) < 1e-3
 
 
 def test_segmentation_edge_cases(ctx, dev, oracle_models):
