@@ -165,6 +165,14 @@ int make_conv(b200_ctx* ctx, const b200_conv_bn& src, int cin, int cout, int k, 
   int rc;
   if ((rc = upload(ctx, w, &L->w))) return rc;
   if ((rc = upload(ctx, bias, &L->bias))) return rc;
+  if (k == 3 && stride == 1) {   // zero-padded copy for the channels-as-M kernel
+    const int rows = (cout + 127) / 128 * 128;
+    std::vector<__half> w3((size_t)9 * rows * cin, __float2half(0.f));
+    for (int t = 0; t < 9; ++t)
+      for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin; ++ci) w3[((size_t)t * rows + co) * cin + ci] = w[((size_t)t * cout + co) * cin + ci];
+    if ((rc = upload(ctx, w3, &L->w3))) return rc;
+  }
   return B200_OK;
 }
 
@@ -213,7 +221,7 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value) {
   else if (k == "profile") ctx->profile = (int)value;
   else if (k == "seg_gemm_impl") ctx->seg_gemm_impl = (int)value;
   else B200_CHECK(false, B200_ERR_INVALID, "unknown option '%s'", key);
-  B200_CHECK(ctx->seg_max_batch >= 1 && ctx->emb_max_batch >= 1 && ctx->conv_impl >= 0 && ctx->conv_impl <= 6,
+  B200_CHECK(ctx->seg_max_batch >= 1 && ctx->emb_max_batch >= 1 && ctx->conv_impl >= 0 && ctx->conv_impl <= 7,
              B200_ERR_INVALID, "option '%s' value %lld out of range", key, (long long)value);
   return B200_OK;
 }

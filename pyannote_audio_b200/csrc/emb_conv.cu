@@ -445,6 +445,201 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// conv_tc3_kernel: "channels-as-M" orientation for stride-1 3x3 convolutions
+//
+// Measured (profiles/r01_conv_tc_v1_summary.md, r01_launches_emb_v2): with both operands in shared memory a
+// tcgen05.mma M=128 costs >= 128 cycles per K=16 step because the A operand is read at one 32-byte row per cycle, so
+// the pixels-as-M kernels only balance when N = C_out = 256 (N=128 -> 50 %, 64 -> 25 %, 32 -> 12 % of peak).  Here the
+// roles are swapped:   D[c_out][pixel] += W_tap[c_out][c_in] * X_tap[pixel][c_in]^T
+//   A = weights tile  [128 c_out x Ck]  (rows beyond C_out are zero padding),
+//   B = activation tile [N = 256 pixels x Ck] straight from a TMA box (Ck, bw, bh) with bw*bh <= 256 pixels of one
+//       image (bh > 1 when the image is narrower than 256), zero-filled at the borders, shifted per tap,
+//   N = 256 -> 128 cycles of math per instruction = the A-read time: full tensor rate for C_out >= 128.
+// The accumulator has channels on TMEM lanes and pixels on columns, so the epilogue transposes 32x32 blocks through
+// shared memory to keep NHWC stores (and residual loads) 16-byte vectorised.
+// ------------------------------------------------------------------------------------------------
+struct ConvV3Params {
+  int B, H, W, C_in, C_out;
+  int Ck, ncc, kblocks, bw, bh, tiles_w, tiles_h, m_tiles, num_items, relu;
+  const float* bias;
+  const __half* residual;
+  __half* out;
+  uint32_t a_bytes, b_bytes, stage_bytes, nstages, idesc, swizzle;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvV3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  // [0,64) full  [64,128) empty  [128,144) tfull  [144,160) tempty  [192] tmem slot  [1024,2048) bias
+  // [2048, 2048+16K) epilogue transpose staging (4 warps x (2 KB out + 2 KB residual))  then the stages
+  const uint32_t bar_full = base, bar_empty = base + 64, bar_tfull = base + 128, bar_tempty = base + 144;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + 192);
+  float* s_bias = reinterpret_cast<float*>(gbase + 1024);
+  uint8_t* s_stage_ep = gbase + 2048;
+  const uint32_t stage0 = base + 2048 + 16384;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < p.C_out; i += blockDim.x) s_bias[i] = p.bias[i];
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < p.nstages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int ksteps = p.Ck / 16;
+
+  // item -> (b, th, tw, mt); mt fastest
+  auto decode = [&](int item, int& b, int& h0, int& w0, int& mt) {
+    mt = item % p.m_tiles;
+    int t = item / p.m_tiles;
+    const int tw = t % p.tiles_w; t /= p.tiles_w;
+    const int th = t % p.tiles_h;
+    b = t / p.tiles_h;
+    h0 = th * p.bh;
+    w0 = tw * p.bw;
+  };
+
+  if (warp == 0) {
+    const bool leader = elect_one_sync();
+    if (leader) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+    }
+    uint32_t stage = 0, phase = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int b, h0, w0, mt;
+      decode(item, b, h0, w0, mt);
+      int tap = 0, cc = 0, kh = 0, kw = 0;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (leader) {
+          mbar_expect_tx(bar_full + 8 * stage, p.b_bytes);   // bytes delivered by the two boxes
+          const uint32_t sa = stage0 + stage * p.stage_bytes;
+          tma_load_3d(&tmW, bar_full + 8 * stage, sa, cc * p.Ck, mt * 128, tap);
+          tma_load_4d(&tmX, bar_full + 8 * stage, sa + p.a_bytes, cc * p.Ck, w0 + kw - 1, h0 + kh - 1, b);
+        }
+        __syncwarp();
+        if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+        if (++cc == p.ncc) { cc = 0; ++tap; if (++kw == 3) { kw = 0; ++kh; } }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one_sync();
+    const uint32_t dhi = desc_hi((p.swizzle == 128) ? 1024u : 512u, (p.swizzle == 128) ? 2u : 4u);
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256u;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t sa = stage0 + stage * p.stage_bytes;
+          const uint32_t alo = desc_lo(sa), blo = desc_lo(sa + p.a_bytes);
+          tc_mma_f16(d_tmem, desc_from(dhi, alo), desc_from(dhi, blo), p.idesc, kb != 0);
+          tc_mma_f16(d_tmem, desc_from(dhi, alo + 2), desc_from(dhi, blo + 2), p.idesc, 1);
+          if (ksteps == 4) {
+            tc_mma_f16(d_tmem, desc_from(dhi, alo + 4), desc_from(dhi, blo + 4), p.idesc, 1);
+            tc_mma_f16(d_tmem, desc_from(dhi, alo + 6), desc_from(dhi, blo + 6), p.idesc, 1);
+          }
+          tc_commit(bar_empty + 8 * stage);
+        }
+        __syncwarp();
+        if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+      }
+      if (leader) tc_commit(bar_tfull + 8 * acc);
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    const int q = warp & 3;                                // TMEM lane quadrant = block of 32 output channels
+    __half* s_out = reinterpret_cast<__half*>(s_stage_ep + q * 4096);          // [32 px][32 ch]
+    __half* s_res = reinterpret_cast<__half*>(s_stage_ep + q * 4096 + 2048);   // [32 px][32 ch]
+    const int prow = lane >> 2, ppart = lane & 3;          // cooperative 16-byte I/O: 8 pixels x 4 parts per pass
+    uint32_t acc = 0, acc_phase = 0;
+    const int npix = p.bw * p.bh;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int b, h0, w0, mt;
+      decode(item, b, h0, w0, mt);
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const int c0 = mt * 128 + q * 32;                    // first channel of this warp
+      if (c0 < p.C_out) {
+        const float bias = s_bias[c0 + lane];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
+        for (int n0 = 0; n0 < npix; n0 += 32) {
+          uint32_t r[32];
+          tc_ld32(taddr + n0, r);
+          // global pixel index of the 4 pixels this lane moves (16-byte pieces), -1 when outside the image
+          long long gp[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int n = n0 + i * 8 + prow;
+            const int rr = n / p.bw, x = n - rr * p.bw;
+            const bool ok = n < npix && (h0 + rr) < p.H && (w0 + x) < p.W;
+            gp[i] = ok ? (((long long)b * p.H + h0 + rr) * p.W + w0 + x) : -1;
+          }
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias;
+          if (p.residual) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u = make_uint4(0, 0, 0, 0);
+              if (gp[i] >= 0) u = __ldg(reinterpret_cast<const uint4*>(p.residual + gp[i] * p.C_out + c0 + ppart * 8));
+              *reinterpret_cast<uint4*>(s_res + (i * 8 + prow) * 32 + ppart * 8) = u;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __half2float(s_res[j * 32 + lane]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float a = v[j];
+            if (p.relu) a = fmaxf(a, 0.f);
+            s_out[j * 32 + lane] = __float2half_rn(a);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (gp[i] >= 0)
+              *reinterpret_cast<uint4*>(p.out + gp[i] * p.C_out + c0 + ppart * 8) =
+                  *reinterpret_cast<const uint4*>(s_out + (i * 8 + prow) * 32 + ppart * 8);
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // SIMT reference conv (same math, CUDA cores) -- debugging aid and A/B check for the tensor-core path
 // ------------------------------------------------------------------------------------------------
@@ -577,6 +772,76 @@ PFN_encodeTiled get_encode() {
   return fn;
 }
 
+static int conv3_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H, int W,
+                         int relu, int num_sms, cudaStream_t stream) {
+  B200_CHECK(L.w3 != nullptr, B200_ERR_STATE, "conv v3: padded weights missing");
+  ConvV3Params p{};
+  p.B = B; p.H = H; p.W = W; p.C_in = L.C_in; p.C_out = L.C_out; p.relu = relu;
+  p.bias = L.bias; p.residual = residual; p.out = out;
+  p.Ck = (L.C_in >= 64) ? 64 : 32;
+  p.ncc = L.C_in / p.Ck;
+  p.kblocks = 9 * p.ncc;
+  p.swizzle = (p.Ck == 64) ? 128 : 64;
+  // pixel tile: up to 256 pixels of one image; several rows when the image is narrower than 256
+  if (W >= 256) { p.bw = 256; p.bh = 1; }
+  else { p.bw = W; p.bh = 256 / W; if (p.bh > H) p.bh = H; }
+  p.tiles_w = ceil_div(W, p.bw);
+  p.tiles_h = ceil_div(H, p.bh);
+  p.m_tiles = ceil_div(L.C_out, 128);
+  p.num_items = B * p.tiles_h * p.tiles_w * p.m_tiles;
+  p.a_bytes = 128u * p.Ck * 2;
+  p.b_bytes = (uint32_t)align_up((size_t)p.bw * p.bh * p.Ck * 2, 1024);
+  const uint32_t b_full = 256u * p.Ck * 2;                 // the MMA reads N = 256 rows: keep the slot that large
+  p.stage_bytes = p.a_bytes + (uint32_t)p.bw * p.bh * p.Ck * 2;   // bytes the two TMA boxes deliver
+  const uint32_t slot = p.a_bytes + b_full;
+  p.nstages = (200u * 1024 - 16384) / slot;
+  if (p.nstages > 8) p.nstages = 8;
+  p.idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  PFN_encodeTiled enc = get_encode();
+  B200_CHECK(enc != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  CUtensorMap tmX, tmW;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)L.C_in, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)L.C_in * 2, (cuuint64_t)W * L.C_in * 2, (cuuint64_t)H * W * L.C_in * 2};
+    cuuint32_t box[4] = {(cuuint32_t)p.Ck, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(in), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     p.swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(X, v3) failed: %d", (int)r);
+  }
+  {
+    const int rows = p.m_tiles * 128;                       // padded output-channel rows
+    cuuint64_t dims[3] = {(cuuint64_t)L.C_in, (cuuint64_t)rows, 9};
+    cuuint64_t strides[2] = {(cuuint64_t)L.C_in * 2, (cuuint64_t)rows * L.C_in * 2};
+    cuuint32_t box[3] = {(cuuint32_t)p.Ck, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(L.w3), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     p.swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(W, v3) failed: %d", (int)r);
+  }
+  // the kernel addresses stage s at stage0 + s * stage_bytes: make that the full slot so that N = 256 rows exist
+  const uint32_t delivered = p.stage_bytes;
+  p.stage_bytes = slot;
+  p.b_bytes = delivered - p.a_bytes;                        // (kept for reference) bytes of the activation box
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(conv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const size_t smem = 1024 + 2048 + 16384 + (size_t)p.nstages * slot;
+  const int grid = p.num_items < num_sms ? p.num_items : num_sms;
+  // expect_tx must equal the delivered bytes, the slot stride is `slot`: pass both
+  ConvV3Params q = p;
+  q.b_bytes = delivered;                                    // reuse field: bytes to expect per stage
+  conv_tc3_kernel<<<grid, kTcThreads, smem, stream>>>(tmX, tmW, q);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
 static int conv2_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H, int W,
                          int relu, int base_off_mode, int num_sms, cudaStream_t stream) {
   ConvV2Params p{};
@@ -662,6 +927,11 @@ static int conv2_forward(const ConvLayer& L, const __half* in, const __half* res
 
 int conv_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H_in, int W_in,
                  int relu, int impl, int num_sms, cudaStream_t stream) {
+  if (impl == 7) {
+    // channels-as-M tcgen05 conv for stride-1 3x3, per-tap pixels-as-M kernel otherwise
+    if (L.ksize == 3 && L.stride == 1) return conv3_forward(L, in, residual, out, B, H_in, W_in, relu, num_sms, stream);
+    impl = 1;
+  }
   if (impl >= 3) {
     // 3: v2 for C_in >= 64 (128B swizzle), base_offset set; 4: v2 also for C_in = 32 (64B swizzle);
     // 5 / 6: same as 3 / 4 with base_offset left at 0 (hardware-semantics A/B)
