@@ -170,7 +170,12 @@ int make_conv(b200_ctx* ctx, const b200_conv_bn& src, int cin, int cout, int k, 
     std::vector<__half> w3((size_t)9 * rows * cin, __float2half(0.f));
     for (int t = 0; t < 9; ++t)
       for (int co = 0; co < cout; ++co)
-        for (int ci = 0; ci < cin; ++ci) w3[((size_t)t * rows + co) * cin + ci] = w[((size_t)t * cout + co) * cin + ci];
+        for (int ci = 0; ci < cin; ++ci) {
+          // C_out < 128: spread the channels over the four 32-lane TMEM quadrants (cout/4 per quadrant)
+          const int cpq = cout >= 128 ? 32 : cout / 4;
+          const int row = cout >= 128 ? co : (co / cpq) * 32 + (co % cpq);
+          w3[((size_t)t * rows + row) * cin + ci] = w[((size_t)t * cout + co) * cin + ci];
+        }
     if ((rc = upload(ctx, w3, &L->w3))) return rc;
   }
   return B200_OK;

@@ -389,22 +389,32 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int r = 0; r < R; ++r) {
         const uint32_t g = grow + (uint32_t)r;
         const uint32_t acc = g & 3u;
+        const size_t pix = (((size_t)b * p.H + (h0 + r)) * p.W + (valid ? w : 0)) * (size_t)p.C_out + (size_t)nh * N;
+        uint4 rpre[4];
+        auto load_res = [&](int n0) {                    // residual does not depend on the MMAs: prefetch it
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix + n0);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) rpre[j4] = valid ? __ldg(rp + j4) : make_uint4(0, 0, 0, 0);
+        };
+        if (p.residual) load_res(0);
         mbar_wait(bar_tfull + 8 * acc, (g >> 2) & 1u);
         tc_fence_after();
-        const size_t pix = (((size_t)b * p.H + (h0 + r)) * p.W + (valid ? w : 0)) * (size_t)p.C_out + (size_t)nh * N;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)N;
         for (int n0 = 0; n0 < N; n0 += 32) {
           uint32_t rr[32];
           tc_ld32(taddr + n0, rr);
+          uint4 rcur[4];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) rcur[j4] = rpre[j4];
+          if (p.residual && n0 + 32 < N) load_res(n0 + 32);
           if (valid) {
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) + s_bias[nh * N + n0 + j];
             if (p.residual) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix + n0);
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
-                uint4 u = __ldg(rp + j4);
+                uint4 u = rcur[j4];
                 const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -567,62 +577,82 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    const int q = warp & 3;                                // TMEM lane quadrant = block of 32 output channels
-    __half* s_out = reinterpret_cast<__half*>(s_stage_ep + q * 4096);          // [32 px][32 ch]
-    __half* s_res = reinterpret_cast<__half*>(s_stage_ep + q * 4096 + 2048);   // [32 px][32 ch]
-    const int prow = lane >> 2, ppart = lane & 3;          // cooperative 16-byte I/O: 8 pixels x 4 parts per pass
+    const int q = warp & 3;                                // TMEM lane quadrant
+    // Output channels are spread over the four lane quadrants (cpq per quadrant: 8 / 16 / 32 for C_out = 32 / 64 /
+    // >= 128; the weight rows were permuted accordingly at load) so that all four epilogue warps share the work.
+    const int cpq = p.C_out >= 128 ? 32 : p.C_out / 4;
+    const int parts = cpq / 8;                             // 16-byte pieces per pixel owned by this warp
+    __half* s_out = reinterpret_cast<__half*>(s_stage_ep + q * 4096);          // [32 px][cpq ch]
+    __half* s_res = reinterpret_cast<__half*>(s_stage_ep + q * 4096 + 2048);   // [32 px][cpq ch]
     uint32_t acc = 0, acc_phase = 0;
     const int npix = p.bw * p.bh;
+    const bool lane_on = lane < cpq;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       int b, h0, w0, mt;
       decode(item, b, h0, w0, mt);
+      const int c0 = p.C_out >= 128 ? mt * 128 + q * 32 : q * cpq;      // first channel of this warp
+      const float bias = lane_on ? s_bias[c0 + lane] : 0.f;
+      // piece e = i*32 + lane of a 32-pixel chunk -> (pixel e / parts, part e % parts); global pixel index or -1
+      auto pixel_of = [&](int n) -> long long {
+        const int rr = n / p.bw, x = n - rr * p.bw;
+        const bool ok = n < npix && (h0 + rr) < p.H && (w0 + x) < p.W;
+        return ok ? (((long long)b * p.H + h0 + rr) * p.W + w0 + x) : -1;
+      };
+      uint4 rpre[4];
+      auto load_res = [&](int n0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          rpre[i] = make_uint4(0, 0, 0, 0);
+          if (i < parts) {
+            const int e = i * 32 + lane;
+            const long long gp = pixel_of(n0 + e / parts);
+            if (gp >= 0) rpre[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + gp * p.C_out + c0 + (e % parts) * 8));
+          }
+        }
+      };
+      if (p.residual) load_res(0);                         // independent of the MMAs: issue before waiting
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
-      const int c0 = mt * 128 + q * 32;                    // first channel of this warp
-      if (c0 < p.C_out) {
-        const float bias = s_bias[c0 + lane];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
-        for (int n0 = 0; n0 < npix; n0 += 32) {
-          uint32_t r[32];
-          tc_ld32(taddr + n0, r);
-          // global pixel index of the 4 pixels this lane moves (16-byte pieces), -1 when outside the image
-          long long gp[4];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
+      for (int n0 = 0; n0 < npix; n0 += 32) {
+        uint32_t r[32];
+        tc_ld32(taddr + n0, r);
+        float v[32];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int n = n0 + i * 8 + prow;
-            const int rr = n / p.bw, x = n - rr * p.bw;
-            const bool ok = n < npix && (h0 + rr) < p.H && (w0 + x) < p.W;
-            gp[i] = ok ? (((long long)b * p.H + h0 + rr) * p.W + w0 + x) : -1;
-          }
-          float v[32];
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias;
+        if (p.residual) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias;
-          if (p.residual) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 u = make_uint4(0, 0, 0, 0);
-              if (gp[i] >= 0) u = __ldg(reinterpret_cast<const uint4*>(p.residual + gp[i] * p.C_out + c0 + ppart * 8));
-              *reinterpret_cast<uint4*>(s_res + (i * 8 + prow) * 32 + ppart * 8) = u;
+          for (int i = 0; i < 4; ++i)
+            if (i < parts) {
+              const int e = i * 32 + lane;
+              *reinterpret_cast<uint4*>(s_res + (e / parts) * cpq + (e % parts) * 8) = rpre[i];
             }
-            __syncwarp();
+          __syncwarp();
+          if (n0 + 32 < npix) load_res(n0 + 32);           // prefetch the next chunk's residual
+          if (lane_on) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __half2float(s_res[j * 32 + lane]);
+            for (int j = 0; j < 32; ++j) v[j] += __half2float(s_res[j * cpq + lane]);
           }
+        }
+        if (lane_on) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float a = v[j];
             if (p.relu) a = fmaxf(a, 0.f);
-            s_out[j * 32 + lane] = __float2half_rn(a);
+            s_out[j * cpq + lane] = __float2half_rn(a);
           }
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (gp[i] >= 0)
-              *reinterpret_cast<uint4*>(p.out + gp[i] * p.C_out + c0 + ppart * 8) =
-                  *reinterpret_cast<const uint4*>(s_out + (i * 8 + prow) * 32 + ppart * 8);
-          }
-          __syncwarp();
         }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < parts) {
+            const int e = i * 32 + lane;
+            const long long gp = pixel_of(n0 + e / parts);
+            if (gp >= 0)
+              *reinterpret_cast<uint4*>(p.out + gp * p.C_out + c0 + (e % parts) * 8) =
+                  *reinterpret_cast<const uint4*>(s_out + (e / parts) * cpq + (e % parts) * 8);
+          }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
