@@ -15,7 +15,7 @@ struct b200_ctx {
   int device = 0;
   int num_sms = 148;
   int seg_gemm_impl = 1;   // 1 = split-fp16 tcgen05 GEMMs for the LSTM input projections / linear layers, 0 = fp32 SIMT
-  int conv_impl = 6;   // strip-streaming tcgen05 conv for stride-1 3x3, per-tap tcgen05 conv otherwise
+  int conv_impl = 8;   // channels-as-M conv for C_out >= 128, strip-streaming conv for the narrow stride-1 3x3, per-tap conv otherwise
   int seg_max_batch = 2368;     // chunks per segmentation sub-batch (37 LSTM tiles of 64 sequences x 2 directions)
   int emb_max_batch = 256;      // chunks per embedding sub-batch
   int64_t launches = 0;
@@ -165,17 +165,12 @@ int make_conv(b200_ctx* ctx, const b200_conv_bn& src, int cin, int cout, int k, 
   int rc;
   if ((rc = upload(ctx, w, &L->w))) return rc;
   if ((rc = upload(ctx, bias, &L->bias))) return rc;
-  if (k == 3 && stride == 1) {   // zero-padded copy for the channels-as-M kernel
+  if (k == 3 && stride == 1 && cout >= 128) {   // copy for the channels-as-M kernel (rows padded to 128)
     const int rows = (cout + 127) / 128 * 128;
     std::vector<__half> w3((size_t)9 * rows * cin, __float2half(0.f));
     for (int t = 0; t < 9; ++t)
       for (int co = 0; co < cout; ++co)
-        for (int ci = 0; ci < cin; ++ci) {
-          // C_out < 128: spread the channels over the four 32-lane TMEM quadrants (cout/4 per quadrant)
-          const int cpq = cout >= 128 ? 32 : cout / 4;
-          const int row = cout >= 128 ? co : (co / cpq) * 32 + (co % cpq);
-          w3[((size_t)t * rows + row) * cin + ci] = w[((size_t)t * cout + co) * cin + ci];
-        }
+        for (int ci = 0; ci < cin; ++ci) w3[((size_t)t * rows + co) * cin + ci] = w[((size_t)t * cout + co) * cin + ci];
     if ((rc = upload(ctx, w3, &L->w3))) return rc;
   }
   return B200_OK;
@@ -226,7 +221,7 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value) {
   else if (k == "profile") ctx->profile = (int)value;
   else if (k == "seg_gemm_impl") ctx->seg_gemm_impl = (int)value;
   else B200_CHECK(false, B200_ERR_INVALID, "unknown option '%s'", key);
-  B200_CHECK(ctx->seg_max_batch >= 1 && ctx->emb_max_batch >= 1 && ctx->conv_impl >= 0 && ctx->conv_impl <= 7,
+  B200_CHECK(ctx->seg_max_batch >= 1 && ctx->emb_max_batch >= 1 && ctx->conv_impl >= 0 && ctx->conv_impl <= 8,
              B200_ERR_INVALID, "option '%s' value %lld out of range", key, (long long)value);
   return B200_OK;
 }
@@ -401,6 +396,15 @@ int b200_emb_load(b200_ctx* ctx, const b200_emb_weights* w) {
     }
   B200_CHECK(w->seg1_weight && w->seg1_bias, B200_ERR_INVALID, "seg_1 missing");
   std::vector<float> sw(w->seg1_weight, w->seg1_weight + (size_t)256 * 5120), sb(w->seg1_bias, w->seg1_bias + 256);
+  {
+    std::vector<__half> hi(sw.size()), lo(sw.size());
+    for (size_t i = 0; i < sw.size(); ++i) {
+      hi[i] = __float2half(sw[i]);
+      lo[i] = __float2half(sw[i] - __half2float(hi[i]));
+    }
+    if ((rc = upload(ctx, hi, &E.seg1_w_hi))) return rc;
+    if ((rc = upload(ctx, lo, &E.seg1_w_lo))) return rc;
+  }
   if ((rc = upload(ctx, sw, &E.seg1_w))) return rc;
   if ((rc = upload(ctx, sb, &E.seg1_b))) return rc;
   E.loaded = true;
@@ -540,11 +544,17 @@ int b200_emb_forward(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, 
   DeviceGuard g(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int nbmax = num_chunks < ctx->emb_max_batch ? num_chunks : ctx->emb_max_batch;
-  int rc = ensure_ws(ctx, carve_emb(nbmax, nullptr, nullptr) + 4096);
+  // pooled statistics of ALL chunks as fp16 (hi, lo) pairs -> one tensor-core GEMM for the Linear 5120 -> 256
+  const size_t rows = (size_t)num_chunks * kSpeakers;
+  const size_t split_bytes = align_up(rows * 2 * kStatsDim * sizeof(__half), 1024);
+  const size_t sub_bytes = carve_emb(nbmax, nullptr, nullptr);
+  int rc = ensure_ws(ctx, sub_bytes + 2 * split_bytes + 4096);
   if (rc) return rc;
   if ((rc = push_meta(ctx, chunk_off, chunk_valid, num_chunks, st))) return rc;
   EmbWs w;
   carve_emb(nbmax, ctx->ws, &w);
+  __half* st_hi = reinterpret_cast<__half*>(reinterpret_cast<char*>(ctx->ws) + sub_bytes);
+  __half* st_lo = reinterpret_cast<__half*>(reinterpret_cast<char*>(ctx->ws) + sub_bytes + split_bytes);
   for (int c0 = 0; c0 < num_chunks; c0 += nbmax) {
     const int nb = (num_chunks - c0) < nbmax ? (num_chunks - c0) : nbmax;
     if ((rc = fbank_forward(ctx->emb, wav, ctx->d_off + c0, ctx->d_valid + c0, nb, w.fbank, w.fmean, st))) return rc;
@@ -554,13 +564,15 @@ int b200_emb_forward(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, 
       if ((rc = trunk_run(ctx, w, nb, st))) return rc;
     }
     if (ctx->profile) ctx->trunk_segments += nb;
-    if ((rc = stats_pool_forward(w.A, masks + (size_t)c0 * kSpeakers * kFrames, w.stats, nb, st))) return rc;
-    if ((rc = sgemm_nt(w.stats, 2 * kStatsDim, ctx->emb.seg1_w, 2 * kStatsDim, emb + (size_t)c0 * kSpeakers * kEmbDim,
-                       kEmbDim, ctx->emb.seg1_b, nb * kSpeakers, kEmbDim, 2 * kStatsDim, 0, st)))
+    const size_t o = (size_t)c0 * kSpeakers * 2 * kStatsDim;
+    if ((rc = stats_pool_forward(w.A, masks + (size_t)c0 * kSpeakers * kFrames, nullptr, st_hi + o, st_lo + o, nb, st)))
       return rc;
-    ctx->launches += 2;
+    ctx->launches += 1;
   }
-  return B200_OK;
+  rc = gemm_tc_split(st_hi, st_lo, 2 * kStatsDim, ctx->emb.seg1_w_hi, ctx->emb.seg1_w_lo, 2 * kStatsDim, emb, kEmbDim,
+                     nullptr, nullptr, 0, ctx->emb.seg1_b, (int)rows, kEmbDim, 2 * kStatsDim, 0, ctx->num_sms, st);
+  ctx->launches += 1;
+  return rc;
 }
 
 int b200_emb_fbank(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, const int32_t* chunk_valid,

@@ -34,6 +34,8 @@ struct EmbWeights {
   std::vector<BlockWeights> blocks;   // 16 BasicBlocks
   float* seg1_w = nullptr;       // [256][5120] fp32 (PyTorch layout)
   float* seg1_b = nullptr;       // [256]
+  __half* seg1_w_hi = nullptr;   // fp16 (hi, lo) split of seg1_w for the tensor-core GEMM
+  __half* seg1_w_lo = nullptr;
   // fbank constants
   float* window = nullptr;       // [400] hamming
   float* mel_w = nullptr;        // packed non-zero mel weights
@@ -57,7 +59,8 @@ int fbank_center(float* fbank, const float* fmean, int B, cudaStream_t stream);
 int frames_to_nchw(const __half* feat, float* out, int B, cudaStream_t stream);
 
 // masked statistics pooling: feat [B][10][125][256] fp16 NHWC, masks [B][3][589] u8 -> stats [B*3][5120] fp32
-int stats_pool_forward(const __half* feat, const unsigned char* masks, float* stats, int B, cudaStream_t stream);
+int stats_pool_forward(const __half* feat, const unsigned char* masks, float* stats, __half* stats_hi,
+                       __half* stats_lo, int B, cudaStream_t stream);
 // generic weighted pooling used by the known-answer tests: seq [B][F][T] fp32, w [B][S][Tw] fp32 -> [B][S][2F]
 int stats_pool_generic(const float* seq, const float* w, float* out, int B, int F, int T, int S, int Tw,
                        cudaStream_t stream);

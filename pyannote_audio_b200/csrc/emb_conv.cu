@@ -577,40 +577,37 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    const int q = warp & 3;                                // TMEM lane quadrant
-    // Output channels are spread over the four lane quadrants (cpq per quadrant: 8 / 16 / 32 for C_out = 32 / 64 /
-    // >= 128; the weight rows were permuted accordingly at load) so that all four epilogue warps share the work.
-    const int cpq = p.C_out >= 128 ? 32 : p.C_out / 4;
-    const int parts = cpq / 8;                             // 16-byte pieces per pixel owned by this warp
-    __half* s_out = reinterpret_cast<__half*>(s_stage_ep + q * 4096);          // [32 px][cpq ch]
-    __half* s_res = reinterpret_cast<__half*>(s_stage_ep + q * 4096 + 2048);   // [32 px][cpq ch]
+    const int q = warp & 3;                                // TMEM lane quadrant = block of 32 output channels
+    __half* s_out = reinterpret_cast<__half*>(s_stage_ep + q * 4096);          // [32 px][32 ch]
+    __half* s_res = reinterpret_cast<__half*>(s_stage_ep + q * 4096 + 2048);   // [32 px][32 ch]
+    const int prow = lane >> 2, ppart = lane & 3;          // cooperative 16-byte I/O: 8 pixels x 4 parts per pass
     uint32_t acc = 0, acc_phase = 0;
     const int npix = p.bw * p.bh;
-    const bool lane_on = lane < cpq;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       int b, h0, w0, mt;
       decode(item, b, h0, w0, mt);
-      const int c0 = p.C_out >= 128 ? mt * 128 + q * 32 : q * cpq;      // first channel of this warp
-      const float bias = lane_on ? s_bias[c0 + lane] : 0.f;
-      // piece e = i*32 + lane of a 32-pixel chunk -> (pixel e / parts, part e % parts); global pixel index or -1
-      auto pixel_of = [&](int n) -> long long {
-        const int rr = n / p.bw, x = n - rr * p.bw;
-        const bool ok = n < npix && (h0 + rr) < p.H && (w0 + x) < p.W;
-        return ok ? (((long long)b * p.H + h0 + rr) * p.W + w0 + x) : -1;
-      };
+      const int c0 = mt * 128 + q * 32;                    // first channel of this warp (C_out is a multiple of 128)
+      const float bias = s_bias[c0 + lane];
+      // global pixel index of the 4 pixels this lane moves per chunk (16-byte pieces), -1 when outside the image
+      long long gp[4], gpn[4];
       uint4 rpre[4];
-      auto load_res = [&](int n0) {
+      auto pixels = [&](int n0, long long (&dst)[4]) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          rpre[i] = make_uint4(0, 0, 0, 0);
-          if (i < parts) {
-            const int e = i * 32 + lane;
-            const long long gp = pixel_of(n0 + e / parts);
-            if (gp >= 0) rpre[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + gp * p.C_out + c0 + (e % parts) * 8));
-          }
+          const int n = n0 + i * 8 + prow;
+          const int rr = n / p.bw, x = n - rr * p.bw;
+          const bool ok = n < npix && (h0 + rr) < p.H && (w0 + x) < p.W;
+          dst[i] = ok ? (((long long)b * p.H + h0 + rr) * p.W + w0 + x) : -1;
         }
       };
-      if (p.residual) load_res(0);                         // independent of the MMAs: issue before waiting
+      auto load_res = [&](const long long (&g)[4]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          rpre[i] = g[i] >= 0 ? __ldg(reinterpret_cast<const uint4*>(p.residual + g[i] * p.C_out + c0 + ppart * 8))
+                              : make_uint4(0, 0, 0, 0);
+      };
+      pixels(0, gp);
+      if (p.residual) load_res(gp);                        // independent of the MMAs: issue before waiting
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
@@ -620,39 +617,34 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias;
+        const bool more = n0 + 32 < npix;
+        if (more) pixels(n0 + 32, gpn);
         if (p.residual) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i < parts) {
-              const int e = i * 32 + lane;
-              *reinterpret_cast<uint4*>(s_res + (e / parts) * cpq + (e % parts) * 8) = rpre[i];
-            }
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(s_res + (i * 8 + prow) * 32 + ppart * 8) = rpre[i];
           __syncwarp();
-          if (n0 + 32 < npix) load_res(n0 + 32);           // prefetch the next chunk's residual
-          if (lane_on) {
+          if (more) load_res(gpn);                         // prefetch the next chunk's residual
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __half2float(s_res[j * cpq + lane]);
-          }
+          for (int j = 0; j < 32; ++j) v[j] += __half2float(s_res[j * 32 + lane]);
         }
-        if (lane_on) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = v[j];
-            if (p.relu) a = fmaxf(a, 0.f);
-            s_out[j * cpq + lane] = __float2half_rn(a);
-          }
+        for (int j = 0; j < 32; ++j) {
+          float a = v[j];
+          if (p.relu) a = fmaxf(a, 0.f);
+          s_out[j * 32 + lane] = __float2half_rn(a);
         }
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < parts) {
-            const int e = i * 32 + lane;
-            const long long gp = pixel_of(n0 + e / parts);
-            if (gp >= 0)
-              *reinterpret_cast<uint4*>(p.out + gp * p.C_out + c0 + (e % parts) * 8) =
-                  *reinterpret_cast<const uint4*>(s_out + (e / parts) * cpq + (e % parts) * 8);
-          }
+        for (int i = 0; i < 4; ++i) {
+          if (gp[i] >= 0)
+            *reinterpret_cast<uint4*>(p.out + gp[i] * p.C_out + c0 + ppart * 8) =
+                *reinterpret_cast<const uint4*>(s_out + (i * 8 + prow) * 32 + ppart * 8);
+        }
         __syncwarp();
+        if (more) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) gp[i] = gpn[i];
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -745,46 +737,54 @@ __global__ void conv_simt_kernel(const __half* __restrict__ in, const __half* __
 // first conv: 1 -> 32 channels on the (mean-centred) fbank, fp32 in, fp16 NHWC out
 //   x[b][h=f][w=t] = fbank[b][t][f] - mean[b][f]   (resnet.py:411-413 permute + wespeaker/__init__.py:138)
 // ------------------------------------------------------------------------------------------------
-__global__ void conv1_kernel(const float* __restrict__ fbank, const float* __restrict__ fmean,
+// block = (b, tile of 128 time frames): the (130 x 80) fbank tile is staged in shared memory with coalesced reads,
+// then thread = time frame walks the 80 frequency rows so that every warp store is 32 x 64 B contiguous.
+constexpr int kC1Tile = 128;
+__global__ void __launch_bounds__(kC1Tile) conv1_kernel(const float* __restrict__ fbank, const float* __restrict__ fmean,
                              const float* __restrict__ w /*[32][9] folded*/, const float* __restrict__ bias /*[32]*/,
                              __half* __restrict__ out, int B) {
   __shared__ float sw[32 * 9];
   __shared__ float sb[32];
+  __shared__ float sx[(kC1Tile + 2) * (kMel + 1)];        // [t][f], +1 padding against bank conflicts
+  const int b = blockIdx.y, t0 = blockIdx.x * kC1Tile;
   for (int i = threadIdx.x; i < 288; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*80*998, h fastest for coalesced reads
-  const size_t total = (size_t)B * kMel * kFbankFrames;
-  if (idx >= total) return;
-  const int h = idx % kMel;
-  const int t = (idx / kMel) % kFbankFrames;
-  const int b = idx / ((size_t)kMel * kFbankFrames);
-  float x[9];
-#pragma unroll
-  for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-    for (int kw = 0; kw < 3; ++kw) {
-      const int hh = h + kh - 1, tt = t + kw - 1;
-      float v = 0.f;
-      if (hh >= 0 && hh < kMel && tt >= 0 && tt < kFbankFrames)
-        v = fbank[((size_t)b * kFbankFrames + tt) * kMel + hh] - fmean[b * kMel + hh];
-      x[kh * 3 + kw] = v;
-    }
-  __half2 o[16];
-#pragma unroll
-  for (int c = 0; c < 32; c += 2) {
-    float a0 = sb[c], a1 = sb[c + 1];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      a0 = fmaf(x[k], sw[c * 9 + k], a0);
-      a1 = fmaf(x[k], sw[(c + 1) * 9 + k], a1);
-    }
-    o[c / 2] = __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+  for (int i = threadIdx.x; i < (kC1Tile + 2) * kMel; i += blockDim.x) {
+    const int tt = i / kMel, f = i - tt * kMel;
+    const int t = t0 - 1 + tt;
+    float v = 0.f;
+    if (t >= 0 && t < kFbankFrames) v = fbank[((size_t)b * kFbankFrames + t) * kMel + f] - fmean[b * kMel + f];
+    sx[tt * (kMel + 1) + f] = v;
   }
-  uint4* op = reinterpret_cast<uint4*>(out + (((size_t)b * kMel + h) * kFbankFrames + t) * 32);
-  const uint4* src = reinterpret_cast<const uint4*>(o);
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= kFbankFrames) return;
+  const float* col = sx + threadIdx.x * (kMel + 1);        // rows tt = threadIdx.x + {0,1,2} <-> t-1, t, t+1
+  for (int h = 0; h < kMel; ++h) {
+    float x[9];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) op[i] = src[i];
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hh = h + kh - 1;
+      const bool ok = hh >= 0 && hh < kMel;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) x[kh * 3 + kw] = ok ? col[kw * (kMel + 1) + hh] : 0.f;
+    }
+    __half2 o[16];
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+      float a0 = sb[c], a1 = sb[c + 1];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        a0 = fmaf(x[k], sw[c * 9 + k], a0);
+        a1 = fmaf(x[k], sw[(c + 1) * 9 + k], a1);
+      }
+      o[c / 2] = __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+    }
+    uint4* op = reinterpret_cast<uint4*>(out + (((size_t)b * kMel + h) * kFbankFrames + t) * 32);
+    const uint4* src = reinterpret_cast<const uint4*>(o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) op[i] = src[i];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -957,10 +957,12 @@ static int conv2_forward(const ConvLayer& L, const __half* in, const __half* res
 
 int conv_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H_in, int W_in,
                  int relu, int impl, int num_sms, cudaStream_t stream) {
-  if (impl == 7) {
-    // channels-as-M tcgen05 conv for stride-1 3x3, per-tap pixels-as-M kernel otherwise
-    if (L.ksize == 3 && L.stride == 1) return conv3_forward(L, in, residual, out, B, H_in, W_in, relu, num_sms, stream);
-    impl = 1;
+  if (impl == 7 || impl == 8) {
+    // channels-as-M tcgen05 conv for stride-1 3x3 with C_out >= 128 (N = 256 pixels balances the A-operand read);
+    // impl 8 (default): narrower layers use the strip-streaming pixels-as-M kernel, impl 7: the per-tap kernel
+    if (L.ksize == 3 && L.stride == 1 && L.C_out >= 128)
+      return conv3_forward(L, in, residual, out, B, H_in, W_in, relu, num_sms, stream);
+    impl = (impl == 8) ? 6 : 1;
   }
   if (impl >= 3) {
     // 3: v2 for C_in >= 64 (128B swizzle), base_offset set; 4: v2 also for C_in = 32 (64B swizzle);
@@ -1036,8 +1038,8 @@ int conv_forward(const ConvLayer& L, const __half* in, const __half* residual, _
 
 int conv1_forward(const float* fbank, const float* fmean, const float* w, const float* bias, __half* out, int B,
                   cudaStream_t stream) {
-  const size_t total = (size_t)B * kMel * kFbankFrames;
-  conv1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(fbank, fmean, w, bias, out, B);
+  dim3 grid(ceil_div(kFbankFrames, kC1Tile), B);
+  conv1_kernel<<<grid, kC1Tile, 0, stream>>>(fbank, fmean, w, bias, out, B);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }

@@ -178,7 +178,8 @@ int fbank_forward(const EmbWeights& W, const float* wav, const long long* chunk_
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) stats_pool_kernel(const __half* __restrict__ feat,
                                                          const unsigned char* __restrict__ masks,
-                                                         float* __restrict__ stats) {
+                                                         float* __restrict__ stats, __half* __restrict__ stats_hi,
+                                                         __half* __restrict__ stats_lo) {
   // grid (10 freq rows, B); thread = channel c; feat[b][h][t][c]
   __shared__ float s_w[kSpeakers][kEmbT];
   const int h = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
@@ -221,15 +222,26 @@ __global__ void __launch_bounds__(256) stats_pool_kernel(const __half* __restric
 #pragma unroll
   for (int s = 0; s < kSpeakers; ++s) {
     const float var = sd[s] / (v1[s] - v2[s] / v1[s] + 1e-8f);
-    float* o = stats + ((size_t)b * kSpeakers + s) * (2 * kStatsDim);
-    o[c * 10 + h] = mean[s];
-    o[kStatsDim + c * 10 + h] = sqrtf(var);
+    const size_t row = ((size_t)b * kSpeakers + s) * (2 * kStatsDim);
+    const float sdv = sqrtf(var);
+    if (stats) {
+      stats[row + c * 10 + h] = mean[s];
+      stats[row + kStatsDim + c * 10 + h] = sdv;
+    }
+    if (stats_hi) {   // (hi, lo) fp16 split consumed by gemm_tc_split (Linear 5120 -> 256)
+      const __half mh = __float2half_rn(mean[s]), sh = __float2half_rn(sdv);
+      stats_hi[row + c * 10 + h] = mh;
+      stats_lo[row + c * 10 + h] = __float2half_rn(mean[s] - __half2float(mh));
+      stats_hi[row + kStatsDim + c * 10 + h] = sh;
+      stats_lo[row + kStatsDim + c * 10 + h] = __float2half_rn(sdv - __half2float(sh));
+    }
   }
 }
 
-int stats_pool_forward(const __half* feat, const unsigned char* masks, float* stats, int B, cudaStream_t stream) {
+int stats_pool_forward(const __half* feat, const unsigned char* masks, float* stats, __half* stats_hi,
+                       __half* stats_lo, int B, cudaStream_t stream) {
   dim3 grid(10, B);
-  stats_pool_kernel<<<grid, 256, 0, stream>>>(feat, masks, stats);
+  stats_pool_kernel<<<grid, 256, 0, stream>>>(feat, masks, stats, stats_hi, stats_lo);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }
