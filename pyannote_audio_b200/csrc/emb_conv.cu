@@ -662,6 +662,220 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// conv_tc4_kernel: layer1 (32 -> 32 channels, stride-1 3x3) with the horizontal taps folded into N
+//
+// With C_out = 32 the pixels-as-M kernels issue 18 MMAs of N = 32 per 128-pixel row, each paying the 128-cycle
+// A-operand read (12 % of the tensor rate).  Here one MMA produces the partial sums of all three horizontal taps:
+//   P[m][(kw, co)] = sum_{kh, ci} X[row + kh - 1][m][ci] * W[kh][kw][co][ci]          N = 3 * 32 = 96
+// (6 MMAs per row, unshifted A), and the epilogue finishes   out[s][co] = P[s-1][(0,co)] + P[s][(1,co)] + P[s+1][(2,co)]
+// with warp shuffles across neighbouring pixels (= neighbouring TMEM lanes); tiles advance by 126 pixels because the
+// first and last pixel of a 128-row slot only serve as halo.  Strip streaming over input rows as in conv_tc2_kernel.
+// ------------------------------------------------------------------------------------------------
+struct ConvV4Params {
+  int B, H, W, tiles_w, R, nhseg, num_items, relu, n_aslots;
+  const float* bias;
+  const __half* residual;
+  __half* out;
+  uint32_t a_bytes, idesc, w_off, a_off, x_off;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvV4Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t bar_afull = base, bar_aempty = base + 64, bar_tfull = base + 384, bar_tempty = base + 416;
+  const uint32_t bar_w = base + 448;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + 512);
+  float* s_bias = reinterpret_cast<float*>(gbase + 1024);
+  float* s_x = reinterpret_cast<float*>(gbase + p.x_off);      // [2 parity][4 warps][2 (P0 of lane 31, P2 of lane 0)][32]
+  const uint32_t w_smem = base + p.w_off, a_smem = base + p.a_off;
+  constexpr uint32_t kWBytes = 96 * 32 * 2;                    // one kh slice of the folded weights
+  constexpr uint32_t kAccCols = 128;                           // TMEM column stride between accumulators
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.n_aslots; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
+    for (int a = 0; a < 4; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+    mbar_init(bar_w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int item, int& b, int& wt, int& h0, int& h1) {
+    const int hs = item % p.nhseg;
+    int t = item / p.nhseg;
+    wt = t % p.tiles_w;
+    b = t / p.tiles_w;
+    h0 = hs * p.R;
+    h1 = min(p.H, h0 + p.R);
+  };
+
+  if (warp == 0) {
+    const bool leader = elect_one_sync();
+    if (leader) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      mbar_expect_tx(bar_w, 3u * kWBytes);
+      for (int kh = 0; kh < 3; ++kh) tma_load_3d(&tmB, bar_w, w_smem + kh * kWBytes, 0, 0, kh);
+    }
+    __syncwarp();
+    uint32_t as = 0, aph = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int b, wt, h0, h1;
+      decode(item, b, wt, h0, h1);
+      const int R = h1 - h0;
+      for (int t = 0; t < R + 2; ++t) {
+        mbar_wait(bar_aempty + 8 * as, aph ^ 1);
+        if (leader) {
+          mbar_expect_tx(bar_afull + 8 * as, p.a_bytes);
+          tma_load_4d(&tmA, bar_afull + 8 * as, a_smem + as * p.a_bytes, 0, wt * 126 - 1, h0 - 1 + t, b);
+        }
+        __syncwarp();
+        if (++as == (uint32_t)p.n_aslots) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one_sync();
+    const uint32_t dhi = desc_hi(512u, 4u);                 // 64-byte rows, SWIZZLE_64B
+    mbar_wait(bar_w, 0);
+    tc_fence_after();
+    uint32_t as = 0, aph = 0, grow = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int b, wt, h0, h1;
+      decode(item, b, wt, h0, h1);
+      const int R = h1 - h0;
+      for (int t = 0; t < R + 2; ++t) {
+        mbar_wait(bar_afull + 8 * as, aph);
+        tc_fence_after();
+        const uint32_t alo = desc_lo(a_smem + as * p.a_bytes);
+        for (int kh = 0; kh < 3; ++kh) {
+          const int r = t - kh;
+          if (r < 0 || r >= R) continue;
+          const uint32_t g = grow + (uint32_t)r;
+          const uint32_t acc = g & 3u;
+          if (kh == 0) {
+            mbar_wait(bar_tempty + 8 * acc, ((g >> 2) & 1u) ^ 1u);
+            tc_fence_after();
+          }
+          if (leader) {
+            const uint32_t d_tmem = tmem_base + acc * kAccCols;
+            const uint32_t blo = desc_lo(w_smem + kh * kWBytes);
+            tc_mma_f16(d_tmem, desc_from(dhi, alo), desc_from(dhi, blo), p.idesc, kh != 0);
+            tc_mma_f16(d_tmem, desc_from(dhi, alo + 2), desc_from(dhi, blo + 2), p.idesc, 1);
+            if (kh == 2) tc_commit(bar_tfull + 8 * acc);
+          }
+          __syncwarp();
+        }
+        if (leader) tc_commit(bar_aempty + 8 * as);
+        __syncwarp();
+        if (++as == (uint32_t)p.n_aslots) { as = 0; aph ^= 1; }
+      }
+      grow += (uint32_t)R;
+    }
+  } else {
+    const int q = warp & 3;
+    uint32_t grow = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int b, wt, h0, h1;
+      decode(item, b, wt, h0, h1);
+      const int R = h1 - h0;
+      const int s = q * 32 + lane;                         // slot pixel of this thread
+      const int w = wt * 126 - 1 + s;                      // image column
+      const bool valid = s >= 1 && s <= 126 && w < p.W;
+      for (int r = 0; r < R; ++r) {
+        const uint32_t g = grow + (uint32_t)r;
+        const uint32_t acc = g & 3u;
+        const size_t pix = (((size_t)b * p.H + (h0 + r)) * p.W + (valid ? w : 0)) * 32;
+        uint4 rpre[4];
+        if (p.residual) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) rpre[j4] = valid ? __ldg(rp + j4) : make_uint4(0, 0, 0, 0);
+        }
+        mbar_wait(bar_tfull + 8 * acc, (g >> 2) & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols;
+        uint32_t p0[32], p1[32], p2[32];
+        tc_ld32(taddr, p0);
+        tc_ld32(taddr + 32, p1);
+        tc_ld32(taddr + 64, p2);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);  // accumulator drained into registers
+        // horizontal taps: kw=0 from the pixel to the left (lane-1), kw=2 from the pixel to the right (lane+1)
+        float* xb = s_x + ((g & 1u) * 4 + q) * 64;
+        if (lane == 31) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) xb[j] = __uint_as_float(p0[j]);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) xb[32 + j] = __uint_as_float(p2[j]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const float* xl = s_x + ((g & 1u) * 4 + (q > 0 ? q - 1 : 0)) * 64;        // left warp's lane-31 P0
+        const float* xr = s_x + ((g & 1u) * 4 + (q < 3 ? q + 1 : 3)) * 64 + 32;   // right warp's lane-0 P2
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float l = __shfl_up_sync(0xffffffffu, __uint_as_float(p0[j]), 1);
+          float rr = __shfl_down_sync(0xffffffffu, __uint_as_float(p2[j]), 1);
+          if (lane == 0) l = xl[j];
+          if (lane == 31) rr = xr[j];
+          v[j] = (l + __uint_as_float(p1[j])) + rr + s_bias[j];
+        }
+        if (valid) {
+          if (p.residual) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const __half2* h2 = reinterpret_cast<const __half2*>(&rpre[j4]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 f = __half22float2(h2[e]);
+                v[j4 * 8 + 2 * e] += f.x;
+                v[j4 * 8 + 2 * e + 1] += f.y;
+              }
+            }
+          }
+          uint4* op = reinterpret_cast<uint4*>(p.out + pix);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint4 u;
+            __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a = v[j4 * 8 + 2 * e], c = v[j4 * 8 + 2 * e + 1];
+              if (p.relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+              h2[e] = __floats2half2_rn(a, c);
+            }
+            op[j4] = u;
+          }
+        }
+      }
+      grow += (uint32_t)R;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // SIMT reference conv (same math, CUDA cores) -- debugging aid and A/B check for the tensor-core path
 // ------------------------------------------------------------------------------------------------
@@ -800,6 +1014,60 @@ PFN_encodeTiled get_encode() {
       fn = reinterpret_cast<PFN_encodeTiled>(ptr);
   }
   return fn;
+}
+
+static int conv4_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H, int W,
+                         int relu, int num_sms, cudaStream_t stream) {
+  B200_CHECK(L.w4 != nullptr && L.C_in == 32 && L.C_out == 32, B200_ERR_STATE, "conv v4: folded weights missing");
+  ConvV4Params p{};
+  p.B = B; p.H = H; p.W = W; p.relu = relu; p.bias = L.bias; p.residual = residual; p.out = out;
+  p.tiles_w = ceil_div(W, 126);
+  const int strips = B * p.tiles_w;
+  int nhseg = 1;
+  if (strips < 2 * num_sms) nhseg = ceil_div(2 * num_sms, strips);
+  if (nhseg > H / 2) nhseg = H / 2 > 0 ? H / 2 : 1;
+  p.R = ceil_div(H, nhseg);
+  p.nhseg = ceil_div(H, p.R);
+  p.num_items = B * p.tiles_w * p.nhseg;
+  p.a_bytes = 128u * 32 * 2;
+  p.n_aslots = 8;
+  p.idesc = (1u << 4) | ((uint32_t)(96 >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+  p.x_off = 2048;                    // 2 x 4 x 64 floats = 2 KB
+  p.w_off = 4096;                    // 3 x 6 KB
+  p.a_off = 4096 + 18432 + 1024;     // 23552 = 23 x 1024
+  PFN_encodeTiled enc = get_encode();
+  B200_CHECK(enc != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {64, (cuuint64_t)W * 64, (cuuint64_t)H * W * 64};
+    cuuint32_t box[4] = {32, 128, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(in), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(A, v4) failed: %d", (int)r);
+  }
+  {
+    cuuint64_t dims[3] = {32, 96, 3};
+    cuuint64_t strides[2] = {64, 96 * 64};
+    cuuint32_t box[3] = {32, 96, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(L.w4), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(B, v4) failed: %d", (int)r);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(conv_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const size_t smem = 1024 + p.a_off + (size_t)p.n_aslots * p.a_bytes;
+  const int grid = p.num_items < num_sms ? p.num_items : num_sms;
+  conv_tc4_kernel<<<grid, kTcThreads, smem, stream>>>(tmA, tmB, p);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
 }
 
 static int conv3_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H, int W,
@@ -962,6 +1230,8 @@ int conv_forward(const ConvLayer& L, const __half* in, const __half* residual, _
     // impl 8 (default): narrower layers use the strip-streaming pixels-as-M kernel, impl 7: the per-tap kernel
     if (L.ksize == 3 && L.stride == 1 && L.C_out >= 128)
       return conv3_forward(L, in, residual, out, B, H_in, W_in, relu, num_sms, stream);
+    if (impl == 8 && L.ksize == 3 && L.stride == 1 && L.C_in == 32 && L.C_out == 32 && L.w4)
+      return conv4_forward(L, in, residual, out, B, H_in, W_in, relu, num_sms, stream);   // horizontal taps folded into N
     impl = (impl == 8) ? 6 : 1;
   }
   if (impl >= 3) {
