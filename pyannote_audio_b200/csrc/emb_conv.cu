@@ -830,10 +830,12 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
+          // unconditional broadcast loads + selects: a per-element `if (lane == ..)` compiles to 64 divergent branches
+          const float lx = xl[j], rx = xr[j];
           float l = __shfl_up_sync(0xffffffffu, __uint_as_float(p0[j]), 1);
           float rr = __shfl_down_sync(0xffffffffu, __uint_as_float(p2[j]), 1);
-          if (lane == 0) l = xl[j];
-          if (lane == 31) rr = xr[j];
+          l = (lane == 0) ? lx : l;
+          rr = (lane == 31) ? rx : rr;
           v[j] = (l + __uint_as_float(p1[j])) + rr + s_bias[j];
         }
         if (valid) {
