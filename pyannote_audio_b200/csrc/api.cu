@@ -165,13 +165,14 @@ int make_conv(b200_ctx* ctx, const b200_conv_bn& src, int cin, int cout, int k, 
   int rc;
   if ((rc = upload(ctx, w, &L->w))) return rc;
   if ((rc = upload(ctx, bias, &L->bias))) return rc;
-  if (k == 3 && stride == 1 && cin == 32 && cout == 32) {
-    std::vector<__half> w4((size_t)3 * 96 * 32);
+  if (k == 3 && stride == 1 && cin == cout && (cin == 32 || cin == 64)) {   // conv_tc4_kernel: [kw][(kh, c_out)][c_in]
+    const int C = cin;
+    std::vector<__half> w4((size_t)9 * C * C);
     for (int kh = 0; kh < 3; ++kh)
       for (int kw = 0; kw < 3; ++kw)
-        for (int co = 0; co < 32; ++co)
-          for (int ci = 0; ci < 32; ++ci)
-            w4[((size_t)kh * 96 + kw * 32 + co) * 32 + ci] = w[((size_t)(kh * 3 + kw) * cout + co) * cin + ci];
+        for (int co = 0; co < C; ++co)
+          for (int ci = 0; ci < C; ++ci)
+            w4[(((size_t)kw * 3 + kh) * C + co) * C + ci] = w[((size_t)(kh * 3 + kw) * cout + co) * cin + ci];
     if ((rc = upload(ctx, w4, &L->w4))) return rc;
   }
   if (k == 3 && stride == 1 && cout >= 128) {   // copy for the channels-as-M kernel (rows padded to 128)

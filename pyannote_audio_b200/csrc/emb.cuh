@@ -7,7 +7,7 @@ namespace b200 {
 struct ConvLayer {
   int C_in = 0, C_out = 0, ksize = 3, stride = 1;
   __half* w = nullptr;     // device, [tap][C_out][C_in] fp16, BN scale folded
-  __half* w4 = nullptr;    // 32->32 layers: [kh][(kw, c_out) = 96][c_in] for conv_tc4_kernel (horizontal taps folded into N)
+  __half* w4 = nullptr;    // 32->32 / 64->64 stride-1 layers: [kw][(kh, c_out) = 3C][c_in] for conv_tc4_kernel
   __half* w3 = nullptr;    // same with C_out zero-padded to a multiple of 128 (conv_tc3_kernel's A operand)
   float* bias = nullptr;   // device, [C_out] fp32 (folded BN shift)
 };

@@ -664,43 +664,52 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
 
 // ------------------------------------------------------------------------------------------------
-// conv_tc4_kernel: layer1 (32 -> 32 channels, stride-1 3x3) with the horizontal taps folded into N
+// conv_tc4_kernel: stride-1 3x3 convolutions with few channels (C = C_in = C_out in {32, 64}): vertical taps folded
+// into N, vertical sum done by the tensor core
 //
-// With C_out = 32 the pixels-as-M kernels issue 18 MMAs of N = 32 per 128-pixel row, each paying the 128-cycle
-// A-operand read (12 % of the tensor rate).  Here one MMA produces the partial sums of all three horizontal taps:
-//   P[m][(kw, co)] = sum_{kh, ci} X[row + kh - 1][m][ci] * W[kh][kw][co][ci]          N = 3 * 32 = 96
-// (6 MMAs per row, unshifted A), and the epilogue finishes   out[s][co] = P[s-1][(0,co)] + P[s][(1,co)] + P[s+1][(2,co)]
-// with warp shuffles across neighbouring pixels (= neighbouring TMEM lanes); tiles advance by 126 pixels because the
-// first and last pixel of a 128-row slot only serve as halo.  Strip streaming over input rows as in conv_tc2_kernel.
+// With C_out = N <= 64 the pixels-as-M kernels pay the 128-cycle A-operand read per MMA for 12-25 % of the tensor rate.
+// Here one MMA of input row t (A = 128 pixels x 16 channels, shifted by kw pixel rows inside the slot) multiplies the
+// weights of all three vertical taps at once:
+//     Q_t[m][(kh, co)] = sum_{kw, ci} X[t][m + kw - 1][ci] * W[kh][kw][co][ci]                N = 3 C
+// and   out[r] = Q_{r-1}[kh=0] + Q_r[kh=1] + Q_{r+1}[kh=2]   needs no data movement at all: the accumulators of
+// consecutive output rows are C-column blocks of a TMEM ring laid out in DESCENDING row order, so the N = 3C columns
+// of input row t land exactly on the blocks of output rows t+1, t, t-1 and the tensor core performs the vertical sum.
+// Every MMA accumulates (blocks are zeroed with tcgen05.st by the epilogue after it has drained them), the ring seam
+// and the strip borders split an MMA into two narrower ones.  3x fewer MMAs than conv_tc2_kernel, and the epilogue
+// reads C columns per row (a shuffle-based horizontal fold measured 2140 cycles per tile, 2/3 of it smem exchange).
 // ------------------------------------------------------------------------------------------------
 struct ConvV4Params {
-  int B, H, W, tiles_w, R, nhseg, num_items, relu, n_aslots;
+  int B, H, W, C, tiles_w, R, nhseg, num_items, relu, n_aslots;
+  int nb_shift;                      // ring of NB = 512 / C accumulator blocks
   const float* bias;
   const __half* residual;
   __half* out;
-  uint32_t a_bytes, idesc, w_off, a_off, x_off;
+  uint32_t a_bytes, a_slot_bytes, wkw_bytes, swizzle, w_off, a_off;
 };
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+constexpr int kV4Threads = 320;   // TMA warp, MMA warp, 2 x 4 epilogue warps (alternate rows)
+
+__global__ void __launch_bounds__(kV4Threads, 1)
 conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvV4Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
-  const uint32_t bar_afull = base, bar_aempty = base + 64, bar_tfull = base + 384, bar_tempty = base + 416;
-  const uint32_t bar_w = base + 448;
+  // header: [0,64) a_full  [64,128) a_empty  [128,256) tfull[16]  [256,384) tempty[16]  [384,392) wbar
+  //         [512,516) tmem slot  [1024,1280) bias
+  const uint32_t bar_afull = base, bar_aempty = base + 64, bar_tfull = base + 128, bar_tempty = base + 256;
+  const uint32_t bar_w = base + 384;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + 512);
   float* s_bias = reinterpret_cast<float*>(gbase + 1024);
-  float* s_x = reinterpret_cast<float*>(gbase + p.x_off);      // [2 parity][4 warps][2 (P0 of lane 31, P2 of lane 0)][32]
   const uint32_t w_smem = base + p.w_off, a_smem = base + p.a_off;
-  constexpr uint32_t kWBytes = 96 * 32 * 2;                    // one kh slice of the folded weights
-  constexpr uint32_t kAccCols = 128;                           // TMEM column stride between accumulators
+  const int C = p.C;
+  const uint32_t NB = 1u << p.nb_shift, nb_mask = NB - 1u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x < 32) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+  if ((int)threadIdx.x < C) s_bias[threadIdx.x] = p.bias[threadIdx.x];
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.n_aslots; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
-    for (int a = 0; a < 4; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+    for (uint32_t a = 0; a < NB; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
     mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -713,6 +722,16 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp >= 2) {                                         // all 512 columns start at zero
+    const uint32_t grp = (uint32_t)(warp - 2) >> 2;
+    const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * 256u;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) tc_st32_zero(t0 + c * 32);
+    tc_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   auto decode = [&](int item, int& b, int& wt, int& h0, int& h1) {
     const int hs = item % p.nhseg;
@@ -727,8 +746,8 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const bool leader = elect_one_sync();
     if (leader) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-      mbar_expect_tx(bar_w, 3u * kWBytes);
-      for (int kh = 0; kh < 3; ++kh) tma_load_3d(&tmB, bar_w, w_smem + kh * kWBytes, 0, 0, kh);
+      mbar_expect_tx(bar_w, 3u * p.wkw_bytes);
+      for (int kw = 0; kw < 3; ++kw) tma_load_3d(&tmB, bar_w, w_smem + kw * p.wkw_bytes, 0, 0, kw);
     }
     __syncwarp();
     uint32_t as = 0, aph = 0;
@@ -740,7 +759,7 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(bar_aempty + 8 * as, aph ^ 1);
         if (leader) {
           mbar_expect_tx(bar_afull + 8 * as, p.a_bytes);
-          tma_load_4d(&tmA, bar_afull + 8 * as, a_smem + as * p.a_bytes, 0, wt * 126 - 1, h0 - 1 + t, b);
+          tma_load_4d(&tmA, bar_afull + 8 * as, a_smem + as * p.a_slot_bytes, 0, wt * kTileM - 1, h0 - 1 + t, b);
         }
         __syncwarp();
         if (++as == (uint32_t)p.n_aslots) { as = 0; aph ^= 1; }
@@ -748,7 +767,10 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     const bool leader = elect_one_sync();
-    const uint32_t dhi = desc_hi(512u, 4u);                 // 64-byte rows, SWIZZLE_64B
+    const uint32_t dhi = desc_hi((p.swizzle == 128) ? 1024u : 512u, (p.swizzle == 128) ? 2u : 4u);
+    const uint32_t rowbytes = (uint32_t)C * 2u, row_units = rowbytes >> 4;
+    const int ksteps = C / 16;
+    const uint32_t idesc0 = (1u << 4) | ((uint32_t)(kTileM >> 4) << 24);
     mbar_wait(bar_w, 0);
     tc_fence_after();
     uint32_t as = 0, aph = 0, grow = 0;
@@ -756,113 +778,113 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int b, wt, h0, h1;
       decode(item, b, wt, h0, h1);
       const int R = h1 - h0;
-      for (int t = 0; t < R + 2; ++t) {
+      for (int t = 0; t < R + 2; ++t) {                    // input row h0 - 1 + t feeds output rows t, t-1, t-2
         mbar_wait(bar_afull + 8 * as, aph);
         tc_fence_after();
-        const uint32_t alo = desc_lo(a_smem + as * p.a_bytes);
-        for (int kh = 0; kh < 3; ++kh) {
-          const int r = t - kh;
-          if (r < 0 || r >= R) continue;
-          const uint32_t g = grow + (uint32_t)r;
-          const uint32_t acc = g & 3u;
-          if (kh == 0) {
-            mbar_wait(bar_tempty + 8 * acc, ((g >> 2) & 1u) ^ 1u);
-            tc_fence_after();
-          }
+        if (t < R) {                                       // output row t receives its first contribution
+          const uint32_t g = grow + (uint32_t)t;
+          mbar_wait(bar_tempty + 8 * (g & nb_mask), ((g >> p.nb_shift) & 1u) ^ 1u);
+          tc_fence_after();
+        }
+        const uint32_t alo0 = desc_lo(a_smem + as * p.a_slot_bytes);
+        const int r_lo = max(t - 2, 0);
+        int ra = min(t, R - 1);
+        while (ra >= r_lo) {                               // runs of rows whose blocks are contiguous in TMEM
+          int rb = ra;
+          while (rb > r_lo && ((grow + (uint32_t)rb) & nb_mask) != 0u) --rb;
+          const uint32_t N = (uint32_t)(ra - rb + 1) * (uint32_t)C;
+          const uint32_t d_tmem = tmem_base + (nb_mask - ((grow + (uint32_t)ra) & nb_mask)) * (uint32_t)C;
+          const uint32_t idesc = idesc0 | ((N >> 3) << 17);
+          const uint32_t bofs = (uint32_t)(t - ra) * (uint32_t)C * rowbytes;   // first vertical tap of this run
           if (leader) {
-            const uint32_t d_tmem = tmem_base + acc * kAccCols;
-            const uint32_t blo = desc_lo(w_smem + kh * kWBytes);
-            tc_mma_f16(d_tmem, desc_from(dhi, alo), desc_from(dhi, blo), p.idesc, kh != 0);
-            tc_mma_f16(d_tmem, desc_from(dhi, alo + 2), desc_from(dhi, blo + 2), p.idesc, 1);
-            if (kh == 2) tc_commit(bar_tfull + 8 * acc);
+            for (int kw = 0; kw < 3; ++kw) {
+              const uint32_t alo = alo0 + kw * row_units;  // absolute-address swizzle: base_offset stays 0
+              const uint32_t blo = desc_lo(w_smem + kw * p.wkw_bytes + bofs);
+              tc_mma_f16(d_tmem, desc_from(dhi, alo), desc_from(dhi, blo), idesc, 1);
+              tc_mma_f16(d_tmem, desc_from(dhi, alo + 2), desc_from(dhi, blo + 2), idesc, 1);
+              if (ksteps == 4) {
+                tc_mma_f16(d_tmem, desc_from(dhi, alo + 4), desc_from(dhi, blo + 4), idesc, 1);
+                tc_mma_f16(d_tmem, desc_from(dhi, alo + 6), desc_from(dhi, blo + 6), idesc, 1);
+              }
+            }
           }
           __syncwarp();
+          ra = rb - 1;
         }
-        if (leader) tc_commit(bar_aempty + 8 * as);
+        if (leader) {
+          tc_commit(bar_aempty + 8 * as);
+          if (t >= 2) tc_commit(bar_tfull + 8 * ((grow + (uint32_t)(t - 2)) & nb_mask));   // row t-2 complete
+        }
         __syncwarp();
         if (++as == (uint32_t)p.n_aslots) { as = 0; aph ^= 1; }
       }
       grow += (uint32_t)R;
     }
   } else {
+    // two epilogue warpgroups (warps 2-5 and 6-9) take alternate rows so that a scheduler always has a second warp
     const int q = warp & 3;
+    const uint32_t grp = (uint32_t)(warp - 2) >> 2;
     uint32_t grow = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       int b, wt, h0, h1;
       decode(item, b, wt, h0, h1);
       const int R = h1 - h0;
-      const int s = q * 32 + lane;                         // slot pixel of this thread
-      const int w = wt * 126 - 1 + s;                      // image column
-      const bool valid = s >= 1 && s <= 126 && w < p.W;
+      const int w = wt * kTileM + q * 32 + lane;
+      const bool valid = w < p.W;
       for (int r = 0; r < R; ++r) {
         const uint32_t g = grow + (uint32_t)r;
-        const uint32_t acc = g & 3u;
-        const size_t pix = (((size_t)b * p.H + (h0 + r)) * p.W + (valid ? w : 0)) * 32;
-        uint4 rpre[4];
+        if ((g & 1u) != grp) continue;
+        const uint32_t blk = g & nb_mask;
+        const size_t pix = (((size_t)b * p.H + (h0 + r)) * p.W + (valid ? w : 0)) * (size_t)C;
+        uint4 rpre[8];
         if (p.residual) {
           const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix);
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) rpre[j4] = valid ? __ldg(rp + j4) : make_uint4(0, 0, 0, 0);
+          for (int j4 = 0; j4 < 8; ++j4)
+            if (j4 * 8 < C) rpre[j4] = valid ? __ldg(rp + j4) : make_uint4(0, 0, 0, 0);
         }
-        mbar_wait(bar_tfull + 8 * acc, (g >> 2) & 1u);
+        mbar_wait(bar_tfull + 8 * blk, (g >> p.nb_shift) & 1u);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols;
-        uint32_t p0[32], p1[32], p2[32];
-        tc_ld32(taddr, p0);
-        tc_ld32(taddr + 32, p1);
-        tc_ld32(taddr + 64, p2);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (nb_mask - blk) * (uint32_t)C;
+        uint32_t acc[64];
+        tc_ld32(taddr, acc);
+        if (C == 64) tc_ld32(taddr + 32, acc + 32);
+        tc_st32_zero(taddr);                               // hand the block back zeroed
+        if (C == 64) tc_st32_zero(taddr + 32);
+        tc_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);  // accumulator drained into registers
-        // horizontal taps: kw=0 from the pixel to the left (lane-1), kw=2 from the pixel to the right (lane+1)
-        float* xb = s_x + ((g & 1u) * 4 + q) * 64;
-        if (lane == 31) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) xb[j] = __uint_as_float(p0[j]);
-        }
-        if (lane == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) xb[32 + j] = __uint_as_float(p2[j]);
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const float* xl = s_x + ((g & 1u) * 4 + (q > 0 ? q - 1 : 0)) * 64;        // left warp's lane-31 P0
-        const float* xr = s_x + ((g & 1u) * 4 + (q < 3 ? q + 1 : 3)) * 64 + 32;   // right warp's lane-0 P2
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          // unconditional broadcast loads + selects: a per-element `if (lane == ..)` compiles to 64 divergent branches
-          const float lx = xl[j], rx = xr[j];
-          float l = __shfl_up_sync(0xffffffffu, __uint_as_float(p0[j]), 1);
-          float rr = __shfl_down_sync(0xffffffffu, __uint_as_float(p2[j]), 1);
-          l = (lane == 0) ? lx : l;
-          rr = (lane == 31) ? rx : rr;
-          v[j] = (l + __uint_as_float(p1[j])) + rr + s_bias[j];
-        }
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * blk);
         if (valid) {
-          if (p.residual) {
+          uint4* op = reinterpret_cast<uint4*>(p.out + pix);
+          const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const __half2* h2 = reinterpret_cast<const __half2*>(&rpre[j4]);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            if (j4 * 8 < C) {
+              const float4 b0 = reinterpret_cast<const float4*>(s_bias)[2 * j4];
+              const float4 b1 = reinterpret_cast<const float4*>(s_bias)[2 * j4 + 1];
+              float v[8] = {__uint_as_float(acc[j4 * 8 + 0]) + b0.x, __uint_as_float(acc[j4 * 8 + 1]) + b0.y,
+                            __uint_as_float(acc[j4 * 8 + 2]) + b0.z, __uint_as_float(acc[j4 * 8 + 3]) + b0.w,
+                            __uint_as_float(acc[j4 * 8 + 4]) + b1.x, __uint_as_float(acc[j4 * 8 + 5]) + b1.y,
+                            __uint_as_float(acc[j4 * 8 + 6]) + b1.z, __uint_as_float(acc[j4 * 8 + 7]) + b1.w};
+              if (p.residual) {
+                const __half2* h2 = reinterpret_cast<const __half2*>(&rpre[j4]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __half22float2(h2[e]);
+                  v[2 * e] += f.x;
+                  v[2 * e + 1] += f.y;
+                }
+              }
+              uint4 u;
+              __half2* o2 = reinterpret_cast<__half2*>(&u);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                float2 f = __half22float2(h2[e]);
-                v[j4 * 8 + 2 * e] += f.x;
-                v[j4 * 8 + 2 * e + 1] += f.y;
+                const __half2 hv = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                o2[e] = p.relu ? __hmax2(hv, zero2) : hv;   // relu after rounding == rounding after relu
               }
+              op[j4] = u;
             }
-          }
-          uint4* op = reinterpret_cast<uint4*>(p.out + pix);
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            uint4 u;
-            __half2* h2 = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float a = v[j4 * 8 + 2 * e], c = v[j4 * 8 + 2 * e + 1];
-              if (p.relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
-              h2[e] = __floats2half2_rn(a, c);
-            }
-            op[j4] = u;
           }
         }
       }
@@ -1020,10 +1042,14 @@ PFN_encodeTiled get_encode() {
 
 static int conv4_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H, int W,
                          int relu, int num_sms, cudaStream_t stream) {
-  B200_CHECK(L.w4 != nullptr && L.C_in == 32 && L.C_out == 32, B200_ERR_STATE, "conv v4: folded weights missing");
+  const int C = L.C_in;
+  B200_CHECK(L.w4 != nullptr && L.C_in == L.C_out && (C == 32 || C == 64), B200_ERR_STATE,
+             "conv v4: folded weights missing");
   ConvV4Params p{};
-  p.B = B; p.H = H; p.W = W; p.relu = relu; p.bias = L.bias; p.residual = residual; p.out = out;
-  p.tiles_w = ceil_div(W, 126);
+  p.B = B; p.H = H; p.W = W; p.C = C; p.relu = relu; p.bias = L.bias; p.residual = residual; p.out = out;
+  p.nb_shift = (C == 32) ? 4 : 3;
+  p.swizzle = (C == 64) ? 128 : 64;
+  p.tiles_w = ceil_div(W, kTileM);
   const int strips = B * p.tiles_w;
   int nhseg = 1;
   if (strips < 2 * num_sms) nhseg = ceil_div(2 * num_sms, strips);
@@ -1031,32 +1057,33 @@ static int conv4_forward(const ConvLayer& L, const __half* in, const __half* res
   p.R = ceil_div(H, nhseg);
   p.nhseg = ceil_div(H, p.R);
   p.num_items = B * p.tiles_w * p.nhseg;
-  p.a_bytes = 128u * 32 * 2;
-  p.n_aslots = 8;
-  p.idesc = (1u << 4) | ((uint32_t)(96 >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-  p.x_off = 2048;                    // 2 x 4 x 64 floats = 2 KB
-  p.w_off = 4096;                    // 3 x 6 KB
-  p.a_off = 4096 + 18432 + 1024;     // 23552 = 23 x 1024
+  p.a_bytes = 130u * C * 2;
+  p.a_slot_bytes = (uint32_t)align_up(p.a_bytes, 1024);
+  p.wkw_bytes = 3u * C * C * 2;                              // one horizontal tap: [(kh, co) = 3C][ci = C]
+  p.n_aslots = 7;
+  p.w_off = 2048;
+  p.a_off = 2048 + (uint32_t)align_up(3u * p.wkw_bytes, 1024);
   PFN_encodeTiled enc = get_encode();
   B200_CHECK(enc != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  const CUtensorMapSwizzle sw = (C == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap tmA, tmB;
   {
-    cuuint64_t dims[4] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {64, (cuuint64_t)W * 64, (cuuint64_t)H * W * 64};
-    cuuint32_t box[4] = {32, 128, 1, 1};
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)C, 130, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(in), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(A, v4) failed: %d", (int)r);
   }
   {
-    cuuint64_t dims[3] = {32, 96, 3};
-    cuuint64_t strides[2] = {64, 96 * 64};
-    cuuint32_t box[3] = {32, 96, 1};
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)3 * C, 3};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)3 * C * C * 2};
+    cuuint32_t box[3] = {(cuuint32_t)C, (cuuint32_t)3 * C, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(L.w4), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(B, v4) failed: %d", (int)r);
   }
@@ -1065,9 +1092,9 @@ static int conv4_forward(const ConvLayer& L, const __half* in, const __half* res
     B200_CUDA_OK(cudaFuncSetAttribute(conv_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const size_t smem = 1024 + p.a_off + (size_t)p.n_aslots * p.a_bytes;
+  const size_t smem = 1024 + p.a_off + (size_t)p.n_aslots * p.a_slot_bytes;
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
-  conv_tc4_kernel<<<grid, kTcThreads, smem, stream>>>(tmA, tmB, p);
+  conv_tc4_kernel<<<grid, kV4Threads, smem, stream>>>(tmA, tmB, p);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }
@@ -1232,8 +1259,8 @@ int conv_forward(const ConvLayer& L, const __half* in, const __half* residual, _
     // impl 8 (default): narrower layers use the strip-streaming pixels-as-M kernel, impl 7: the per-tap kernel
     if (L.ksize == 3 && L.stride == 1 && L.C_out >= 128)
       return conv3_forward(L, in, residual, out, B, H_in, W_in, relu, num_sms, stream);
-    if (impl == 8 && L.ksize == 3 && L.stride == 1 && L.C_in == 32 && L.C_out == 32 && L.w4)
-      return conv4_forward(L, in, residual, out, B, H_in, W_in, relu, num_sms, stream);   // horizontal taps folded into N
+    if (impl == 8 && L.ksize == 3 && L.stride == 1 && L.C_in == L.C_out && L.C_in <= 64 && L.w4)
+      return conv4_forward(L, in, residual, out, B, H_in, W_in, relu, num_sms, stream);   // vertical taps folded into N
     impl = (impl == 8) ? 6 : 1;
   }
   if (impl >= 3) {

@@ -80,6 +80,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// zero 32 TMEM columns of this warp's 32 lanes (accumulator blocks that the MMAs only ever add into)
+__device__ __forceinline__ void tc_st32_zero(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // One lane of the (converged) warp; the tcgen05 / TMA instructions take warp-uniform operands, so the role loops are
 // executed by the whole warp and only the issue itself is predicated on the elected lane.  (A single-lane divergent
 // loop makes the compiler emit ELECT/BRA.U.ANY "for each active lane" sequences around every such instruction:
