@@ -519,28 +519,41 @@ static size_t carve_emb(int NB, void* base, EmbWs* w) {
   return align_up(off, 1024);
 }
 
+// one BasicBlock on nb segments: A -> (Bf, Cf) -> A, in place on the residual
+static int block_run(b200_ctx* ctx, const BlockWeights& B, __half* A, __half* Bf, __half* Cf, int nb, int H, int Wd,
+                     cudaStream_t st) {
+  const int s = B.conv1.stride;
+  const int impl1 = (ctx->conv_impl == 2) ? (s == 1 ? 1 : 0) : ctx->conv_impl;
+  const int impl_s1 = ctx->conv_impl == 2 ? 1 : ctx->conv_impl;
+  const int Ho = (H + 2 - 3) / s + 1, Wo = (Wd + 2 - 3) / s + 1;
+  int rc;
+  if ((rc = conv_forward(B.conv1, A, nullptr, Bf, nb, H, Wd, 1, impl1, ctx->num_sms, st))) return rc;
+  const __half* res = A;
+  if (B.has_shortcut) {
+    if ((rc = conv_forward(B.shortcut, A, nullptr, Cf, nb, H, Wd, 0, impl1, ctx->num_sms, st))) return rc;
+    res = Cf;
+    ctx->launches += 1;
+  }
+  if ((rc = conv_forward(B.conv2, Bf, res, A, nb, Ho, Wo, 1, impl_s1, ctx->num_sms, st))) return rc;
+  ctx->launches += 2;
+  return B200_OK;
+}
+
 // conv1 + 16 BasicBlocks; result (NHWC fp16 [nb][10][125][256]) is left in ws.A
 static int trunk_run(b200_ctx* ctx, const EmbWs& w, int nb, cudaStream_t st) {
   const EmbWeights& E = ctx->emb;
   int rc;
+  int H = kMel, Wd = kFbankFrames;
+  // (running stem + layer1 in L2-sized groups of segments was measured 12-35 % slower than whole sub-batches:
+  //  small grids lose more to tails and launch gaps than the L2 hits return)
   if ((rc = conv1_forward(w.fbank, w.fmean, E.conv1_w, E.conv1_b, w.A, nb, st))) return rc;
   ctx->launches += 1;
-  int H = kMel, Wd = kFbankFrames;
-  for (const BlockWeights& B : E.blocks) {
+  const size_t first = 0;
+  for (size_t b = first; b < E.blocks.size(); ++b) {
+    const BlockWeights& B = E.blocks[b];
+    if ((rc = block_run(ctx, B, w.A, w.Bf, w.Cf, nb, H, Wd, st))) return rc;
     const int s = B.conv1.stride;
-    const int impl1 = (ctx->conv_impl == 2) ? (s == 1 ? 1 : 0) : ctx->conv_impl;
-    const int impl_s1 = ctx->conv_impl == 2 ? 1 : ctx->conv_impl;
-    const int Ho = (H + 2 - 3) / s + 1, Wo = (Wd + 2 - 3) / s + 1;
-    if ((rc = conv_forward(B.conv1, w.A, nullptr, w.Bf, nb, H, Wd, 1, impl1, ctx->num_sms, st))) return rc;
-    const __half* res = w.A;
-    if (B.has_shortcut) {
-      if ((rc = conv_forward(B.shortcut, w.A, nullptr, w.Cf, nb, H, Wd, 0, impl1, ctx->num_sms, st))) return rc;
-      res = w.Cf;
-      ctx->launches += 1;
-    }
-    if ((rc = conv_forward(B.conv2, w.Bf, res, w.A, nb, Ho, Wo, 1, impl_s1, ctx->num_sms, st))) return rc;
-    ctx->launches += 2;
-    H = Ho; Wd = Wo;
+    H = (H + 2 - 3) / s + 1; Wd = (Wd + 2 - 3) / s + 1;
   }
   B200_CHECK(H == 10 && Wd == kEmbT, B200_ERR_STATE, "unexpected trunk output %dx%d", H, Wd);
   return B200_OK;

@@ -1051,11 +1051,13 @@ static int conv4_forward(const ConvLayer& L, const __half* in, const __half* res
   p.swizzle = (C == 64) ? 128 : 64;
   p.tiles_w = ceil_div(W, kTileM);
   const int strips = B * p.tiles_w;
-  int nhseg = 1;
-  if (strips < 2 * num_sms) nhseg = ceil_div(2 * num_sms, strips);
-  if (nhseg > H / 2) nhseg = H / 2 > 0 ? H / 2 : 1;
-  p.R = ceil_div(H, nhseg);
-  p.nhseg = ceil_div(H, p.R);
+  // split H so that (waves of items) x (rows streamed per item, halo included) is smallest
+  long best_cost = -1;
+  for (int nh = 1; nh <= (H > 1 ? H / 2 : 1); ++nh) {
+    const int R = ceil_div(H, nh), n = ceil_div(H, R);
+    const long cost = (long)ceil_div(strips * n, num_sms) * (R + 3);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; p.R = R; p.nhseg = n; }
+  }
   p.num_items = B * p.tiles_w * p.nhseg;
   p.a_bytes = 130u * C * 2;
   p.a_slot_bytes = (uint32_t)align_up(p.a_bytes, 1024);
