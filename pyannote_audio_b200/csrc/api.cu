@@ -15,8 +15,9 @@ struct b200_ctx {
   int device = 0;
   int num_sms = 148;
   int seg_gemm_impl = 1;   // 1 = split-fp16 tcgen05 GEMMs for the LSTM input projections / linear layers, 0 = fp32 SIMT
+  int seg_rec_impl = 1;    // 1 = LSTM recurrence on the tensor cores (needs seg_gemm_impl = 1), 0 = fp32 SIMT cluster kernel
   int conv_impl = 8;   // channels-as-M conv for C_out >= 128, strip-streaming conv for the narrow stride-1 3x3, per-tap conv otherwise
-  int seg_max_batch = 2368;     // chunks per segmentation sub-batch (37 LSTM tiles of 64 sequences x 2 directions)
+  int seg_max_batch = 4736;     // chunks per segmentation sub-batch (37 LSTM tiles of 128 sequences x 2 directions = 74 clusters)
   int emb_max_batch = 256;      // chunks per embedding sub-batch
   int64_t launches = 0;
   SegWeights seg;
@@ -230,6 +231,7 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value) {
   else if (k == "emb_max_batch") ctx->emb_max_batch = (int)value;
   else if (k == "profile") ctx->profile = (int)value;
   else if (k == "seg_gemm_impl") ctx->seg_gemm_impl = (int)value;
+  else if (k == "seg_rec_impl") ctx->seg_rec_impl = (int)value;
   else B200_CHECK(false, B200_ERR_INVALID, "unknown option '%s'", key);
   B200_CHECK(ctx->seg_max_batch >= 1 && ctx->emb_max_batch >= 1 && ctx->conv_impl >= 0 && ctx->conv_impl <= 8,
              B200_ERR_INVALID, "option '%s' value %lld out of range", key, (long long)value);
@@ -345,6 +347,23 @@ int b200_seg_load(b200_ctx* ctx, const b200_seg_weights* w) {
     if ((rc = upload(ctx, wih, &S.w_ih[l]))) return rc;
     if ((rc = upload(ctx, bg, &S.b_g[l]))) return rc;
     if ((rc = upload(ctx, whh, &S.w_hh[l]))) return rc;
+    {   // tensor-core recurrence: rows (dir, rank, unit_local, gate), k contiguous, as fp16 (hi, lo)
+      std::vector<__half> hi((size_t)1024 * 128), lo((size_t)1024 * 128);
+      for (int d = 0; d < 2; ++d) {
+        const float* Wh = w->lstm_w_hh[l * 2 + d];
+        for (int r = 0; r < 2; ++r)
+          for (int ul = 0; ul < 64; ++ul)
+            for (int gt = 0; gt < 4; ++gt)
+              for (int k = 0; k < 128; ++k) {
+                const float v = Wh[(size_t)(gt * 128 + 64 * r + ul) * 128 + k];
+                const size_t o = ((size_t)((d * 2 + r) * 256 + ul * 4 + gt)) * 128 + k;
+                hi[o] = __float2half(v);
+                lo[o] = __float2half(v - __half2float(hi[o]));
+              }
+      }
+      if ((rc = upload(ctx, hi, &S.w_hh_hi[l]))) return rc;
+      if ((rc = upload(ctx, lo, &S.w_hh_lo[l]))) return rc;
+    }
   }
   const int lin_in[2] = {256, 128};
   for (int i = 0; i < 2; ++i) {
@@ -447,7 +466,7 @@ static int seg_run(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, co
     if (sinc_out) continue;
     if ((rc = lstm_head_forward(ctx->seg, x0, nb, region, classes + (size_t)c0 * kFrames,
                                 logp ? logp + (size_t)c0 * kFrames * kClasses : nullptr, ctx->num_sms,
-                                ctx->seg_gemm_impl, st)))
+                                ctx->seg_gemm_impl, ctx->seg_rec_impl, st)))
       return rc;
     ctx->launches += 2 * ctx->seg.lstm_layers + 3;
   }

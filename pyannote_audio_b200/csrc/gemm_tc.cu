@@ -29,6 +29,7 @@ struct GemmTcParams {
   __half* C_lo;
   int ldc, ldc_h;
   uint32_t a_bytes, b_bytes, stage_bytes, nstages, idesc;
+  int gx_T;            // > 0: "gx mode" (see gemm_tc_split_gx): M tiles are (t, 128 consecutive sequences)
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -72,8 +73,14 @@ gemm_tc_split_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_cons
         if (leader) {
           mbar_expect_tx(bar_full + 8 * stage, p.stage_bytes);
           const uint32_t sa = stage0 + stage * p.stage_bytes;
-          tma_load_2d(&tmAh, bar_full + 8 * stage, sa, kb * kGemmK, tm * kGemmM);
-          tma_load_2d(&tmAl, bar_full + 8 * stage, sa + p.a_bytes, kb * kGemmK, tm * kGemmM);
+          if (p.gx_T > 0) {   // rows = 128 consecutive sequences at one time step of a [b][t][k] array
+            const int t = tm % p.gx_T, b0 = (tm / p.gx_T) * kGemmM;
+            tma_load_3d(&tmAh, bar_full + 8 * stage, sa, kb * kGemmK, t, b0);
+            tma_load_3d(&tmAl, bar_full + 8 * stage, sa + p.a_bytes, kb * kGemmK, t, b0);
+          } else {
+            tma_load_2d(&tmAh, bar_full + 8 * stage, sa, kb * kGemmK, tm * kGemmM);
+            tma_load_2d(&tmAl, bar_full + 8 * stage, sa + p.a_bytes, kb * kGemmK, tm * kGemmM);
+          }
           tma_load_2d(&tmBh, bar_full + 8 * stage, sa + 2 * p.a_bytes, kb * kGemmK, tn * Nt);
           tma_load_2d(&tmBl, bar_full + 8 * stage, sa + 2 * p.a_bytes + p.b_bytes, kb * kGemmK, tn * Nt);
         }
@@ -123,6 +130,21 @@ gemm_tc_split_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_cons
       const int m = tm * kGemmM + q * 32 + lane;
       const bool valid = m < p.M;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)Nt;
+      if (p.gx_T > 0) {
+        // gx layout [b/32][t][col/4][b%32][4]: the 32 lanes (sequences) of a warp store 512 contiguous bytes
+        const int t = tm % p.gx_T, b32 = (tm / p.gx_T) * 4 + q;
+        float4* gp = reinterpret_cast<float4*>(p.C) + ((size_t)b32 * p.gx_T + t) * (size_t)(p.N / 4) * 32 + lane;
+        for (int n0 = 0; n0 < Nt; n0 += 32) {
+          uint32_t r[32];
+          tc_ld32(taddr + n0, r);
+          const int col = tn * Nt + n0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            gp[(size_t)((col >> 2) + j) * 32] =
+                make_float4(__uint_as_float(r[4 * j]) + s_bias[col + 4 * j], __uint_as_float(r[4 * j + 1]) + s_bias[col + 4 * j + 1],
+                            __uint_as_float(r[4 * j + 2]) + s_bias[col + 4 * j + 2], __uint_as_float(r[4 * j + 3]) + s_bias[col + 4 * j + 3]);
+        }
+      } else
       for (int n0 = 0; n0 < Nt; n0 += 32) {
         uint32_t r[32];
         tc_ld32(taddr + n0, r);
@@ -209,30 +231,35 @@ static int make_map_2d(CUtensorMap* tm, const __half* ptr, int rows, int K, int 
   return B200_OK;
 }
 
-int gemm_tc_split(const __half* A_hi, const __half* A_lo, int lda, const __half* B_hi, const __half* B_lo, int ldb,
-                  float* C, int ldc, __half* C_hi, __half* C_lo, int ldc_h, const float* bias, int M, int N, int K,
-                  int act, int num_sms, cudaStream_t stream) {
-  B200_CHECK(K % kGemmK == 0 && N % 128 == 0 && N <= 1024 && lda % 8 == 0 && ldb % 8 == 0, B200_ERR_INVALID,
-             "gemm_tc_split: unsupported shape M=%d N=%d K=%d", M, N, K);
-  GemmTcParams p{};
-  p.M = M; p.N = N; p.K = K; p.act = act; p.bias = bias; p.C = C; p.C_hi = C_hi; p.C_lo = C_lo; p.ldc = ldc;
-  p.ldc_h = ldc_h;
+static int make_map_3d(CUtensorMap* tm, const __half* ptr, int NB, int T, int K, int ld) {
+  PFN_encodeTiled enc = get_encode();
+  B200_CHECK(enc != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)T, (cuuint64_t)NB};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)T * ld * 2};
+  cuuint32_t box[3] = {(cuuint32_t)kGemmK, 1, (cuuint32_t)kGemmM};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(gemm gx) failed: %d", (int)r);
+  return B200_OK;
+}
+
+static int launch_gemm(GemmTcParams& p, const CUtensorMap& tmAh, const CUtensorMap& tmAl, const __half* B_hi,
+                       const __half* B_lo, int ldb, int num_sms, cudaStream_t stream) {
   p.Nt = 128;
-  p.kblocks = K / kGemmK;
-  p.tiles_m = ceil_div(M, kGemmM);
-  p.tiles_n = N / p.Nt;
+  p.kblocks = p.K / kGemmK;
+  p.tiles_n = p.N / p.Nt;
   p.num_tiles = p.tiles_m * p.tiles_n;
   p.a_bytes = kGemmM * kGemmK * 2;
   p.b_bytes = p.Nt * kGemmK * 2;
   p.stage_bytes = 2 * p.a_bytes + 2 * p.b_bytes;          // 64 KB
   p.nstages = 3;
   p.idesc = (1u << 4) | ((uint32_t)(p.Nt >> 3) << 17) | ((uint32_t)(kGemmM >> 4) << 24);
-  CUtensorMap tmAh, tmAl, tmBh, tmBl;
+  CUtensorMap tmBh, tmBl;
   int rc;
-  if ((rc = make_map_2d(&tmAh, A_hi, M, K, lda, kGemmM))) return rc;
-  if ((rc = make_map_2d(&tmAl, A_lo, M, K, lda, kGemmM))) return rc;
-  if ((rc = make_map_2d(&tmBh, B_hi, N, K, ldb, p.Nt))) return rc;
-  if ((rc = make_map_2d(&tmBl, B_lo, N, K, ldb, p.Nt))) return rc;
+  if ((rc = make_map_2d(&tmBh, B_hi, p.N, p.K, ldb, p.Nt))) return rc;
+  if ((rc = make_map_2d(&tmBl, B_lo, p.N, p.K, ldb, p.Nt))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -243,6 +270,39 @@ int gemm_tc_split(const __half* A_hi, const __half* A_lo, int lda, const __half*
   gemm_tc_split_kernel<<<grid, kGemmThreads, smem, stream>>>(tmAh, tmAl, tmBh, tmBl, p);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
+}
+
+int gemm_tc_split(const __half* A_hi, const __half* A_lo, int lda, const __half* B_hi, const __half* B_lo, int ldb,
+                  float* C, int ldc, __half* C_hi, __half* C_lo, int ldc_h, const float* bias, int M, int N, int K,
+                  int act, int num_sms, cudaStream_t stream) {
+  B200_CHECK(K % kGemmK == 0 && N % 128 == 0 && N <= 1024 && lda % 8 == 0 && ldb % 8 == 0, B200_ERR_INVALID,
+             "gemm_tc_split: unsupported shape M=%d N=%d K=%d", M, N, K);
+  GemmTcParams p{};
+  p.M = M; p.N = N; p.K = K; p.act = act; p.bias = bias; p.C = C; p.C_hi = C_hi; p.C_lo = C_lo; p.ldc = ldc;
+  p.ldc_h = ldc_h;
+  p.tiles_m = ceil_div(M, kGemmM);
+  CUtensorMap tmAh, tmAl;
+  int rc;
+  if ((rc = make_map_2d(&tmAh, A_hi, M, K, lda, kGemmM))) return rc;
+  if ((rc = make_map_2d(&tmAl, A_lo, M, K, lda, kGemmM))) return rc;
+  return launch_gemm(p, tmAh, tmAl, B_hi, B_lo, ldb, num_sms, stream);
+}
+
+// LSTM input projection for lstm_rec_tc_kernel: A is [NB][T][K] (hi, lo), the result G = A B^T + bias is written in
+// "gx layout" [ceil(NB/128)*4][T][N/4][32][4] fp32 (sequence-major inside 32-sequence groups, padded sequences hold
+// the bias), so that a warp of 32 sequences reads/writes 512 contiguous bytes per column group.
+int gemm_tc_split_gx(const __half* A_hi, const __half* A_lo, int lda, const __half* B_hi, const __half* B_lo, int ldb,
+                     float* G, const float* bias, int NB, int T, int N, int K, int num_sms, cudaStream_t stream) {
+  B200_CHECK(K % kGemmK == 0 && N % 128 == 0 && N <= 1024 && lda % 8 == 0 && ldb % 8 == 0, B200_ERR_INVALID,
+             "gemm_tc_split_gx: unsupported shape NB=%d N=%d K=%d", NB, N, K);
+  GemmTcParams p{};
+  p.M = NB * T; p.N = N; p.K = K; p.act = 0; p.bias = bias; p.C = G; p.gx_T = T;
+  p.tiles_m = ceil_div(NB, kGemmM) * T;
+  CUtensorMap tmAh, tmAl;
+  int rc;
+  if ((rc = make_map_3d(&tmAh, A_hi, NB, T, K, lda))) return rc;
+  if ((rc = make_map_3d(&tmAl, A_lo, NB, T, K, lda))) return rc;
+  return launch_gemm(p, tmAh, tmAl, B_hi, B_lo, ldb, num_sms, stream);
 }
 
 }  // namespace b200

@@ -17,7 +17,9 @@ struct SegWeights {
   float* w_ih[8] = {};
   float* b_g[8] = {};
   int k_in[8] = {};                 // padded input size (64, 256, ...)
-  float* w_hh[8] = {};              // [2 dir][2 rank][128 k][256]  (smem image of the recurrent kernel)
+  float* w_hh[8] = {};              // [2 dir][2 rank][128 k][256]  (smem image of the SIMT recurrent kernel)
+  __half* w_hh_hi[8] = {};          // [2 dir][2 rank][256 = (unit, gate)][128 k] fp16 (hi, lo) for lstm_rec_tc_kernel
+  __half* w_hh_lo[8] = {};
   // fp16 (hi, lo) splits of the GEMM weights for the tensor-core path (gemm_tc.cu)
   __half* w_ih_hi[8] = {};
   __half* w_ih_lo[8] = {};
@@ -37,6 +39,11 @@ int gemm_tc_split(const __half* A_hi, const __half* A_lo, int lda, const __half*
                   float* C, int ldc, __half* C_hi, __half* C_lo, int ldc_h, const float* bias, int M, int N, int K,
                   int act, int num_sms, cudaStream_t stream);
 int split_f16(const float* x, __half* hi, __half* lo, size_t n, cudaStream_t st);
+int gemm_tc_split_gx(const __half* A_hi, const __half* A_lo, int lda, const __half* B_hi, const __half* B_lo, int ldb,
+                     float* G, const float* bias, int NB, int T, int N, int K, int num_sms, cudaStream_t stream);
+// tensor-core recurrence (seg_lstm_tc.cu): G in gx layout -> layer output as fp16 (hi, lo) [NB][589][256]
+int lstm_rec_tc(const float* G, const __half* Whh_hi, const __half* Whh_lo, __half* Yh, __half* Yl, int NB,
+                cudaStream_t stream);
 
 // SincNet front-end on NB chunks: wav + per-chunk (offset, valid) -> X0 [NB][589][64] fp32 (60 features + 4 zero pad)
 size_t sincnet_workspace_bytes(int NB);
@@ -46,6 +53,6 @@ int sincnet_forward(const SegWeights& W, const float* wav, const long long* chun
 // BiLSTM stack + linear head: X0 -> class ids [NB][589] u8 (+ optional log-probs [NB][589][7])
 size_t lstm_workspace_bytes(int NB);
 int lstm_head_forward(const SegWeights& W, const float* x0, int NB, void* ws, unsigned char* cls, float* logp,
-                      int num_sms, int gemm_impl, cudaStream_t stream);
+                      int num_sms, int gemm_impl, int rec_impl, cudaStream_t stream);
 
 }  // namespace b200
