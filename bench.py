@@ -7,7 +7,7 @@ over a batch of synthetic 10-minute files (12 per GPU by default = BASELINE.json
 
   value : audio-hours/sec, waveforms already resident in HBM (CUDA events, max over ranks)
   e2e   : the same through SpeakerDiarization.apply_batch with HOST waveforms (H2D + D2H inside the timed region)
-  roofline     : conv_tc_kernel (ResNet34 trunk, ~98 % of the FLOPs) measured live with CUDA events
+  roofline     : ResNet34 trunk conv kernels (~98 % of the FLOPs) measured live with CUDA events
   cpu_baseline : the CPU oracle (reference-equivalent: 3 trunk passes per chunk) on a bounded sample, rank 0, N=1
 
 `--impl reference` times the CPU oracle arm (the reference package itself cannot be imported in this image:
@@ -228,9 +228,16 @@ def main():
     pk = peaks()
     peak = pk.get("bf16_tflops_sustained", 1400.0)
     achieved = trunk_segments * TRUNK_FLOP_PER_SEGMENT / (trunk_ms / 1e3) / 1e12 if trunk_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (ResNet34 trunk, 36 launches per sub-batch)",
+    # DRAM traffic of one 256-segment trunk pass (stem + 35 tcgen05 conv launches) from ncu
+    # (profiles/r01_trunk_traffic_256.csv: 29.66 GB read + 18.70 GB written; algorithmic minimum 50.9 GB counting every
+    # activation tensor once per read/write, i.e. no re-read waste; small layers hit L2)
+    traffic_256 = 48.354e9
+    roofline = {"bound": "tensor",
+                "kernel": "ResNet34 trunk = conv_tc4/conv_tc3/conv_tc kernels, 36 dependent launches per 256-segment sub-batch",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (fp16 = same tensor rate)"
+                "traffic": traffic_256, "traffic_unit": "bytes per 256-segment trunk pass (ncu dram read+write)",
+                "algorithmic_flop_per_launch_unit": 256 * TRUNK_FLOP_PER_SEGMENT,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (fp16 = same tensor rate)"
                 if pk else "fallback 1.4 PFLOP/s sustained",
                 "trunk_ms_per_step": trunk_ms / args.steps, "seg_ms_per_step": seg_ms / args.steps}
     cpu = None

@@ -38,17 +38,21 @@ __device__ __forceinline__ float fast_rcp(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+// Spin without acquire semantics (an acquiring try_wait invalidates L1 on every poll); `acquire` adds ONE cluster-scope
+// fence after the spin.  The MMA warp (no memory operations in flight) acquires the h tiles written by the peer; the
+// epilogue warps only need the control dependency of peer_done (their fence would also wait for the Gx prefetch).
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, bool acquire) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
       "}" ::"r"(bar), "r"(parity)
       : "memory");
+  if (acquire) asm volatile("fence.acq_rel.cluster;" ::: "memory");
 }
 __device__ __forceinline__ uint32_t map_to_peer(uint32_t saddr, uint32_t peer) {
   uint32_t r;
@@ -70,7 +74,11 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t raddr, uint4 v) {
                "r"(v.w)
                : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// generic-proxy shared-memory writes (own CTA and peer, through DSMEM) -> async-proxy reads by tcgen05.mma.  The
+// unqualified fence.proxy.async also drains global memory (MEMBAR.ALL + ERRBAR: 14 % of all stall samples in ncu).
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cluster;" ::: "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -138,7 +146,7 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_consta
     const uint32_t dhi = desc_hi(1024u, 2u);                // 128-byte rows, SWIZZLE_128B
     const uint32_t idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     for (int s = 0; s < T; ++s) {
-      if (s > 0) mbar_wait_cluster(bar_h, (uint32_t)(s - 1) & 1u);
+      if (s > 0) mbar_wait_cluster(bar_h, (uint32_t)(s - 1) & 1u, true);
       fence_proxy_async();
       tc_fence_after();
       if (leader) {
@@ -227,17 +235,18 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_consta
           hv[u] = (1.f - ec) * fast_rcp((1.f + eo) * (1.f + ec));               // sigmoid(o) * tanh(c)
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const __half h0 = __float2half_rn(hv[2 * e]), h1 = __float2half_rn(hv[2 * e + 1]);
-          ph2[e] = __halves2half2(h0, h1);
-          pl2[e] = __floats2half2_rn(hv[2 * e] - __half2float(h0), hv[2 * e + 1] - __half2float(h1));
+        for (int e = 0; e < 4; ++e) {                       // packed conversions only (scalar F2F runs on the MUFU pipe)
+          const __half2 hh = __floats2half2_rn(hv[2 * e], hv[2 * e + 1]);
+          const float2 hb = __half22float2(hh);
+          ph2[e] = hh;
+          pl2[e] = __floats2half2_rn(hv[2 * e] - hb.x, hv[2 * e + 1] - hb.y);
         }
         if (live) {
           const size_t o = (y_row + (size_t)t) * 256 + (size_t)(y_col + chunk * 8);
           *reinterpret_cast<uint4*>(p.Yh + o) = ph;
           *reinterpret_cast<uint4*>(p.Yl + o) = pl;
         }
-        if (chunk == 0) mbar_wait_cluster(bar_peer, (uint32_t)s & 1u);          // peer's MMAs of this step are done
+        if (chunk == 0) mbar_wait_cluster(bar_peer, (uint32_t)s & 1u, false);          // peer's MMAs of this step are done
         const uint32_t coff = (uint32_t)(((half * 4 + chunk) ^ (m & 7)) << 4);  // 16-byte chunk inside the swizzled row
         st_shared_v4(a_hi_row + coff, ph);
         st_shared_v4(a_lo_row + coff, pl);
