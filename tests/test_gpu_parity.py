@@ -106,6 +106,13 @@ def test_segmentation_parity(ctx, dev, oracle_models):
     np.testing.assert_allclose(logp0.cpu().numpy(), ref_logp, atol=2e-4, rtol=0)
     assert float((logp0 - logp).abs().max()) < 1e-4
     assert float((cls0 != cls).float().mean()) < 1e-3
+    # tensor-core LSTM recurrence (default) against the fp32 CUDA-core cluster kernel
+    ctx.set_option("seg_rec_impl", 0)
+    cls1, logp1 = ctx.seg_forward(buf, off, valid, return_logp=True)
+    ctx.set_option("seg_rec_impl", 1)
+    np.testing.assert_allclose(logp1.cpu().numpy(), ref_logp, atol=2e-4, rtol=0)
+    assert float((logp1 - logp).abs().max()) < 1e-4
+    assert float((cls1 != cls).float().mean()) < 1e-3
 
 
 def test_segmentation_edge_cases(ctx, dev, oracle_models):
@@ -137,14 +144,14 @@ def test_embedding_parity(ctx, dev, oracle_models):
     np.testing.assert_allclose(fb.cpu().numpy(), ref_fb.numpy(), atol=5e-3, rtol=0)
     # trunk: tensor-core path and CUDA-core path against the fp32 oracle, and against each other
     out = {}
-    for impl in (0, 1, 2):
+    for impl in (0, 1, 6, 8):                             # CUDA cores, per-tap, strip streaming, default mix (tc3 + tc4)
         ctx.set_option("conv_impl", impl)
         out[impl] = ctx.emb_trunk(ref_fb.to(dev)).cpu().numpy()
         rel = np.abs(out[impl] - ref_frames.numpy()).max() / np.abs(ref_frames.numpy()).max()
         assert rel < 2e-2, f"impl {impl}: trunk relative error {rel}"
-    ctx.set_option("conv_impl", 1)
-    assert np.abs(out[1] - out[0]).max() <= 2e-2 * np.abs(out[0]).max()
-    assert np.abs(out[1] - out[2]).max() <= 2e-2 * np.abs(out[0]).max()
+    ctx.set_option("conv_impl", 8)
+    for impl in (1, 6, 8):
+        assert np.abs(out[impl] - out[0]).max() <= 2e-2 * np.abs(out[0]).max()
     rng = np.random.default_rng(0)
     masks = (rng.uniform(size=(n, 3, 589)) < 0.5).astype(np.uint8)
     masks[0, 2] = 0                                        # all-zero weights (test_stats_pool.py:111-131 case)
