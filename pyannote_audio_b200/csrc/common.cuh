@@ -61,6 +61,23 @@ constexpr int kEmbT = 125;           // ResNet time frames after 3 stride-2 stag
 constexpr int kEmbDim = 256;
 constexpr int kStatsDim = 2560;      // 256 channels x 10 freq bins
 
+// Packed fp32x2 FMA (Blackwell FFMA2): two independent IEEE fma.rn per instruction.  The FP32 kernels here are
+// limited by instruction issue / operand dispatch (ncu: FMA pipe 50 %, issue 60 %), not by the FMA lanes.
+typedef unsigned long long f32x2_t;
+#ifdef __CUDACC__
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(f32x2_t& d, f32x2_t a, f32x2_t b) {   // d = a * b + d (lane-wise)
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+#endif
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

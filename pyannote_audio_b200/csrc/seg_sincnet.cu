@@ -85,47 +85,58 @@ __global__ void __launch_bounds__(128) sinc_pool_kernel(const float* __restrict_
     reinterpret_cast<float4*>(fs)[i] = reinterpret_cast<const float4*>(filt)[i];
   __syncthreads();
 
+  // accumulators as packed channel pairs (c, c+1): one FFMA2 per pair
+  f32x2_t ac2[3][10], as2[3][10];
+#pragma unroll
+  for (int p = 0; p < 3; ++p)
+#pragma unroll
+    for (int c = 0; c < 10; ++c) { ac2[p][c] = 0ull; as2[p][c] = 0ull; }
+  const float* xb = xs + j * 30;
+  for (int k = 0; k < 125; ++k) {
+    f32x2_t sv[3], dv[3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      const float a = xb[p * 10 + k], m = xb[p * 10 + 250 - k];
+      sv[p] = pack2(a + m, a + m);
+      dv[p] = pack2(a - m, a - m);
+    }
+    const ulonglong2* fc = reinterpret_cast<const ulonglong2*>(fs + k * 80 + half * 20);
+    const ulonglong2* fn = reinterpret_cast<const ulonglong2*>(fs + k * 80 + 40 + half * 20);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const ulonglong2 wc = fc[q], wn = fn[q];
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        ffma2(ac2[p][2 * q], sv[p], wc.x);
+        ffma2(ac2[p][2 * q + 1], sv[p], wc.y);
+        ffma2(as2[p][2 * q], dv[p], wn.x);
+        ffma2(as2[p][2 * q + 1], dv[p], wn.y);
+      }
+    }
+  }
+  {  // centre tap (cos bank only; the sin bank's centre is exactly 0)
+    const ulonglong2* fc = reinterpret_cast<const ulonglong2*>(fs + 125 * 80 + half * 20);
+    f32x2_t xc[3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) xc[p] = pack2(xb[p * 10 + 125], xb[p * 10 + 125]);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const ulonglong2 wc = fc[q];
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        ffma2(ac2[p][2 * q], xc[p], wc.x);
+        ffma2(ac2[p][2 * q + 1], xc[p], wc.y);
+      }
+    }
+  }
   float ac[3][20], as[3][20];
 #pragma unroll
   for (int p = 0; p < 3; ++p)
 #pragma unroll
-    for (int c = 0; c < 20; ++c) { ac[p][c] = 0.f; as[p][c] = 0.f; }
-  const float* xb = xs + j * 30;
-  for (int k = 0; k < 125; ++k) {
-    float sv[3], dv[3];
-#pragma unroll
-    for (int p = 0; p < 3; ++p) {
-      const float a = xb[p * 10 + k], m = xb[p * 10 + 250 - k];
-      sv[p] = a + m;
-      dv[p] = a - m;
+    for (int c = 0; c < 10; ++c) {
+      unpack2(ac2[p][c], ac[p][2 * c], ac[p][2 * c + 1]);
+      unpack2(as2[p][c], as[p][2 * c], as[p][2 * c + 1]);
     }
-    const float4* fc = reinterpret_cast<const float4*>(fs + k * 80 + half * 20);
-    const float4* fn = reinterpret_cast<const float4*>(fs + k * 80 + 40 + half * 20);
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-      const float4 wc = fc[q], wn = fn[q];
-      const float wcv[4] = {wc.x, wc.y, wc.z, wc.w}, wnv[4] = {wn.x, wn.y, wn.z, wn.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-#pragma unroll
-        for (int p = 0; p < 3; ++p) {
-          ac[p][q * 4 + e] = fmaf(sv[p], wcv[e], ac[p][q * 4 + e]);
-          as[p][q * 4 + e] = fmaf(dv[p], wnv[e], as[p][q * 4 + e]);
-        }
-    }
-  }
-  {  // centre tap (cos bank only; the sin bank's centre is exactly 0)
-    const float4* fc = reinterpret_cast<const float4*>(fs + 125 * 80 + half * 20);
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-      const float4 wc = fc[q];
-      const float wcv[4] = {wc.x, wc.y, wc.z, wc.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-#pragma unroll
-        for (int p = 0; p < 3; ++p) ac[p][q * 4 + e] = fmaf(xb[p * 10 + 125], wcv[e], ac[p][q * 4 + e]);
-    }
-  }
   __syncthreads();                   // everyone done with fs -> reuse as pooled tile [80][65]
   float* pt = fs;
   const int pglob = tile * kTileP + j;
@@ -204,11 +215,11 @@ __global__ void __launch_bounds__(192) conv5_pool_kernel(const float* __restrict
     }
     xin[i] = v;
   }
-  float acc[3][20];
+  f32x2_t acc2[3][10];                 // packed channel pairs (c, c+1): one FFMA2 per pair
 #pragma unroll
   for (int p = 0; p < 3; ++p)
 #pragma unroll
-    for (int c = 0; c < 20; ++c) acc[p][c] = 0.f;
+    for (int c = 0; c < 10; ++c) acc2[p][c] = 0ull;
   for (int c0 = 0; c0 < CIN; c0 += CCH) {
     __syncthreads();
     for (int i = tid; i < CCH * 5 * 60 / 4; i += 192)
@@ -217,24 +228,29 @@ __global__ void __launch_bounds__(192) conv5_pool_kernel(const float* __restrict
 #pragma unroll 2
     for (int cc = 0; cc < CCH; ++cc) {
       const float* xr = xin + (c0 + cc) * TW + j * 3;
-      float xv[7];
+      f32x2_t xv[7];
 #pragma unroll
-      for (int i = 0; i < 7; ++i) xv[i] = xr[i];
+      for (int i = 0; i < 7; ++i) xv[i] = pack2(xr[i], xr[i]);
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const float4* wp = reinterpret_cast<const float4*>(ws + (cc * 5 + k) * 60 + grp * 20);
+        const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(ws + (cc * 5 + k) * 60 + grp * 20);
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
-          const float4 w4 = wp[q];
-          const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+          const ulonglong2 w4 = wp[q];
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-#pragma unroll
-            for (int p = 0; p < 3; ++p) acc[p][q * 4 + e] = fmaf(xv[p + k], wv[e], acc[p][q * 4 + e]);
+          for (int p = 0; p < 3; ++p) {
+            ffma2(acc2[p][2 * q], xv[p + k], w4.x);
+            ffma2(acc2[p][2 * q + 1], xv[p + k], w4.y);
+          }
         }
       }
     }
   }
+  float acc[3][20];
+#pragma unroll
+  for (int p = 0; p < 3; ++p)
+#pragma unroll
+    for (int c = 0; c < 10; ++c) unpack2(acc2[p][c], acc[p][2 * c], acc[p][2 * c + 1]);
   __syncthreads();
   float* pt = ws;                      // pooled tile [60][65] = 3900 floats <= 6000
   const int pglob = tile * kTileP + j;
