@@ -131,6 +131,31 @@ class BaseClustering:
         return hard, soft
 
 
+class _Tick:
+    """B200_TIMING=2: synchronising wall-clock split of cluster_batch (diagnostics only)."""
+
+    def __init__(self, dev):
+        import os, time
+        self.on = os.environ.get("B200_TIMING") == "2"
+        self.dev, self.t, self.acc, self._time = dev, None, {}, time
+        if self.on:
+            torch.cuda.synchronize(dev)
+            self.t = time.perf_counter()
+
+    def __call__(self, name):
+        if not self.on:
+            return
+        torch.cuda.synchronize(self.dev)
+        now = self._time.perf_counter()
+        self.acc[name] = self.acc.get(name, 0.0) + (now - self.t) * 1e3
+        self.t = now
+
+    def report(self):
+        if self.on:
+            import sys
+            print("[b200 clustering] " + ", ".join(f"{k}={v:.1f}ms" for k, v in self.acc.items()), file=sys.stderr)
+
+
 class VBxClustering(BaseClustering):
     expects_num_clusters: bool = False
 
@@ -156,6 +181,7 @@ class VBxClustering(BaseClustering):
         """
         ctx = self._ctx(emb_all)
         dev = ctx.device
+        tick = _Tick(dev)
         min_clusters = min_clusters if min_clusters is not None else 1
         max_clusters = max_clusters if max_clusters is not None else np.inf
         F = len(bounds) - 1
@@ -173,6 +199,7 @@ class VBxClustering(BaseClustering):
         train_all = emb_all.reshape(-1, dim)[flat_idx].double()
         emb64_all = emb_all.double()
         active_all = active_all.bool()
+        tick("filter")
         results = [None] * F
         todo = []
         for f in range(F):
@@ -198,6 +225,7 @@ class VBxClustering(BaseClustering):
             x_link = torch.cat([train_all[row_off[f]: row_off[f + 1]] for f in todo])
             link_off = sub_off
         Z_all = ctx.linkage_centroid_batched(x_link, link_off, normalize=True).cpu().numpy()   # sync
+        tick("linkage")
         ahcs, S_f, zpos = {}, {}, 0
         for f in todo:
             n = int(n_f[f])
@@ -207,6 +235,7 @@ class VBxClustering(BaseClustering):
             _, ahc = np.unique(ahc, return_inverse=True)
             ahcs[f], S_f[f] = ahc, int(ahc.max()) + 1
             results[f] = dict(dendrogram=Z, ahc=ahc)
+        tick("fcluster(host)")
         # ---- VBx: PLDA transform of all rows, initial responsibilities built on the host, one launch ----------
         fea = self.plda.transform(x_link)
         hot_blocks = []
@@ -218,11 +247,13 @@ class VBxClustering(BaseClustering):
             g[np.arange(n), ahcs[f]] = 1.0 / tot
             hot_blocks.append(g.reshape(-1))
         gamma0 = torch.from_numpy(np.concatenate(hot_blocks)).to(dev)
+        tick("plda+gamma0")
         phi = self.plda._consts(dev)["phi"]
         n_list = [int(n_f[f]) for f in todo]
         S_list = [S_f[f] for f in todo]
         gamma, pi, _ = ctx.vbx_batched(fea, phi, gamma0, n_list, S_list, self.Fa, self.Fb, max_iters=20)
         pi_host = pi.cpu().numpy()                                                                 # sync
+        tick("vbx")
         gpos = spos = rpos = 0
         for f, n, S in zip(todo, n_list, S_list):
             c0, c1 = int(bounds[f]), int(bounds[f + 1])
@@ -251,6 +282,8 @@ class VBxClustering(BaseClustering):
             hard, soft = self._assign(ctx, emb64_all[c0:c1], centroids.contiguous(), active_all[c0:c1], constrained)
             results[f].update(hard=hard, soft=soft, centroids=centroids, active=active_all[c0:c1], q=q, sp=sp,
                               train=train, fea=fea[rpos - n: rpos], trivial=False)
+        tick("centroids+assign")
+        tick.report()
         return results
 
     def __call__(self, embeddings, segmentations=None, num_clusters=None, min_clusters=None, max_clusters=None,

@@ -244,16 +244,25 @@ __device__ __forceinline__ double block_sum_1024(double v, double* red) {
   return red[32];
 }
 
-__global__ void __launch_bounds__(1024) vbx_kernel(const VbxJob* __restrict__ jobs, const double* __restrict__ fea_all,
-                                                   const double* __restrict__ phi, int D, double Fa, double Fb,
-                                                   int max_iters, double epsilon, double* __restrict__ gamma_all,
-                                                   double* __restrict__ pi_all, double* __restrict__ rho_all,
-                                                   double* __restrict__ G_all, double* __restrict__ lpx_all,
-                                                   double* __restrict__ alpha_all, double* __restrict__ invL_all,
-                                                   double* __restrict__ cst_all, int* __restrict__ iters_all) {
-  const VbxJob job = jobs[blockIdx.x];
+constexpr int kVbxCtas = 8;        // thread-block cluster per problem; phases separated by cluster barriers
+
+__device__ __forceinline__ void vbx_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(kVbxCtas, 1, 1) __launch_bounds__(1024)
+vbx_kernel(const VbxJob* __restrict__ jobs, const double* __restrict__ fea_all, const double* __restrict__ phi, int D,
+           double Fa, double Fb, int max_iters, double epsilon, double* __restrict__ gamma_all,
+           double* __restrict__ pi_all, double* __restrict__ rho_all, double* __restrict__ G_all,
+           double* __restrict__ lpx_all, double* __restrict__ alpha_all, double* __restrict__ invL_all,
+           double* __restrict__ cst_all, double* __restrict__ praw_all, double* __restrict__ part_all,
+           int* __restrict__ iters_all) {
+  const int prob = blockIdx.x / kVbxCtas;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const VbxJob job = jobs[prob];
   const int n = job.n, S = job.S;
-  if (n <= 0 || S <= 0) return;
+  if (n <= 0 || S <= 0) return;                            // uniform over the cluster
   const double* X = fea_all + (size_t)job.fea_off * D;
   double* rho = rho_all + (size_t)job.fea_off * D;
   double* G = G_all + job.fea_off;
@@ -261,14 +270,18 @@ __global__ void __launch_bounds__(1024) vbx_kernel(const VbxJob* __restrict__ jo
   double* gamma = gamma_all + job.gam_off;
   double* pi = pi_all + job.pi_off;
   double* cst = cst_all + job.pi_off;
+  double* praw = praw_all + job.pi_off;
+  double* part = part_all + (size_t)prob * 2 * kVbxCtas;
   double* alpha = alpha_all + (size_t)job.mod_off * D;
   double* invL = invL_all + (size_t)job.mod_off * D;
   __shared__ double red[33];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gtid = (int)rank * 1024 + tid, gthreads = kVbxCtas * 1024;
+  const int gwarp = (int)rank * 32 + warp, gwarps = kVbxCtas * 32;
   const double FaFb = Fa / Fb;
 
   // rho = X * sqrt(phi);  G = -0.5 * (|x|^2 + D log(2 pi))    (one warp per frame)
-  for (int i = warp; i < n; i += 32) {
+  for (int i = gwarp; i < n; i += gwarps) {
     double s = 0.0;
     for (int d = lane; d < D; d += 32) {
       const double x = X[(size_t)i * D + d];
@@ -278,16 +291,17 @@ __global__ void __launch_bounds__(1024) vbx_kernel(const VbxJob* __restrict__ jo
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) G[i] = -0.5 * (s + D * log(2.0 * M_PI));
   }
-  for (int s = tid; s < S; s += 1024) pi[s] = 1.0 / S;
-  __syncthreads();
+  for (int s = gtid; s < S; s += gthreads) pi[s] = 1.0 / S;
+  vbx_cluster_sync();
 
   double prev = 0.0;
   int it = 0;
   for (; it < max_iters; ++it) {
-    // speaker models: one (s, d) pair per thread
-    for (int e = tid; e < S * D; e += 1024) {
+    // speaker models: one (s, d) pair per thread, frames summed in order
+    for (int e = gtid; e < S * D; e += gthreads) {
       const int s = e / D, d = e - s * D;
       double ng = 0.0, acc = 0.0;
+#pragma unroll 4
       for (int i = 0; i < n; ++i) {
         const double g = gamma[(size_t)i * S + s];
         ng += g;
@@ -297,8 +311,8 @@ __global__ void __launch_bounds__(1024) vbx_kernel(const VbxJob* __restrict__ jo
       invL[e] = il;
       alpha[e] = FaFb * il * acc;
     }
-    __syncthreads();
-    for (int s = warp; s < S; s += 32) {
+    vbx_cluster_sync();
+    for (int s = gwarp; s < S; s += gwarps) {
       double c = 0.0;
       for (int d = lane; d < D; d += 32) {
         const double al = alpha[s * D + d];
@@ -307,9 +321,9 @@ __global__ void __launch_bounds__(1024) vbx_kernel(const VbxJob* __restrict__ jo
       for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
       if (lane == 0) cst[s] = -0.5 * c;
     }
-    __syncthreads();
+    vbx_cluster_sync();
     // responsibilities: one warp per frame
-    for (int i = warp; i < n; i += 32) {
+    for (int i = gwarp; i < n; i += gwarps) {
       double mx = -DBL_MAX;
       for (int s = 0; s < S; ++s) {
         double dot = 0.0;
@@ -327,31 +341,33 @@ __global__ void __launch_bounds__(1024) vbx_kernel(const VbxJob* __restrict__ jo
       for (int s = lane; s < S; s += 32) gamma[(size_t)i * S + s] = exp(gamma[(size_t)i * S + s] - lse);
       if (lane == 0) lpx[i] = lse;
     }
-    __syncthreads();
-    // priors
-    double tot = 0.0;
-    for (int s = 0; s < S; ++s) {
+    vbx_cluster_sync();
+    // priors (one warp per speaker) and the two ELBO sums (per-CTA partials, combined in rank order)
+    for (int s = gwarp; s < S; s += gwarps) {
       double c = 0.0;
-      for (int i = tid; i < n; i += 1024) c += gamma[(size_t)i * S + s];
-      c = block_sum_1024(c, red);
-      if (tid == 0) pi[s] = c;
-      tot += c;
+      for (int i = lane; i < n; i += 32) c += gamma[(size_t)i * S + s];
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (lane == 0) praw[s] = c;
     }
-    __syncthreads();
-    for (int s = tid; s < S; s += 1024) pi[s] = pi[s] / tot;
-    // ELBO (vbx.py:130)
     double l = 0.0;
-    for (int i = tid; i < n; i += 1024) l += lpx[i];
+    for (int i = gtid; i < n; i += gthreads) l += lpx[i];
     l = block_sum_1024(l, red);
     double r = 0.0;
-    for (int e = tid; e < S * D; e += 1024) r += log(invL[e]) - invL[e] - alpha[e] * alpha[e] + 1.0;
+    for (int e = gtid; e < S * D; e += gthreads) r += log(invL[e]) - invL[e] - alpha[e] * alpha[e] + 1.0;
     r = block_sum_1024(r, red);
-    const double E = l + Fb * 0.5 * r;
-    __syncthreads();
+    if (tid == 0) { part[2 * rank] = l; part[2 * rank + 1] = r; }
+    vbx_cluster_sync();
+    double tot = 0.0;
+    for (int s = 0; s < S; ++s) tot += praw[s];
+    for (int s = gtid; s < S; s += gthreads) pi[s] = praw[s] / tot;
+    l = 0.0; r = 0.0;
+    for (int k = 0; k < kVbxCtas; ++k) { l += part[2 * k]; r += part[2 * k + 1]; }
+    const double E = l + Fb * 0.5 * r;                     // ELBO (vbx.py:130); identical in every thread
+    vbx_cluster_sync();                                    // pi visible, part/praw reusable
     if (it > 0 && E - prev < epsilon) { ++it; break; }
     prev = E;
   }
-  if (tid == 0) iters_all[blockIdx.x] = it;
+  if (tid == 0 && rank == 0) iters_all[prob] = it;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -466,7 +482,8 @@ int cdist_cosine(const double* a, int m, const double* b, int k, int dim, double
 size_t vbx_workspace_bytes_batched(const int* n, const int* S, int nfiles, int D) {
   size_t ntot = 0, stot = 0;
   for (int f = 0; f < nfiles; ++f) { ntot += n[f]; stot += S[f]; }
-  return (ntot * D + 2 * ntot + 2 * stot * D + stot + 64) * 8 + (size_t)nfiles * (sizeof(VbxJob) + 4) + 8192;
+  return (ntot * D + 2 * ntot + 2 * stot * D + 2 * stot + 64 + (size_t)nfiles * 2 * kVbxCtas) * 8 +
+         (size_t)nfiles * (sizeof(VbxJob) + 4) + 8192;
 }
 
 // fea [sum n][D], gamma concatenated per problem ([n_f][S_f] row-major), pi concatenated ([S_f])
@@ -487,11 +504,13 @@ int vbx_run_batched(const double* fea, const double* phi, const int* n, const in
   double* alpha = p; p += stot * D;
   double* invL = p; p += stot * D;
   double* cst = p; p += stot + 8;
+  double* praw = p; p += stot + 8;
+  double* part = p; p += (size_t)nfiles * 2 * kVbxCtas;
   VbxJob* djobs = (VbxJob*)p;
   int* iters = (int*)(djobs + nfiles);
   B200_CUDA_OK(cudaMemcpyAsync(djobs, jobs.data(), sizeof(VbxJob) * nfiles, cudaMemcpyHostToDevice, st));
-  vbx_kernel<<<nfiles, 1024, 0, st>>>(djobs, fea, phi, D, Fa, Fb, max_iters, epsilon, gamma, pi, rho, G, lpx, alpha,
-                                      invL, cst, iters);
+  vbx_kernel<<<nfiles * kVbxCtas, 1024, 0, st>>>(djobs, fea, phi, D, Fa, Fb, max_iters, epsilon, gamma, pi, rho, G, lpx,
+                                                 alpha, invL, cst, praw, part, iters);
   B200_CUDA_OK(cudaGetLastError());
   if (iters_host) {
     B200_CUDA_OK(cudaMemcpyAsync(iters_host, iters, sizeof(int) * nfiles, cudaMemcpyDeviceToHost, st));
