@@ -681,6 +681,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 struct ConvV4Params {
   int B, H, W, C, tiles_w, R, nhseg, num_items, relu, n_aslots;
   int nb_shift;                      // ring of NB = 512 / C accumulator blocks
+  int res_pf;                        // residual L2 prefetch distance in rows (0 = off)
   const float* bias;
   const __half* residual;
   __half* out;
@@ -838,6 +839,13 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const size_t pix = (((size_t)b * p.H + (h0 + r)) * p.W + (valid ? w : 0)) * (size_t)C;
         uint4 rpre[8];
         if (p.residual) {
+          // the residual streams from HBM: pull the rows this group will need next into L2 (one 64/128-byte pixel per
+          // thread), so that the register prefetch below only pays L2 latency
+          if (p.res_pf && valid && r + p.res_pf < R) {
+            const __half* nxt = p.residual + pix + (size_t)p.res_pf * p.W * C;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+            if (C == 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 32));
+          }
           const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix);
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4)
@@ -1048,6 +1056,7 @@ static int conv4_forward(const ConvLayer& L, const __half* in, const __half* res
   ConvV4Params p{};
   p.B = B; p.H = H; p.W = W; p.C = C; p.relu = relu; p.bias = L.bias; p.residual = residual; p.out = out;
   p.nb_shift = (C == 32) ? 4 : 3;
+  { const char* e = getenv("B200_RES_PF"); p.res_pf = e ? atoi(e) : 4; }
   p.swizzle = (C == 64) ? 128 : 64;
   p.tiles_w = ceil_div(W, kTileM);
   const int strips = B * p.tiles_w;
