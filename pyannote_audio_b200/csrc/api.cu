@@ -16,6 +16,7 @@ struct b200_ctx {
   int num_sms = 148;
   int seg_gemm_impl = 1;   // 1 = split-fp16 tcgen05 GEMMs for the LSTM input projections / linear layers, 0 = fp32 SIMT
   int seg_rec_impl = 1;    // 1 = LSTM recurrence on the tensor cores (needs seg_gemm_impl = 1), 0 = fp32 SIMT cluster kernel
+  int conv_fuse = 1;       // 1 = layer1 BasicBlocks as one fused kernel (conv_block32_kernel) when conv_impl == 8
   int conv_impl = 8;   // channels-as-M conv for C_out >= 128, strip-streaming conv for the narrow stride-1 3x3, per-tap conv otherwise
   int seg_max_batch = 4736;     // chunks per segmentation sub-batch (37 LSTM tiles of 128 sequences x 2 directions = 74 clusters)
   int emb_max_batch = 256;      // chunks per embedding sub-batch
@@ -232,6 +233,7 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value) {
   else if (k == "profile") ctx->profile = (int)value;
   else if (k == "seg_gemm_impl") ctx->seg_gemm_impl = (int)value;
   else if (k == "seg_rec_impl") ctx->seg_rec_impl = (int)value;
+  else if (k == "conv_fuse") ctx->conv_fuse = (int)value;
   else B200_CHECK(false, B200_ERR_INVALID, "unknown option '%s'", key);
   B200_CHECK(ctx->seg_max_batch >= 1 && ctx->emb_max_batch >= 1 && ctx->conv_impl >= 0 && ctx->conv_impl <= 8,
              B200_ERR_INVALID, "option '%s' value %lld out of range", key, (long long)value);
@@ -558,23 +560,33 @@ static int block_run(b200_ctx* ctx, const BlockWeights& B, __half* A, __half* Bf
   return B200_OK;
 }
 
-// conv1 + 16 BasicBlocks; result (NHWC fp16 [nb][10][125][256]) is left in ws.A
-static int trunk_run(b200_ctx* ctx, const EmbWs& w, int nb, cudaStream_t st) {
+// conv1 + 16 BasicBlocks; returns the buffer holding the result (NHWC fp16 [nb][10][125][256])
+static int trunk_run(b200_ctx* ctx, const EmbWs& w, int nb, cudaStream_t st, const __half** result) {
   const EmbWeights& E = ctx->emb;
   int rc;
   int H = kMel, Wd = kFbankFrames;
   // (running stem + layer1 in L2-sized groups of segments was measured 12-35 % slower than whole sub-batches:
   //  small grids lose more to tails and launch gaps than the L2 hits return)
-  if ((rc = conv1_forward(w.fbank, w.fmean, E.conv1_w, E.conv1_b, w.A, nb, st))) return rc;
+  __half* cur = w.A;            // current activation; the other two buffers are scratch
+  __half* s1 = w.Bf;
+  __half* s2 = w.Cf;
+  if ((rc = conv1_forward(w.fbank, w.fmean, E.conv1_w, E.conv1_b, cur, nb, st))) return rc;
   ctx->launches += 1;
-  const size_t first = 0;
-  for (size_t b = first; b < E.blocks.size(); ++b) {
-    const BlockWeights& B = E.blocks[b];
-    if ((rc = block_run(ctx, B, w.A, w.Bf, w.Cf, nb, H, Wd, st))) return rc;
+  for (const BlockWeights& B : E.blocks) {
     const int s = B.conv1.stride;
+    if (ctx->conv_impl == 8 && ctx->conv_fuse && !B.has_shortcut && s == 1 && B.conv1.C_in == 32 && B.conv1.w4 &&
+        B.conv2.w4) {
+      // layer1: the whole block in one kernel, intermediate activation kept in shared memory
+      if ((rc = conv_block32_forward(B.conv1, B.conv2, cur, s1, nb, H, Wd, ctx->num_sms, st))) return rc;
+      ctx->launches += 1;
+      __half* t = cur; cur = s1; s1 = t;
+      continue;
+    }
+    if ((rc = block_run(ctx, B, cur, s1, s2, nb, H, Wd, st))) return rc;
     H = (H + 2 - 3) / s + 1; Wd = (Wd + 2 - 3) / s + 1;
   }
   B200_CHECK(H == 10 && Wd == kEmbT, B200_ERR_STATE, "unexpected trunk output %dx%d", H, Wd);
+  *result = cur;
   return B200_OK;
 }
 
@@ -597,17 +609,18 @@ int b200_emb_forward(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, 
   carve_emb(nbmax, ctx->ws, &w);
   __half* st_hi = reinterpret_cast<__half*>(reinterpret_cast<char*>(ctx->ws) + sub_bytes);
   __half* st_lo = reinterpret_cast<__half*>(reinterpret_cast<char*>(ctx->ws) + sub_bytes + split_bytes);
+  const __half* feat = nullptr;
   for (int c0 = 0; c0 < num_chunks; c0 += nbmax) {
     const int nb = (num_chunks - c0) < nbmax ? (num_chunks - c0) : nbmax;
     if ((rc = fbank_forward(ctx->emb, wav, ctx->d_off + c0, ctx->d_valid + c0, nb, w.fbank, w.fmean, st))) return rc;
     ctx->launches += 2;
     {
       ScopedTimer timer(ctx, &ctx->trunk_events, st);
-      if ((rc = trunk_run(ctx, w, nb, st))) return rc;
+      if ((rc = trunk_run(ctx, w, nb, st, &feat))) return rc;
     }
     if (ctx->profile) ctx->trunk_segments += nb;
     const size_t o = (size_t)c0 * kSpeakers * 2 * kStatsDim;
-    if ((rc = stats_pool_forward(w.A, masks + (size_t)c0 * kSpeakers * kFrames, nullptr, st_hi + o, st_lo + o, nb, st)))
+    if ((rc = stats_pool_forward(feat, masks + (size_t)c0 * kSpeakers * kFrames, nullptr, st_hi + o, st_lo + o, nb, st)))
       return rc;
     ctx->launches += 1;
   }
@@ -649,8 +662,9 @@ int b200_emb_trunk(b200_ctx* ctx, const float* fbank, int32_t num_chunks, float*
     B200_CUDA_OK(cudaMemcpyAsync(w.fbank, fbank + (size_t)c0 * kFbankFrames * kMel,
                                  (size_t)nb * kFbankFrames * kMel * sizeof(float), cudaMemcpyDeviceToDevice, st));
     B200_CUDA_OK(cudaMemsetAsync(w.fmean, 0, (size_t)nb * kMel * sizeof(float), st));
-    if ((rc = trunk_run(ctx, w, nb, st))) return rc;
-    if ((rc = frames_to_nchw(w.A, frames + (size_t)c0 * 256 * 10 * kEmbT, nb, st))) return rc;
+    const __half* feat = nullptr;
+    if ((rc = trunk_run(ctx, w, nb, st, &feat))) return rc;
+    if ((rc = frames_to_nchw(feat, frames + (size_t)c0 * 256 * 10 * kEmbT, nb, st))) return rc;
     ctx->launches += 1;
   }
   return B200_OK;

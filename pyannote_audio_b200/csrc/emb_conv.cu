@@ -909,6 +909,312 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------
+// conv_block32_kernel: a whole BasicBlock of layer1 (32 -> 32 -> 32 channels, stride 1, identity shortcut) in one pass
+//
+//     out = relu(conv2(relu(conv1(x) + b1)) + b2 + x)                    (resnet.py BasicBlock.forward, BN folded)
+//
+// conv_tc4_kernel pairs are HBM-limited on layer1 (a 256-segment sub-batch moves 5 x 1.3 GB per block).  Here the
+// intermediate activation never leaves the SM: conv1 accumulates rows in TMEM ring 1 (vertical fold as in
+// conv_tc4_kernel), epilogue warps 2-5 turn a finished row into fp16 and write it -- zero padded outside the image --
+// straight into a shared-memory slot in the swizzled K-major layout TMA would have produced, and conv2 consumes those
+// slots as its A operand into TMEM ring 2; epilogue warps 6-9 add bias + residual (re-read from L2) and store.
+// A tile yields 126 output columns: conv1 evaluates 128 (one halo column each side), the input slot holds 130.
+// ------------------------------------------------------------------------------------------------
+struct ConvBlkParams {
+  int B, H, W, tiles_w, R, nhseg, num_items, n_islots, n_mslots, lag;
+  const float* bias1;
+  const float* bias2;
+  const __half* in;
+  __half* out;
+  uint32_t slot_bytes, w1_off, w2_off, i_off, m_off;
+};
+
+constexpr int kBlkThreads = 576;   // TMA warp, MMA warp, 2 x 4 epilogue-1 warps, 2 x 4 epilogue-2 warps
+
+__global__ void __launch_bounds__(kBlkThreads, 1)
+conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
+                    const __grid_constant__ CUtensorMap tmB2, ConvBlkParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t bar_ifull = base, bar_iempty = base + 64, bar_mfull = base + 128, bar_mempty = base + 192;
+  const uint32_t bar_t1full = base + 256, bar_t1empty = base + 320, bar_t2full = base + 384, bar_t2empty = base + 448;
+  const uint32_t bar_w = base + 512;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + 576);
+  float* s_b1 = reinterpret_cast<float*>(gbase + 1024);
+  float* s_b2 = reinterpret_cast<float*>(gbase + 1152);
+  const uint32_t w1_smem = base + p.w1_off, w2_smem = base + p.w2_off;
+  const uint32_t i_smem = base + p.i_off, m_smem = base + p.m_off;
+  constexpr uint32_t kWkw = 3u * 32 * 32 * 2;               // one horizontal tap of a conv: [(kh, co) = 96][ci = 32] fp16
+  constexpr uint32_t NB = 8, nb_mask = 7, nb_shift = 3;     // two TMEM rings of 8 x 32 columns
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) { s_b1[threadIdx.x] = p.bias1[threadIdx.x]; s_b2[threadIdx.x] = p.bias2[threadIdx.x]; }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(bar_ifull + 8 * s, 1); mbar_init(bar_iempty + 8 * s, 1);
+      mbar_init(bar_mfull + 8 * s, 4); mbar_init(bar_mempty + 8 * s, 1);
+      mbar_init(bar_t1full + 8 * s, 1); mbar_init(bar_t1empty + 8 * s, 4);
+      mbar_init(bar_t2full + 8 * s, 1); mbar_init(bar_t2empty + 8 * s, 4);
+    }
+    mbar_init(bar_w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp >= 2) {                                          // both rings start at zero (every MMA accumulates)
+    const uint32_t grp = (uint32_t)(warp - 2) >> 2;         // 4 warpgroups x 128 columns
+    const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * 128u;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tc_st32_zero(t0 + c * 32);
+    tc_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  auto decode = [&](int item, int& b, int& wt, int& h0, int& h1) {
+    const int hs = item % p.nhseg;
+    int t = item / p.nhseg;
+    wt = t % p.tiles_w;
+    b = t / p.tiles_w;
+    h0 = hs * p.R;
+    h1 = min(p.H, h0 + p.R);
+  };
+
+  if (warp == 0) {
+    // ---- TMA producer: both weight sets once, then input rows h0-2 .. h1+1 of every item -----------------------
+    const bool leader = elect_one_sync();
+    if (leader) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+      mbar_expect_tx(bar_w, 6u * kWkw);
+      for (int kw = 0; kw < 3; ++kw) {
+        tma_load_3d(&tmB1, bar_w, w1_smem + kw * kWkw, 0, 0, kw);
+        tma_load_3d(&tmB2, bar_w, w2_smem + kw * kWkw, 0, 0, kw);
+      }
+    }
+    __syncwarp();
+    uint32_t is = 0, iph = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int b, wt, h0, h1;
+      decode(item, b, wt, h0, h1);
+      const int R = h1 - h0;
+      for (int t = 0; t < R + 4; ++t) {
+        mbar_wait(bar_iempty + 8 * is, iph ^ 1);
+        if (leader) {
+          mbar_expect_tx(bar_ifull + 8 * is, 130u * 64u);
+          tma_load_4d(&tmA, bar_ifull + 8 * is, i_smem + is * p.slot_bytes, 0, wt * 126 - 2, h0 - 2 + t, b);
+        }
+        __syncwarp();
+        if (++is == (uint32_t)p.n_islots) { is = 0; iph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: conv1 on input rows, conv2 `lag` rows behind on the intermediate rows ---------------------
+    const bool leader = elect_one_sync();
+    const uint32_t dhi = desc_hi(512u, 4u);                 // 64-byte rows, SWIZZLE_64B
+    const uint32_t idesc0 = (1u << 4) | ((uint32_t)(kTileM >> 4) << 24);
+    mbar_wait(bar_w, 0);
+    tc_fence_after();
+    // rows [lo, hi] (descending, hi first) of a ring receive the vertical taps tap0, tap0+1, ... of source row `src`
+    auto fold = [&](uint32_t slot_addr, uint32_t w_addr, uint32_t ring_col, uint32_t grow, int src, int lo, int hi) {
+      const uint32_t alo0 = desc_lo(slot_addr);
+      int ra = hi;
+      while (ra >= lo) {
+        int rb = ra;
+        while (rb > lo && ((grow + (uint32_t)rb) & nb_mask) != 0u) --rb;
+        const uint32_t N = (uint32_t)(ra - rb + 1) * 32u;
+        const uint32_t d_tmem = tmem_base + ring_col + (nb_mask - ((grow + (uint32_t)ra) & nb_mask)) * 32u;
+        const uint32_t idesc = idesc0 | ((N >> 3) << 17);
+        const uint32_t bofs = (uint32_t)(src - ra) * 32u * 64u;
+        if (leader) {
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const uint32_t alo = alo0 + kw * 4u;            // one pixel row = 64 bytes = 4 descriptor units
+            const uint32_t blo = desc_lo(w_addr + kw * kWkw + bofs);
+            tc_mma_f16(d_tmem, desc_from(dhi, alo), desc_from(dhi, blo), idesc, 1);
+            tc_mma_f16(d_tmem, desc_from(dhi, alo + 2), desc_from(dhi, blo + 2), idesc, 1);
+          }
+        }
+        __syncwarp();
+        ra = rb - 1;
+      }
+    };
+    uint32_t is = 0, iph = 0, grow1 = 0, grow2 = 0;       // intermediate row g lives in slot g % 8
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int b, wt, h0, h1;
+      decode(item, b, wt, h0, h1);
+      const int R = h1 - h0, R1 = R + 2;                    // output rows, intermediate rows
+      for (int step = 0; step < R + 4 + p.lag; ++step) {
+        const int t = step;                                 // input row h0 - 2 + t feeds intermediate rows t, t-1, t-2
+        if (t < R + 4) {
+          mbar_wait(bar_ifull + 8 * is, iph);
+          tc_fence_after();
+          if (t < R1) {
+            const uint32_t g = grow1 + (uint32_t)t;
+            mbar_wait(bar_t1empty + 8 * (g & nb_mask), ((g >> nb_shift) & 1u) ^ 1u);
+            tc_fence_after();
+          }
+          fold(i_smem + is * p.slot_bytes, w1_smem, 0u, grow1, t, max(t - 2, 0), min(t, R1 - 1));
+          if (leader) {
+            tc_commit(bar_iempty + 8 * is);
+            if (t >= 2) tc_commit(bar_t1full + 8 * ((grow1 + (uint32_t)(t - 2)) & nb_mask));
+          }
+          __syncwarp();
+          if (++is == (uint32_t)p.n_islots) { is = 0; iph ^= 1; }
+        }
+        const int u = step - p.lag;                         // intermediate row h0 - 1 + u feeds output rows u, u-1, u-2
+        if (u >= 0 && u < R1) {
+          const uint32_t gm = grow1 + (uint32_t)u, ms = gm & 7u, mph = (gm >> 3) & 1u;
+          mbar_wait(bar_mfull + 8 * ms, mph);
+          tc_fence_after();
+          if (u < R) {
+            const uint32_t g = grow2 + (uint32_t)u;
+            mbar_wait(bar_t2empty + 8 * (g & nb_mask), ((g >> nb_shift) & 1u) ^ 1u);
+            tc_fence_after();
+          }
+          fold(m_smem + ms * p.slot_bytes, w2_smem, 256u, grow2, u, max(u - 2, 0), min(u, R - 1));
+          if (leader) {
+            tc_commit(bar_mempty + 8 * ms);
+            if (u >= 2) tc_commit(bar_t2full + 8 * ((grow2 + (uint32_t)(u - 2)) & nb_mask));
+          }
+          __syncwarp();
+        }
+      }
+      grow1 += (uint32_t)R1;
+      grow2 += (uint32_t)R;
+    }
+  } else if (warp < 10) {
+    // ---- epilogue 1 (two warpgroups, alternate rows): ring 1 -> relu(. + b1) -> fp16 -> intermediate slot ----------
+    const int q = warp & 3;
+    const uint32_t grp = (uint32_t)(warp - 2) >> 2;
+    const int m1 = q * 32 + lane;                           // conv1 row of the tile = TMEM lane
+    uint32_t grow1 = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int b, wt, h0, h1;
+      decode(item, b, wt, h0, h1);
+      const int R1 = h1 - h0 + 2;
+      const int c_img = wt * 126 - 1 + m1;
+      const bool col_ok = c_img >= 0 && c_img < p.W;
+      for (int u = 0; u < R1; ++u) {
+        const uint32_t g = grow1 + (uint32_t)u;
+        if ((g & 1u) != grp) continue;
+        const uint32_t blk = g & nb_mask;
+        const uint32_t ms = g & 7u, mph = (g >> 3) & 1u;
+        const int row_img = h0 - 1 + u;
+        const bool keep = col_ok && row_img >= 0 && row_img < p.H;    // zero padding of conv2's input
+        mbar_wait(bar_t1full + 8 * blk, (g >> nb_shift) & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (nb_mask - blk) * 32u;
+        uint32_t acc[32];
+        tc_ld32(taddr, acc);
+        tc_st32_zero(taddr);
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_t1empty + 8 * blk);
+        mbar_wait(bar_mempty + 8 * ms, mph ^ 1);            // conv2 has finished reading this slot
+        const uint32_t row_addr = m_smem + ms * p.slot_bytes + (uint32_t)(m1 + 1) * 64u;
+        const uint32_t sw = (row_addr >> 7) & 3u;           // SWIZZLE_64B: 16-byte chunk index ^ address bits [7,9)
+        const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b0 = reinterpret_cast<const float4*>(s_b1)[2 * j4];
+          const float4 b1 = reinterpret_cast<const float4*>(s_b1)[2 * j4 + 1];
+          uint4 v;
+          __half2* o2 = reinterpret_cast<__half2*>(&v);
+          o2[0] = __hmax2(__floats2half2_rn(__uint_as_float(acc[j4 * 8 + 0]) + b0.x, __uint_as_float(acc[j4 * 8 + 1]) + b0.y), zero2);
+          o2[1] = __hmax2(__floats2half2_rn(__uint_as_float(acc[j4 * 8 + 2]) + b0.z, __uint_as_float(acc[j4 * 8 + 3]) + b0.w), zero2);
+          o2[2] = __hmax2(__floats2half2_rn(__uint_as_float(acc[j4 * 8 + 4]) + b1.x, __uint_as_float(acc[j4 * 8 + 5]) + b1.y), zero2);
+          o2[3] = __hmax2(__floats2half2_rn(__uint_as_float(acc[j4 * 8 + 6]) + b1.z, __uint_as_float(acc[j4 * 8 + 7]) + b1.w), zero2);
+          if (!keep) v = make_uint4(0, 0, 0, 0);
+          const uint32_t a = row_addr + (((uint32_t)j4 ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                       : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tcgen05.mma reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_mfull + 8 * ms);
+      }
+      grow1 += (uint32_t)R1;
+    }
+  } else {
+    // ---- epilogue 2: ring 2 -> + b2 + residual -> relu -> NHWC store ---------------------------------------------
+    const int q = warp & 3;
+    const uint32_t grp = (uint32_t)(warp - 10) >> 2;
+    const int m = q * 32 + lane;
+    uint32_t grow2 = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int b, wt, h0, h1;
+      decode(item, b, wt, h0, h1);
+      const int R = h1 - h0;
+      const int w = wt * 126 - 1 + m;
+      const bool valid = m >= 1 && m <= 126 && w < p.W;
+      for (int r = 0; r < R; ++r) {
+        const uint32_t g = grow2 + (uint32_t)r;
+        if ((g & 1u) != grp) continue;
+        const uint32_t blk = g & nb_mask;
+        const size_t pix = (((size_t)b * p.H + (h0 + r)) * p.W + (valid ? w : 0)) * 32;
+        uint4 rpre[4];
+        {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.in + pix);   // residual = block input (L2: just streamed)
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) rpre[j4] = valid ? __ldg(rp + j4) : make_uint4(0, 0, 0, 0);
+        }
+        mbar_wait(bar_t2full + 8 * blk, (g >> nb_shift) & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (nb_mask - blk) * 32u;
+        uint32_t acc[32];
+        tc_ld32(taddr, acc);
+        tc_st32_zero(taddr);
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_t2empty + 8 * blk);
+        if (valid) {
+          uint4* op = reinterpret_cast<uint4*>(p.out + pix);
+          const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b0 = reinterpret_cast<const float4*>(s_b2)[2 * j4];
+            const float4 b1 = reinterpret_cast<const float4*>(s_b2)[2 * j4 + 1];
+            float v[8] = {__uint_as_float(acc[j4 * 8 + 0]) + b0.x, __uint_as_float(acc[j4 * 8 + 1]) + b0.y,
+                          __uint_as_float(acc[j4 * 8 + 2]) + b0.z, __uint_as_float(acc[j4 * 8 + 3]) + b0.w,
+                          __uint_as_float(acc[j4 * 8 + 4]) + b1.x, __uint_as_float(acc[j4 * 8 + 5]) + b1.y,
+                          __uint_as_float(acc[j4 * 8 + 6]) + b1.z, __uint_as_float(acc[j4 * 8 + 7]) + b1.w};
+            const __half2* h2 = reinterpret_cast<const __half2*>(&rpre[j4]);
+            uint4 u;
+            __half2* o2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(h2[e]);
+              o2[e] = __hmax2(__floats2half2_rn(v[2 * e] + f.x, v[2 * e + 1] + f.y), zero2);
+            }
+            op[j4] = u;
+          }
+        }
+      }
+      grow2 += (uint32_t)R;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // SIMT reference conv (same math, CUDA cores) -- debugging aid and A/B check for the tensor-core path
 // ------------------------------------------------------------------------------------------------
 __global__ void conv_simt_kernel(const __half* __restrict__ in, const __half* __restrict__ wt, ConvParams p) {
@@ -1106,6 +1412,63 @@ static int conv4_forward(const ConvLayer& L, const __half* in, const __half* res
   const size_t smem = 1024 + p.a_off + (size_t)p.n_aslots * p.a_slot_bytes;
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
   conv_tc4_kernel<<<grid, kV4Threads, smem, stream>>>(tmA, tmB, p);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+// fused BasicBlock (conv_block32_kernel): in -> out, out must not alias in (tiles read their neighbours' halo)
+int conv_block32_forward(const ConvLayer& L1, const ConvLayer& L2, const __half* in, __half* out, int B, int H, int W,
+                         int num_sms, cudaStream_t stream) {
+  B200_CHECK(L1.w4 && L2.w4 && L1.C_in == 32 && L1.C_out == 32 && L2.C_in == 32 && L2.C_out == 32 && in != out,
+             B200_ERR_STATE, "conv block: needs two folded 32->32 convs and distinct buffers");
+  ConvBlkParams p{};
+  p.B = B; p.H = H; p.W = W; p.bias1 = L1.bias; p.bias2 = L2.bias; p.in = in; p.out = out;
+  p.tiles_w = ceil_div(W, 126);
+  p.lag = 4;
+  const int strips = B * p.tiles_w;
+  long best_cost = -1;
+  for (int nh = 1; nh <= (H > 1 ? H / 2 : 1); ++nh) {
+    const int R = ceil_div(H, nh), n = ceil_div(H, R);
+    const long cost = (long)ceil_div(strips * n, num_sms) * (R + 4 + p.lag + 1);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; p.R = R; p.nhseg = n; }
+  }
+  p.num_items = B * p.tiles_w * p.nhseg;
+  p.slot_bytes = 9216;                                       // 130 pixel rows x 64 B, 1024-aligned
+  p.n_islots = 6; p.n_mslots = 8;
+  p.w1_off = 2048; p.w2_off = 2048 + 18432;
+  p.i_off = 2048 + 2 * 18432;                                // 38912 = 38 x 1024
+  p.m_off = p.i_off + p.n_islots * p.slot_bytes;
+  PFN_encodeTiled enc = get_encode();
+  B200_CHECK(enc != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  CUtensorMap tmA, tmB1, tmB2;
+  {
+    cuuint64_t dims[4] = {32, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {64, (cuuint64_t)W * 64, (cuuint64_t)H * W * 64};
+    cuuint32_t box[4] = {32, 130, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(in), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(A, block) failed: %d", (int)r);
+  }
+  for (int i = 0; i < 2; ++i) {
+    cuuint64_t dims[3] = {32, 96, 3};
+    cuuint64_t strides[2] = {64, 96 * 64};
+    cuuint32_t box[3] = {32, 96, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(i ? &tmB2 : &tmB1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(i ? L2.w4 : L1.w4), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(B, block) failed: %d", (int)r);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(conv_block32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const size_t smem = 1024 + p.m_off + (size_t)p.n_mslots * p.slot_bytes;
+  const int grid = p.num_items < num_sms ? p.num_items : num_sms;
+  conv_block32_kernel<<<grid, kBlkThreads, smem, stream>>>(tmA, tmB1, tmB2, p);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }

@@ -99,12 +99,17 @@ if args.stage == "conv_ab":
     torch.cuda.synchronize()
     report(f"trunk impl={args.impl} vs SIMT", got.cpu().numpy(), ref)
     big = fb.repeat(43, 1, 1)[:256].contiguous()
-    for impl in (1, args.impl):
+    ctx.set_option("conv_fuse", 0)
+    got_u = ctx.emb_trunk(fb)
+    torch.cuda.synchronize()
+    report("fused layer1 blocks vs unfused", got.cpu().numpy(), got_u.cpu().numpy())
+    for impl, fuse in ((1, 0), (args.impl, 0), (args.impl, 1)):
+        ctx.set_option("conv_fuse", fuse)
         ctx.set_option("conv_impl", impl)
         ctx.emb_trunk(big); torch.cuda.synchronize()
         t0 = time.time(); ctx.emb_trunk(big); torch.cuda.synchronize()
         dt = time.time() - t0
-        print(f"  impl={impl}: 256 segments trunk {dt*1e3:.1f} ms -> {256*45.18e9/dt/1e12:.0f} TFLOP/s", flush=True)
+        print(f"  impl={impl} fuse={fuse}: 256 segments trunk {dt*1e3:.1f} ms -> {256*45.18e9/dt/1e12:.0f} TFLOP/s", flush=True)
 
 if args.stage == "post":
     x = torch.tensor([[[2.0, 4.0], [2.0, 4.0]], [[1.0, 1.0], [1.0, 1.0]]], device=dev)
