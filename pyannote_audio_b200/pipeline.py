@@ -97,6 +97,20 @@ class PretrainedSpeakerEmbedding:
         return self.model_(waveforms, weights=masks).cpu().numpy()
 
 
+def _sparse_true(x: np.ndarray) -> np.ndarray:
+    """Flat indices of the True entries of a (mostly False) bool array: scan 8 flags per uint64 word, then only the
+    few non-zero words (np.nonzero on the 2-D array costs 0.35 ms for a 10-minute file, this 0.03 ms)."""
+    flat = np.ascontiguousarray(x).ravel()
+    pad = (-flat.size) % 8
+    if pad:
+        flat = np.concatenate([flat, np.zeros(pad, dtype=bool)])
+    words = np.flatnonzero(flat.view(np.uint64))
+    if words.size == 0:
+        return np.zeros(0, dtype=np.int64)
+    sub_w, sub_b = np.nonzero(flat.reshape(-1, 8)[words])
+    return words[sub_w] * 8 + sub_b
+
+
 def binarize_frames(discrete: np.ndarray, frames: SlidingWindow, min_duration_off: float = 0.0,
                     uri: Optional[str] = None) -> Tuple[Annotation, np.ndarray]:
     """to_annotation (diarization.py:188-218) / Binarize(onset=offset=0.5) (utils/signal.py:254-318), vectorised.
@@ -108,11 +122,11 @@ def binarize_frames(discrete: np.ndarray, frames: SlidingWindow, min_duration_of
     n, K = discrete.shape
     if n < 2 or K == 0:
         return Annotation(uri=uri), np.zeros((0, 3), dtype=np.int64)
-    act = np.zeros((n + 2, K), dtype=np.int8)
-    act[1:-1] = discrete > 0
-    d = np.diff(act, axis=0)                                   # (n+1, K): +1 at onsets, -1 at offsets
-    on_t, on_k = np.nonzero(d.T == 1)[::-1]                    # column-major scan: grouped by k, ascending t
-    off_t, off_k = np.nonzero(d.T == -1)[::-1]
+    act = np.zeros((K, n + 2), dtype=bool)                     # speaker-major and contiguous: nonzero() scans rows
+    act[:, 1:-1] = discrete.T > 0
+    # grouped by k, ascending t; the i-th offset closes the i-th onset
+    on_k, on_t = np.divmod(_sparse_true(act[:, 1:] & ~act[:, :-1]), n + 1)
+    off_k, off_t = np.divmod(_sparse_true(act[:, :-1] & ~act[:, 1:]), n + 1)
     off_t = np.minimum(off_t, n - 1)                           # still active at the end -> last frame
     order = np.lexsort((on_k, off_t, on_t))                    # sort by (start, end, k)
     rows = np.stack([on_t[order], off_t[order], on_k[order]], axis=1).astype(np.int64)
