@@ -136,6 +136,13 @@ int b200_reconstruct(b200_ctx* ctx, const uint8_t* seg, const int8_t* hard_clust
                      int32_t num_chunks, int32_t num_frames, const uint8_t* count, int32_t num_clusters_out,
                      uint8_t* discrete, void* stream);
 
+/* Onsets / offsets of a discrete diarization discrete[num_frames][num_clusters] u8 (to_annotation ->
+ * Binarize(onset=offset=0.5), pipelines/utils/diarization.py:188-218, utils/signal.py:254-318) as unordered events
+ * k * (num_frames + 1) + f.  buf (DEVICE int32[2 + 2 * cap]) = [n_on, n_off, on[cap], off[cap]]; counts may exceed
+ * cap (then only cap events were stored: call again with a larger buffer). */
+int b200_frame_transitions(b200_ctx* ctx, const uint8_t* discrete, int32_t num_frames, int32_t num_clusters,
+                           int32_t cap, int32_t* buf, void* stream);
+
 /* ---- clustering (pipelines/clustering.py:77-140, 572-669; utils/vbx.py; scipy linkage/fcluster) --------------- */
 /* filter_embeddings: clean-frame counts per (chunk, speaker): out[num_chunks][3] int32, plus active[num_chunks][3] u8
  * = any frame active (inactive speakers, speaker_diarization.py:681). */

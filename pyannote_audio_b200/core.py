@@ -176,17 +176,20 @@ class Annotation:
 
     @classmethod
     def from_rows(cls, starts: np.ndarray, ends: np.ndarray, labels, uri: Optional[str] = None) -> "Annotation":
-        """Rows must already be sorted by (start, end, track)."""
+        """Rows must already be sorted by (start, end, track).  ``labels`` may be an integer array (kept as such:
+        relabelling thousands of segments then is one table lookup instead of a Python loop)."""
         a = cls(uri=uri)
-        a._rows = (np.asarray(starts, dtype=np.float64), np.asarray(ends, dtype=np.float64),
-                   np.asarray(labels, dtype=object))
+        lab = np.asarray(labels)
+        if lab.dtype.kind not in "iu":
+            lab = np.asarray(labels, dtype=object)
+        a._rows = (np.asarray(starts, dtype=np.float64), np.asarray(ends, dtype=np.float64), lab)
         a._tracks = None
         return a
 
     def _materialise(self):
         if self._tracks is None:
             st, en, lab = self._rows
-            self._tracks = [(Segment(float(a), float(b)), i, l) for i, (a, b, l) in enumerate(zip(st, en, lab))]
+            self._tracks = [(Segment(float(a), float(b)), i, l) for i, (a, b, l) in enumerate(zip(st, en, lab.tolist()))]
             self._sorted = True
             self._rows = None
 
@@ -216,13 +219,22 @@ class Annotation:
 
     def labels(self):
         if self._tracks is None:
-            return sorted(set(self._rows[2].tolist()), key=lambda v: (str(type(v)), v))
+            lab = self._rows[2]
+            if lab.dtype.kind in "iu":
+                return np.unique(lab).tolist()
+            return sorted(set(lab.tolist()), key=lambda v: (str(type(v)), v))
         return sorted({label for _, _, label in self._tracks}, key=lambda v: (str(type(v)), v))
 
     def rename_labels(self, mapping: dict) -> "Annotation":
         if self._tracks is None:
             st, en, lab = self._rows
-            new = np.array([mapping.get(l, l) for l in lab.tolist()], dtype=object) if len(lab) else lab
+            if len(lab) and lab.dtype.kind in "iu":
+                uniq, inv = np.unique(lab, return_inverse=True)
+                table = np.empty(len(uniq), dtype=object)
+                table[:] = [mapping.get(u, u) for u in uniq.tolist()]
+                new = table[inv]
+            else:
+                new = np.array([mapping.get(l, l) for l in lab.tolist()], dtype=object) if len(lab) else lab
             return Annotation.from_rows(st, en, new, uri=self.uri)
         out = Annotation(uri=self.uri)
         out._tracks = [(s, t, mapping.get(lab, lab)) for s, t, lab in self._tracks]

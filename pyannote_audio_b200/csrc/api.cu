@@ -208,6 +208,8 @@ int b200_ctx_create(b200_ctx** out, int device) {
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   if (const char* e = std::getenv("B200_CONV_IMPL")) c->conv_impl = std::atoi(e);
+  if (const char* e = std::getenv("B200_EMB_MAX_BATCH")) c->emb_max_batch = std::atoi(e) > 0 ? std::atoi(e) : c->emb_max_batch;
+  if (const char* e = std::getenv("B200_SEG_MAX_BATCH")) c->seg_max_batch = std::atoi(e) > 0 ? std::atoi(e) : c->seg_max_batch;
   *out = c;
   return B200_OK;
 }
@@ -697,6 +699,15 @@ int b200_reconstruct(b200_ctx* ctx, const uint8_t* seg, const int8_t* hard_clust
   ctx->launches += 1;
   return reconstruct(seg, (const signed char*)hard_clusters, start_frame, num_chunks, num_frames, num_clusters_out,
                      count, discrete, (cudaStream_t)stream);
+}
+
+int b200_frame_transitions(b200_ctx* ctx, const uint8_t* discrete, int32_t num_frames, int32_t num_clusters,
+                           int32_t cap, int32_t* buf, void* stream) {
+  B200_CHECK(ctx && discrete && buf && num_frames > 0 && num_clusters > 0 && cap > 0, B200_ERR_INVALID,
+             "bad arguments");
+  DeviceGuard g(ctx->device);
+  ctx->launches += 1;
+  return frame_transitions(discrete, num_frames, num_clusters, cap, buf, (cudaStream_t)stream);
 }
 
 int b200_clean_frames(b200_ctx* ctx, const uint8_t* seg, int32_t num_chunks, int32_t* clean, uint8_t* active,

@@ -116,6 +116,31 @@ int reconstruct(const unsigned char* seg, const signed char* hard, const int* sf
   return B200_OK;
 }
 
+// ---- onsets / offsets of the discrete diarization (Binarize with onset = offset = 0.5, utils/signal.py:254-318) ----
+// One thread per frame boundary f in [0, F]: speaker k switches on at f when d[f][k] && !d[f-1][k], off when
+// d[f-1][k] && !d[f][k] (f = F closes regions still active at the last frame).  Events are appended unordered as
+// k * (F + 1) + f; the host sorts the (few hundred) events.  buf = [n_on, n_off, on[cap], off[cap]].
+__global__ void __launch_bounds__(256) frame_transitions_kernel(const unsigned char* __restrict__ d, int F, int K,
+                                                                int cap, int* __restrict__ buf) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f > F) return;
+  const unsigned char* cur = d + (size_t)f * K;
+  const unsigned char* prev = cur - K;
+  for (int k = 0; k < K; ++k) {
+    const bool c = f < F && cur[k] != 0, pv = f > 0 && prev[k] != 0;
+    if (c == pv) continue;
+    const int slot = atomicAdd(buf + (c ? 0 : 1), 1);
+    if (slot < cap) buf[2 + (c ? 0 : cap) + slot] = k * (F + 1) + f;
+  }
+}
+
+int frame_transitions(const unsigned char* discrete, int F, int K, int cap, int* buf, cudaStream_t stream) {
+  B200_CUDA_OK(cudaMemsetAsync(buf, 0, 2 * sizeof(int), stream));
+  frame_transitions_kernel<<<ceil_div(F + 1, 256), 256, 0, stream>>>(discrete, F, K, cap, buf);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
 __global__ void clean_frames_kernel(const unsigned char* __restrict__ seg, int C, int* __restrict__ clean,
                                     unsigned char* __restrict__ active) {
   // one warp per chunk

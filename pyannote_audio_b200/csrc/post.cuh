@@ -5,5 +5,6 @@ int powerset_to_multilabel(const unsigned char* cls, long long n, unsigned char*
 int speaker_count(const unsigned char* seg, const int* sf, int C, int F, unsigned char* count, cudaStream_t stream);
 int reconstruct(const unsigned char* seg, const signed char* hard, const int* sf, int C, int F, int Kout,
                 const unsigned char* count, unsigned char* out, cudaStream_t stream);
+int frame_transitions(const unsigned char* discrete, int F, int K, int cap, int* buf, cudaStream_t stream);
 int clean_frames(const unsigned char* seg, int C, int* clean, unsigned char* active, cudaStream_t stream);
 }

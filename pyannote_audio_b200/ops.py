@@ -299,6 +299,26 @@ class Context:
                                                  _ptr(count), num_clusters_out, _ptr(out), _stream(self.device)))
         return out
 
+    def frame_transitions(self, discrete: torch.Tensor, cap: int = 4096):
+        """discrete (F, K) u8 on the device -> sorted flat event indices k * (F + 1) + f of onsets and offsets
+        (host int64 arrays).  One kernel + one 32 KB D2H instead of shipping and scanning the whole matrix."""
+        F, K = int(discrete.shape[0]), int(discrete.shape[1])
+        d = discrete.contiguous()
+        while True:
+            buf = torch.empty((2 + 2 * cap,), dtype=torch.int32, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.b200_frame_transitions(self._h, _ptr(d), F, K, cap, _ptr(buf),
+                                                           _stream(self.device)))
+            host = buf.cpu().numpy()
+            n_on, n_off = int(host[0]), int(host[1])
+            if max(n_on, n_off) <= cap:
+                break
+            cap = 1 << int(max(n_on, n_off) - 1).bit_length()
+        self.last_transfer_bytes = host.nbytes
+        on = np.sort(host[2: 2 + n_on].astype(np.int64))
+        off = np.sort(host[2 + cap: 2 + cap + n_off].astype(np.int64))
+        return on, off
+
     def clean_frames(self, seg: torch.Tensor):
         n = seg.shape[0]
         clean = torch.empty((n, SPEAKERS), dtype=torch.int32, device=self.device)

@@ -15,6 +15,9 @@ from __future__ import annotations
 
 import math
 import textwrap
+import os
+import sys
+import time
 import warnings
 from dataclasses import dataclass
 from typing import Any, Callable, Iterator, List, Mapping, Optional, Sequence, Tuple, Union
@@ -111,22 +114,31 @@ def _sparse_true(x: np.ndarray) -> np.ndarray:
     return words[sub_w] * 8 + sub_b
 
 
-def binarize_frames(discrete: np.ndarray, frames: SlidingWindow, min_duration_off: float = 0.0,
-                    uri: Optional[str] = None) -> Tuple[Annotation, np.ndarray]:
+def binarize_frames(discrete: Optional[np.ndarray], frames: SlidingWindow, min_duration_off: float = 0.0,
+                    uri: Optional[str] = None, events=None) -> Tuple[Annotation, np.ndarray]:
     """to_annotation (diarization.py:188-218) / Binarize(onset=offset=0.5) (utils/signal.py:254-318), vectorised.
 
     A region switched on at frame a and off at frame b is [middle(a), middle(b)]; a region still active at the last
     frame n-1 closes at middle(n-1).  Returns the Annotation (integer labels) and the (n_segments, 3) int array of
     (start_frame, end_frame, label), both in Annotation.itertracks() order: by (start, end), then speaker column.
+    ``events`` = (n, on, off) with the sorted flat indices k * (n + 1) + f found on the device
+    (ops.Context.frame_transitions) replaces the host scan of ``discrete``.
     """
-    n, K = discrete.shape
-    if n < 2 or K == 0:
-        return Annotation(uri=uri), np.zeros((0, 3), dtype=np.int64)
-    act = np.zeros((K, n + 2), dtype=bool)                     # speaker-major and contiguous: nonzero() scans rows
-    act[:, 1:-1] = discrete.T > 0
+    if events is not None:
+        n, on, off = events
+        if n < 2:
+            return Annotation(uri=uri), np.zeros((0, 3), dtype=np.int64)
+    else:
+        n, K = discrete.shape
+        if n < 2 or K == 0:
+            return Annotation(uri=uri), np.zeros((0, 3), dtype=np.int64)
+        act = np.zeros((K, n + 2), dtype=bool)                 # speaker-major and contiguous
+        act[:, 1:-1] = discrete.T > 0
+        on = _sparse_true(act[:, 1:] & ~act[:, :-1])
+        off = _sparse_true(act[:, :-1] & ~act[:, 1:])
     # grouped by k, ascending t; the i-th offset closes the i-th onset
-    on_k, on_t = np.divmod(_sparse_true(act[:, 1:] & ~act[:, :-1]), n + 1)
-    off_k, off_t = np.divmod(_sparse_true(act[:, :-1] & ~act[:, 1:]), n + 1)
+    on_k, on_t = np.divmod(on, n + 1)
+    off_k, off_t = np.divmod(off, n + 1)
     off_t = np.minimum(off_t, n - 1)                           # still active at the end -> last frame
     order = np.lexsort((on_k, off_t, on_t))                    # sort by (start, end, k)
     rows = np.stack([on_t[order], off_t[order], on_k[order]], axis=1).astype(np.int64)
@@ -135,7 +147,7 @@ def binarize_frames(discrete: np.ndarray, frames: SlidingWindow, min_duration_of
     s1 = frames.start + rows[:, 1] * frames.step
     starts = 0.5 * (s0 + (s0 + frames.duration))
     ends = 0.5 * (s1 + (s1 + frames.duration))
-    ann = Annotation.from_rows(starts, ends, rows[:, 2].tolist(), uri=uri)
+    ann = Annotation.from_rows(starts, ends, rows[:, 2], uri=uri)
     if min_duration_off > 0.0:
         ann = ann.support(collar=min_duration_off)
     return ann, rows
@@ -445,6 +457,12 @@ class SpeakerDiarization:
             pending.append((discrete, exclusive, hard, r["centroids"], K))
         tm.mark("reconstruct")
         outs = []
+        d2h_s = 0.0
+        _prof = None
+        if os.environ.get("B200_TIMING") == "3":           # host-side diagnostics of the annotation loop
+            import cProfile
+            _prof = cProfile.Profile()
+            _prof.enable()
         for fi, file in enumerate(files):
             uri = file.get("uri", None)
             artifacts = None
@@ -459,12 +477,18 @@ class SpeakerDiarization:
                 continue
             discrete, exclusive, hard, centroids, K = pending[fi]
             _, nF, fr = grids[fi]
-            discrete_np, exclusive_np = discrete.cpu().numpy(), exclusive.cpu().numpy()          # D2H of the result
+            _t0 = time.perf_counter()
+            # run-length encoding: onsets / offsets are found on the device, only those events cross PCIe; the full
+            # (frames, clusters) matrices are materialised on the host only for hooks / artifacts that look at them
+            ev_d = ctx.frame_transitions(discrete)
+            self.d2h_bytes += ctx.last_transfer_bytes
+            ev_x = ctx.frame_transitions(exclusive)
+            self.d2h_bytes += ctx.last_transfer_bytes
             centroids = centroids.cpu().numpy()
+            self.d2h_bytes += centroids.nbytes + 8
+            d2h_s += time.perf_counter() - _t0
             cmax = int(count_max[fi]) if not np.isfinite(max_speakers) else min(int(count_max[fi]), int(max_speakers))
-            discrete_np = discrete_np[:, : max(K, cmax)]
-            exclusive_np = exclusive_np[:, : max(K, min(cmax, 1))]
-            self.d2h_bytes += discrete.numel() + exclusive.numel() + centroids.nbytes + 8
+            kd, kx = max(K, cmax), max(K, min(cmax, 1))
             if K < min_speakers or K > max_speakers:
                 warnings.warn(textwrap.dedent(f"""
                     The detected number of speakers ({K}) for {uri} is outside
@@ -472,10 +496,11 @@ class SpeakerDiarization:
                     given audio file is too short to contain {min_speakers} or more speakers.
                     Try to lower the desired minimal number of speakers.
                     """))
-            hooks[fi]("discrete_diarization", _Lazy(lambda d=discrete_np, fr=fr: SlidingWindowFeature(
-                d.astype(np.float64), fr)))
-            diarization, rows = binarize_frames(discrete_np, fr, self.min_duration_off, uri=uri)
-            exclusive_diarization, xrows = binarize_frames(exclusive_np, fr, self.min_duration_off, uri=uri)
+            hooks[fi]("discrete_diarization", _Lazy(lambda d=discrete, fr=fr, kd=kd: SlidingWindowFeature(
+                d.cpu().numpy()[:, :kd].astype(np.float64), fr)))
+            diarization, rows = binarize_frames(None, fr, self.min_duration_off, uri=uri, events=(nF,) + ev_d)
+            exclusive_diarization, xrows = binarize_frames(None, fr, self.min_duration_off, uri=uri,
+                                                           events=(nF,) + ev_x)
             labels_int = diarization.labels()
             mapping = {label: expected for label, expected in zip(labels_int, self.classes())}
             diarization = diarization.rename_labels(mapping)
@@ -486,12 +511,19 @@ class SpeakerDiarization:
             centroids = centroids[[inverse[l] for l in diarization.labels()]] if len(labels_int) else centroids[:0]
             output = DiarizeOutput(diarization, exclusive_diarization, centroids)
             if return_artifacts:
-                artifacts.update(hard_clusters=hard.cpu().numpy(), discrete=discrete_np, exclusive=exclusive_np,
-                                 segments=rows, exclusive_segments=xrows, centroids=centroids)
+                artifacts.update(hard_clusters=hard.cpu().numpy(), discrete=discrete.cpu().numpy()[:, :kd],
+                                 exclusive=exclusive.cpu().numpy()[:, :kx], segments=rows, exclusive_segments=xrows,
+                                 centroids=centroids)
                 outs.append(((output.speaker_diarization if self.legacy else output), artifacts))
             else:
                 outs.append(output.speaker_diarization if self.legacy else output)
+        if _prof is not None:
+            import pstats
+            _prof.disable()
+            pstats.Stats(_prof, stream=sys.stderr).sort_stats("tottime").print_stats(12)
         tm.mark("d2h+annotation")
+        if os.environ.get("B200_TIMING") == "2":
+            print(f"[b200 annotation] d2h={d2h_s * 1e3:.1f}ms of the d2h+annotation stage", file=sys.stderr)
         return outs
 
 

@@ -196,6 +196,14 @@ def test_post_processing_bit_exact(ctx, dev):
             d = ctx.reconstruct(seg_dev, hard, sf, F, torch.from_numpy(cnt.data[:, 0].astype(np.uint8)).to(dev), Kout)
             assert np.array_equal(d.cpu().numpy()[:, : ref_d.data.shape[1]], ref_d.data.astype(np.uint8))
             assert not d.cpu().numpy()[:, ref_d.data.shape[1]:].any()
+            # device run-length events == host scan of the same matrix (also with a capacity that overflows once)
+            dn = d.cpu().numpy()
+            act = np.zeros((dn.shape[1], F + 2), dtype=bool)
+            act[:, 1:-1] = dn.T > 0
+            for ecap in (4096, 2):
+                on, off = ctx.frame_transitions(d, cap=ecap)
+                assert np.array_equal(on, np.flatnonzero(act[:, 1:] & ~act[:, :-1]))
+                assert np.array_equal(off, np.flatnonzero(act[:, :-1] & ~act[:, 1:]))
         clean, active = ctx.clean_frames(seg_dev)
         single = seg.sum(2, keepdims=True) == 1
         assert np.array_equal(clean.cpu().numpy(), (seg * single).sum(1).astype(np.int32))

@@ -87,6 +87,15 @@ def test_binarize_frames_matches_oracle():
         assert [tuple(r) for r in rows] == ref_rows
         got = [(s.start, s.end, lab) for s, _, lab in ann.itertracks(yield_label=True)]
         assert got == ref_times
+        # the same from precomputed onset / offset events (what ops.Context.frame_transitions returns)
+        n, K = d.shape
+        act = np.zeros((K, n + 2), dtype=bool)
+        act[:, 1:-1] = d.T > 0
+        on = np.flatnonzero(act[:, 1:] & ~act[:, :-1])
+        off = np.flatnonzero(act[:, :-1] & ~act[:, 1:])
+        ann2, rows2 = binarize_frames(None, frames, events=(n, on, off))
+        assert np.array_equal(rows2, rows)
+        assert [(s.start, s.end, lab) for s, _, lab in ann2.itertracks(yield_label=True)] == got
 
 
 def test_sliding_window_arithmetic_matches_oracle():
