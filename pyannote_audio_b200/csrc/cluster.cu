@@ -90,12 +90,20 @@ __device__ __forceinline__ MinPair warp_min(MinPair m) {
   return m;
 }
 
-// nearest alive j > k of row k, computed by one warp
-__device__ __forceinline__ void row_nn(const double* __restrict__ D, const unsigned char* __restrict__ alive, int n,
-                                       int k, int lane, double* nn_d, int* nn_i) {
+// nearest alive j > k of row k, computed by one warp (four independent loads in flight per lane)
+__device__ __forceinline__ void row_nn(const double* __restrict__ D, const unsigned char* alive, int n, int k, int lane,
+                                       double* nn_d, int* nn_i) {
   MinPair m{DBL_MAX, n};
   const double* row = D + (size_t)k * n;
-  for (int j = k + 1 + lane; j < n; j += 32)
+  int j = k + 1 + lane;
+  for (; j + 96 < n; j += 128) {
+    const double v0 = row[j], v1 = row[j + 32], v2 = row[j + 64], v3 = row[j + 96];
+    if (alive[j]) m = min_pair(m, MinPair{v0, j});
+    if (alive[j + 32]) m = min_pair(m, MinPair{v1, j + 32});
+    if (alive[j + 64]) m = min_pair(m, MinPair{v2, j + 64});
+    if (alive[j + 96]) m = min_pair(m, MinPair{v3, j + 96});
+  }
+  for (; j < n; j += 32)
     if (alive[j]) m = min_pair(m, MinPair{row[j], j});
   m = warp_min(m);
   if (lane == 0) { nn_d[k] = m.v; nn_i[k] = m.i; }
@@ -109,7 +117,13 @@ struct LinkJob {
   long long d_off;    // element offset of this problem's n x n distance matrix
 };
 
-// one CTA per clustering problem (file): problems are independent, so a batch of files fills the machine
+constexpr int kLinkSmemRows = 4096;   // per-row state lives in shared memory up to this many rows
+
+// one CTA per clustering problem (file): problems are independent, so a batch of files fills the machine.
+// Per merge: (A) block-wide argmin over the nearest-neighbour candidates, (B) one fused pass that applies the
+// Lance-Williams update to row/column y, maintains the candidates of the rows k < y and collects the new nearest
+// neighbour of y from the values it has just computed (no re-scan of row y), (C) re-scan of the few rows whose
+// candidate was x or y.  Arithmetic and tie rules are unchanged, so dendrograms still match scipy bit for bit.
 __global__ void __launch_bounds__(1024) linkage_centroid_kernel(const LinkJob* __restrict__ jobs,
                                                                 double* __restrict__ Dall, double* __restrict__ Zall,
                                                                 double* __restrict__ nn_d_all,
@@ -117,17 +131,29 @@ __global__ void __launch_bounds__(1024) linkage_centroid_kernel(const LinkJob* _
                                                                 int* __restrict__ id_all,
                                                                 unsigned char* __restrict__ alive_all,
                                                                 int* __restrict__ todo_all) {
+  extern __shared__ unsigned char link_smem[];
   const LinkJob job = jobs[blockIdx.x];
   const int n = job.n;
   if (n < 2) return;
   double* __restrict__ D = Dall + job.d_off;
   double* __restrict__ Z = Zall + (size_t)job.z_off * 4;
-  double* __restrict__ nn_d = nn_d_all + job.row_off;
-  int* __restrict__ nn_i = nn_i_all + job.row_off;
-  int* __restrict__ size = size_all + job.row_off;
   int* __restrict__ id = id_all + job.row_off;
-  unsigned char* __restrict__ alive = alive_all + job.row_off;
   int* __restrict__ todo = todo_all + job.row_off + blockIdx.x;     // n + 1 entries per problem
+  double* nn_d;
+  int* nn_i;
+  int* size;
+  unsigned char* alive;
+  if (n <= kLinkSmemRows) {            // generic pointers: shared or global
+    nn_d = reinterpret_cast<double*>(link_smem);
+    nn_i = reinterpret_cast<int*>(link_smem + (size_t)kLinkSmemRows * 8);
+    size = reinterpret_cast<int*>(link_smem + (size_t)kLinkSmemRows * 12);
+    alive = link_smem + (size_t)kLinkSmemRows * 16;
+  } else {
+    nn_d = nn_d_all + job.row_off;
+    nn_i = nn_i_all + job.row_off;
+    size = size_all + job.row_off;
+    alive = alive_all + job.row_off;
+  }
   __shared__ MinPair s_red[32];
   __shared__ int s_x, s_y, s_ntodo;
   __shared__ double s_dxy;
@@ -156,7 +182,7 @@ __global__ void __launch_bounds__(1024) linkage_centroid_kernel(const LinkJob* _
       }
     }
     __syncthreads();
-    const int x = s_x, y = s_y;
+    const int x = s_x, y = s_y;                            // x < y: candidates only look right
     const double dxy = s_dxy;
     const double nx = size[x], ny = size[y];
     if (tid == 0) {
@@ -166,34 +192,48 @@ __global__ void __launch_bounds__(1024) linkage_centroid_kernel(const LinkJob* _
       Z[m * 4 + 2] = dxy;
       Z[m * 4 + 3] = nx + ny;
     }
-    // B. Lance-Williams update: merged cluster lives in slot y, slot x dies
+    // B. Lance-Williams update (merged cluster lives in slot y, slot x dies) + candidate maintenance
     const double* rx = D + (size_t)x * n;
     double* ry = D + (size_t)y * n;
+    MinPair ybest{DBL_MAX, n};
     for (int k = tid; k < n; k += 1024) {
       if (!alive[k] || k == x || k == y) continue;
       const double dn = lw_centroid(rx[k], ry[k], dxy, nx, ny);
       ry[k] = dn;
       D[(size_t)k * n + y] = dn;
-    }
-    __syncthreads();
-    if (tid == 0) { alive[x] = 0; size[y] = (int)(nx + ny); id[y] = n + m; }
-    __syncthreads();
-    // C. nearest-neighbour maintenance
-    for (int k = tid; k < y; k += 1024) {
-      if (!alive[k]) continue;
-      const int cur = nn_i[k];
-      if (cur == x || cur == y) {
-        todo[atomicAdd(&s_ntodo, 1)] = k;
+      if (k > y) {
+        ybest = min_pair(ybest, MinPair{dn, k});           // new nearest neighbour of y among j > y
       } else {
-        const double dn = D[(size_t)k * n + y];
-        if (dn < nn_d[k] || (dn == nn_d[k] && y < cur)) { nn_d[k] = dn; nn_i[k] = y; }
+        const int cur = nn_i[k];
+        if (cur == x || cur == y) {
+          todo[atomicAdd(&s_ntodo, 1)] = k;                // its candidate vanished or changed: re-scan
+        } else if (dn < nn_d[k] || (dn == nn_d[k] && y < cur)) {
+          nn_d[k] = dn;
+          nn_i[k] = y;
+        }
       }
     }
-    if (tid == 0) todo[atomicAdd(&s_ntodo, 1)] = y;
+    ybest = warp_min(ybest);
+    __syncthreads();                                       // s_red free again, all reads of size/id done
+    if (lane == 0) s_red[warp] = ybest;
     __syncthreads();
+    if (warp == 0) {
+      MinPair b = warp_min(s_red[lane]);
+      if (lane == 0) {
+        nn_d[y] = b.v;
+        nn_i[y] = b.i;
+        alive[x] = 0;
+        size[y] = (int)(nx + ny);
+        id[y] = n + m;
+      }
+    }
+    __syncthreads();
+    // C. rows whose candidate was x or y
     const int nt = s_ntodo;
-    for (int t = warp; t < nt; t += 32) row_nn(D, alive, n, todo[t], lane, nn_d, nn_i);
-    __syncthreads();
+    if (nt > 0) {
+      for (int t = warp; t < nt; t += 32) row_nn(D, alive, n, todo[t], lane, nn_d, nn_i);
+      __syncthreads();
+    }
   }
 }
 
@@ -468,7 +508,14 @@ int linkage_centroid_batched(const double* x, const int* row_offsets, int nfiles
     dim3 grid(ceil_div(n, 16), ceil_div(n, 16));
     pdist_kernel<<<grid, dim3(16, 16), 0, st>>>(src + (size_t)jobs[f].row_off * dim, D + jobs[f].d_off, n, dim);
   }
-  linkage_centroid_kernel<<<nfiles, 1024, 0, st>>>(djobs, D, Z, nn_d, nn_i, size, id, alive, todo);
+  static bool link_attr = false;
+  const size_t link_smem_bytes = (size_t)kLinkSmemRows * 17;
+  if (!link_attr) {
+    B200_CUDA_OK(cudaFuncSetAttribute(linkage_centroid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)link_smem_bytes));
+    link_attr = true;
+  }
+  linkage_centroid_kernel<<<nfiles, 1024, link_smem_bytes, st>>>(djobs, D, Z, nn_d, nn_i, size, id, alive, todo);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }
