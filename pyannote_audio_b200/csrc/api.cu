@@ -15,6 +15,7 @@ struct b200_ctx {
   int device = 0;
   int num_sms = 148;
   int seg_gemm_impl = 1;   // 1 = split-fp16 tcgen05 GEMMs for the LSTM input projections / linear layers, 0 = fp32 SIMT
+  int seg_conv_impl = 1;   // 1 = SincNet Conv1d(k=5) layers on tcgen05 (split fp16), 0 = fp32 CUDA-core kernel
   int seg_rec_impl = 1;    // 1 = LSTM recurrence on the tensor cores (needs seg_gemm_impl = 1), 0 = fp32 SIMT cluster kernel
   int conv_fuse = 1;       // 1 = layer1 BasicBlocks as one fused kernel (conv_block32_kernel) when conv_impl == 8
   int conv_impl = 8;   // channels-as-M conv for C_out >= 128, strip-streaming conv for the narrow stride-1 3x3, per-tap conv otherwise
@@ -235,6 +236,7 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value) {
   else if (k == "profile") ctx->profile = (int)value;
   else if (k == "seg_gemm_impl") ctx->seg_gemm_impl = (int)value;
   else if (k == "seg_rec_impl") ctx->seg_rec_impl = (int)value;
+  else if (k == "seg_conv_impl") ctx->seg_conv_impl = (int)value;
   else if (k == "conv_fuse") ctx->conv_fuse = (int)value;
   else B200_CHECK(false, B200_ERR_INVALID, "unknown option '%s'", key);
   B200_CHECK(ctx->seg_max_batch >= 1 && ctx->emb_max_batch >= 1 && ctx->conv_impl >= 0 && ctx->conv_impl <= 8,
@@ -315,6 +317,20 @@ int b200_seg_load(b200_ctx* ctx, const b200_seg_weights* w) {
         for (int k = 0; k < 5; ++k) wc[((size_t)ci * 5 + k) * 60 + co] = w->conv_weight[i][((size_t)co * cin[i] + ci) * 5 + k];
     if ((rc = upload(ctx, wc, &S.conv_w[i]))) return rc;
     if ((rc = upload(ctx, bc, &S.conv_b[i]))) return rc;
+    {   // tensor-core layout: [channel block of 16][tap][128 rows = c_out (60 real)][16 c_in] as fp16 (hi, lo)
+      const int ncb = (cin[i] + 15) / 16;
+      std::vector<__half> hi((size_t)ncb * 5 * 128 * 16, __float2half(0.f)), lo(hi.size(), __float2half(0.f));
+      for (int co = 0; co < 60; ++co)
+        for (int ci = 0; ci < cin[i]; ++ci)
+          for (int k = 0; k < 5; ++k) {
+            const float v = w->conv_weight[i][((size_t)co * cin[i] + ci) * 5 + k];
+            const size_t o = ((((size_t)(ci / 16) * 5 + k) * 128) + co) * 16 + (ci % 16);
+            hi[o] = __float2half(v);
+            lo[o] = __float2half(v - __half2float(hi[o]));
+          }
+      if ((rc = upload(ctx, hi, &S.conv_tc_hi[i]))) return rc;
+      if ((rc = upload(ctx, lo, &S.conv_tc_lo[i]))) return rc;
+    }
   }
   for (int l = 0; l < S.lstm_layers; ++l) {
     const int I = l == 0 ? 60 : 256, Kp = l == 0 ? 64 : 256;
@@ -465,7 +481,9 @@ static int seg_run(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, co
     ScopedTimer timer(ctx, &ctx->seg_events, st);
     if (ctx->profile) ctx->seg_chunks += nb;
     float* x0_dst = sinc_out ? sinc_out + (size_t)c0 * kFrames * 64 : x0;
-    if ((rc = sincnet_forward(ctx->seg, wav, ctx->d_off + c0, ctx->d_valid + c0, nb, region, x0_dst, st))) return rc;
+    if ((rc = sincnet_forward(ctx->seg, wav, ctx->d_off + c0, ctx->d_valid + c0, nb, region, x0_dst, ctx->seg_conv_impl,
+                              ctx->num_sms, st)))
+      return rc;
     ctx->launches += 8;
     if (sinc_out) continue;
     if ((rc = lstm_head_forward(ctx->seg, x0, nb, region, classes + (size_t)c0 * kFrames,

@@ -13,6 +13,8 @@ struct SegWeights {
   float* in_beta[3] = {nullptr, nullptr, nullptr};
   float* conv_w[2] = {nullptr, nullptr};   // [CIN][5][60]
   float* conv_b[2] = {nullptr, nullptr};   // [60]
+  __half* conv_tc_hi[2] = {nullptr, nullptr};   // [ncb * 5 taps][128 rows = c_out (60 real)][16 c_in] fp16 hi
+  __half* conv_tc_lo[2] = {nullptr, nullptr};   //                                                              lo
   // LSTM, per layer: W_ih for both directions [1024][Kpad] with row = dir*512 + unit*4 + gate; bias = b_ih+b_hh
   float* w_ih[8] = {};
   float* b_g[8] = {};
@@ -45,10 +47,17 @@ int gemm_tc_split_gx(const __half* A_hi, const __half* A_lo, int lda, const __ha
 int lstm_rec_tc(const float* G, const __half* Whh_hi, const __half* Whh_lo, __half* Yh, __half* Yl, int NB,
                 cudaStream_t stream);
 
+// tensor-core Conv1d(k=5)+MaxPool(3) (seg_conv_tc.cu)
+int in_apply_split(const float* P, const float2* affine, int NB, int C, int Cpad, int L, __half* Xh, __half* Xl,
+                   cudaStream_t stream);
+int conv5_tc_forward(const __half* Xh, const __half* Xl, const __half* Wh, const __half* Wl, const float* bias, int NB,
+                     int L_in, int L_pool, int ncb, float* Pout, double2* part, int ntiles_part, int num_sms,
+                     cudaStream_t stream);
+
 // SincNet front-end on NB chunks: wav + per-chunk (offset, valid) -> X0 [NB][589][64] fp32 (60 features + 4 zero pad)
 size_t sincnet_workspace_bytes(int NB);
 int sincnet_forward(const SegWeights& W, const float* wav, const long long* chunk_off, const int* chunk_valid, int NB,
-                    void* ws, float* x0, cudaStream_t stream);
+                    void* ws, float* x0, int conv_impl, int num_sms, cudaStream_t stream);
 
 // BiLSTM stack + linear head: X0 -> class ids [NB][589] u8 (+ optional log-probs [NB][589][7])
 size_t lstm_workspace_bytes(int NB);

@@ -106,6 +106,15 @@ def test_segmentation_parity(ctx, dev, oracle_models):
     np.testing.assert_allclose(logp0.cpu().numpy(), ref_logp, atol=2e-4, rtol=0)
     assert float((logp0 - logp).abs().max()) < 1e-4
     assert float((cls0 != cls).float().mean()) < 1e-3
+    # tensor-core SincNet conv layers (default) against the fp32 CUDA-core kernels
+    ctx.set_option("seg_conv_impl", 0)
+    sinc0 = ctx.sincnet_forward(buf, off, valid).cpu().numpy()
+    cls2, logp2 = ctx.seg_forward(buf, off, valid, return_logp=True)
+    ctx.set_option("seg_conv_impl", 1)
+    np.testing.assert_allclose(sinc0, ref_sinc, atol=2e-4, rtol=0)
+    np.testing.assert_allclose(sinc0, sinc, atol=1e-4, rtol=0)
+    assert float((logp2 - logp).abs().max()) < 2e-4
+    assert float((cls2 != cls).float().mean()) < 1e-3
     # tensor-core LSTM recurrence (default) against the fp32 CUDA-core cluster kernel
     ctx.set_option("seg_rec_impl", 0)
     cls1, logp1 = ctx.seg_forward(buf, off, valid, return_logp=True)
