@@ -247,14 +247,16 @@ static int make_map_3d(CUtensorMap* tm, const __half* ptr, int NB, int T, int K,
 
 static int launch_gemm(GemmTcParams& p, const CUtensorMap& tmAh, const CUtensorMap& tmAl, const __half* B_hi,
                        const __half* B_lo, int ldb, int num_sms, cudaStream_t stream) {
-  p.Nt = 128;
+  // N = 256 per MMA runs at the full tensor rate (N = 128 at half of it: the A operand read bounds the instruction);
+  // its 96 KB stages leave room for two instead of three
+  p.Nt = (p.N % 256 == 0) ? 256 : 128;
   p.kblocks = p.K / kGemmK;
   p.tiles_n = p.N / p.Nt;
   p.num_tiles = p.tiles_m * p.tiles_n;
   p.a_bytes = kGemmM * kGemmK * 2;
   p.b_bytes = p.Nt * kGemmK * 2;
-  p.stage_bytes = 2 * p.a_bytes + 2 * p.b_bytes;          // 64 KB
-  p.nstages = 3;
+  p.stage_bytes = 2 * p.a_bytes + 2 * p.b_bytes;          // 64 KB (Nt = 128) or 96 KB (Nt = 256)
+  p.nstages = p.Nt == 256 ? 2 : 3;
   p.idesc = (1u << 4) | ((uint32_t)(p.Nt >> 3) << 17) | ((uint32_t)(kGemmM >> 4) << 24);
   CUtensorMap tmBh, tmBl;
   int rc;

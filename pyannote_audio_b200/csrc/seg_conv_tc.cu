@@ -44,14 +44,26 @@ __global__ void __launch_bounds__(256) in_apply_split_kernel(const float* __rest
     tile[c][l] = v;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 64 * Cpad; i += 256) {
-    const int l = i / Cpad, c = i - l * Cpad;
+  // 8 channels per thread: one 16-byte store each for hi and lo, consecutive threads -> consecutive chunks
+  const int groups = Cpad / 8;
+  for (int i = threadIdx.x; i < 64 * groups; i += 256) {
+    const int l = i / groups, c0 = (i - l * groups) * 8;
     if (l0 + l >= L) continue;
-    const float v = c < C ? tile[c][l] : 0.f;
-    const __half h = __float2half_rn(v);
-    const size_t o = ((size_t)b * L + l0 + l) * Cpad + c;
-    Xh[o] = h;
-    Xl[o] = __float2half_rn(v - __half2float(h));
+    uint4 uh, ul;
+    __half2* ph = reinterpret_cast<__half2*>(&uh);
+    __half2* pl = reinterpret_cast<__half2*>(&ul);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float v0 = c0 + 2 * e < C ? tile[c0 + 2 * e][l] : 0.f;
+      const float v1 = c0 + 2 * e + 1 < C ? tile[c0 + 2 * e + 1][l] : 0.f;
+      const __half2 h = __floats2half2_rn(v0, v1);
+      const float2 hb = __half22float2(h);
+      ph[e] = h;
+      pl[e] = __floats2half2_rn(v0 - hb.x, v1 - hb.y);
+    }
+    const size_t o = ((size_t)b * L + l0 + l) * Cpad + c0;
+    *reinterpret_cast<uint4*>(Xh + o) = uh;
+    *reinterpret_cast<uint4*>(Xl + o) = ul;
   }
 }
 
