@@ -21,6 +21,33 @@ constexpr float kEps = 1.1920928955078125e-07f;
 
 __device__ __forceinline__ int bitrev9(int x) { return __brev((unsigned)x) >> 23; }
 
+// smem index with one pad word per 16 elements: the register-blocked FFT passes below read 16 consecutive or
+// 16-strided elements per lane, both conflict-free with this padding
+__device__ __forceinline__ int fpad(int i) { return i + (i >> 4); }
+constexpr int kFftPad = kFft + kFft / 16;   // 544
+
+// 4 radix-2 DIT stages on 16 values held in registers; tw(s, j) returns the twiddle of the butterfly whose upper
+// input is local element j in local stage s
+template <typename TW>
+__device__ __forceinline__ void fft16_stages(float (&xr)[16], float (&xi)[16], TW tw) {
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int half = 1 << s;
+#pragma unroll
+    for (int bf = 0; bf < 8; ++bf) {
+      const int pos = bf & (half - 1);
+      const int j0 = ((bf >> s) << (s + 1)) + pos, j1 = j0 + half;
+      float wr, wi;
+      tw(s, pos, wr, wi);
+      const float tr = wr * xr[j1] - wi * xi[j1];
+      const float ti = wr * xi[j1] + wi * xr[j1];
+      const float ur = xr[j0], ui = xi[j0];
+      xr[j0] = ur + tr; xi[j0] = ui + ti;
+      xr[j1] = ur - tr; xi[j1] = ui - ti;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wav,
                                                     const long long* __restrict__ chunk_off,
                                                     const int* __restrict__ chunk_valid,
@@ -28,8 +55,8 @@ __global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wa
                                                     const float* __restrict__ twiddle, const float* __restrict__ mel_w,
                                                     const int* __restrict__ mel_start, const int* __restrict__ mel_len,
                                                     const int* __restrict__ mel_off, float* __restrict__ out) {
-  __shared__ float s_re[8][kFft];
-  __shared__ float s_im[8][kFft];
+  __shared__ float s_re[8][kFftPad];
+  __shared__ float s_im[8][kFftPad];
   __shared__ float s_tw[256][2];
   for (int i = threadIdx.x; i < 512; i += blockDim.x) (&s_tw[0][0])[i] = twiddle[i];
   __syncthreads();
@@ -63,7 +90,7 @@ __global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wa
 #pragma unroll
   for (int j = 0; j < 13; ++j) {
     const int i = lane + 32 * j;
-    if (i < kFrameLen) im[i] = x[j] - mean;      // stage DC-removed samples in im[]
+    if (i < kFrameLen) im[fpad(i)] = x[j] - mean;      // stage DC-removed samples in im[]
   }
   __syncwarp();
   // pre-emphasis + window, scatter to bit-reversed order in re[]
@@ -72,42 +99,53 @@ __global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wa
     const int i = lane + 32 * j;
     float v = 0.f;
     if (i < kFrameLen) {
-      const float cur = im[i];
-      const float prev = im[i > 0 ? i - 1 : 0];
+      const float cur = im[fpad(i)];
+      const float prev = im[fpad(i > 0 ? i - 1 : 0)];
       v = (cur - 0.97f * prev) * window[i];
     }
-    re[bitrev9(i)] = v;
+    re[fpad(bitrev9(i))] = v;
   }
   __syncwarp();
+  // 512-point radix-2 DIT FFT as 4 + 4 + 1 stages: two register-blocked passes of 16 values per lane, then the last
+  // stage.  (One shared-memory round trip per pass instead of one per stage.)
+  float xr[16], xi[16];
+  {  // stages 0-3: lane owns elements 16 lane .. 16 lane + 15; imaginary input is zero; twiddles are constants
 #pragma unroll
-  for (int j = 0; j < 16; ++j) im[lane + 32 * j] = 0.f;
-  __syncwarp();
-  // radix-2 DIT FFT, 9 stages, 256 butterflies each
-  for (int s = 0; s < 9; ++s) {
-    const int half = 1 << s;
-    const int tstep = 256 >> s;
+    for (int j = 0; j < 16; ++j) { xr[j] = re[fpad(16 * lane + j)]; xi[j] = 0.f; }
+    fft16_stages(xr, xi, [&](int s, int pos, float& wr, float& wi) {
+      const int k = pos * (256 >> s);                      // multiples of 32: compile-time after unrolling
+      wr = s_tw[k][0];
+      wi = s_tw[k][1];
+    });
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int bf = lane + 32 * j;
-      const int pos = bf & (half - 1);
-      const int i0 = ((bf >> s) << (s + 1)) + pos;
-      const int i1 = i0 + half;
-      const float wr = s_tw[pos * tstep][0], wi = s_tw[pos * tstep][1];
-      const float xr = re[i1], xi = im[i1];
-      const float tr = wr * xr - wi * xi;
-      const float ti = wr * xi + wi * xr;
-      const float ur = re[i0], ui = im[i0];
-      re[i0] = ur + tr; im[i0] = ui + ti;
-      re[i1] = ur - tr; im[i1] = ui - ti;
-    }
-    __syncwarp();
+    for (int j = 0; j < 16; ++j) { re[fpad(16 * lane + j)] = xr[j]; im[fpad(16 * lane + j)] = xi[j]; }
   }
-  // power spectrum, bins 0..255 (the Nyquist bin carries zero mel weight: kaldi pads the bank with a zero column)
+  __syncwarp();
+  {  // stages 4-7: lane owns elements e0 + 16 j, e0 = (lane & 15) + 256 (lane >> 4)
+    const int e0 = (lane & 15) + ((lane >> 4) << 8);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { xr[j] = re[fpad(e0 + 16 * j)]; xi[j] = im[fpad(e0 + 16 * j)]; }
+    fft16_stages(xr, xi, [&](int s, int pos, float& wr, float& wi) {
+      // global stage 4 + s, position inside the butterfly group = (lane & 15) + 16 pos
+      const int k = ((lane & 15) + 16 * pos) * (16 >> s);
+      wr = s_tw[k][0];
+      wi = s_tw[k][1];
+    });
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { re[fpad(e0 + 16 * j)] = xr[j]; im[fpad(e0 + 16 * j)] = xi[j]; }
+  }
+  __syncwarp();
+  // stage 8 fused with the power spectrum of bins 0..255 (only the upper output of each butterfly is needed; the
+  // Nyquist bin carries zero mel weight: kaldi pads the bank with a zero column)
   float pw[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int k = lane + 32 * j;
-    const float a = sqrtf(re[k] * re[k] + im[k] * im[k]);   // reference: rfft().abs().pow(2)
+    const float wr = s_tw[k][0], wi = s_tw[k][1];
+    const float br = re[fpad(k + 256)], bi = im[fpad(k + 256)];
+    const float tr = wr * br - wi * bi, ti = wr * bi + wi * br;
+    const float zr = re[fpad(k)] + tr, zi = im[fpad(k)] + ti;
+    const float a = sqrtf(zr * zr + zi * zi);               // reference: rfft().abs().pow(2)
     pw[j] = a * a;
   }
   __syncwarp();
