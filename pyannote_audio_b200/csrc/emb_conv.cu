@@ -1295,11 +1295,11 @@ constexpr int kC1Tile = 128;
 __global__ void __launch_bounds__(kC1Tile) conv1_kernel(const float* __restrict__ fbank, const float* __restrict__ fmean,
                              const float* __restrict__ w /*[32][9] folded*/, const float* __restrict__ bias /*[32]*/,
                              __half* __restrict__ out, int B) {
-  __shared__ float sw[32 * 9];
-  __shared__ float sb[32];
+  __shared__ __align__(16) float sw[9 * 32];               // [tap][channel]: one LDS.128 = 4 channels of a tap
+  __shared__ __align__(16) float sb[32];
   __shared__ float sx[(kC1Tile + 2) * (kMel + 1)];        // [t][f], +1 padding against bank conflicts
   const int b = blockIdx.y, t0 = blockIdx.x * kC1Tile;
-  for (int i = threadIdx.x; i < 288; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < 288; i += blockDim.x) sw[(i % 9) * 32 + i / 9] = w[i];
   if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
   for (int i = threadIdx.x; i < (kC1Tile + 2) * kMel; i += blockDim.x) {
     const int tt = i / kMel, f = i - tt * kMel;
@@ -1321,16 +1321,29 @@ __global__ void __launch_bounds__(kC1Tile) conv1_kernel(const float* __restrict_
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) x[kh * 3 + kw] = ok ? col[kw * (kMel + 1) + hh] : 0.f;
     }
+    // channel pairs on packed FFMA2, weights as 16-byte broadcast loads (the scalar version was LDS-bound: one
+    // shared-memory load per FMA); same fma order per channel, so the result is bit-identical
+    f32x2_t acc2[16];
+    const ulonglong2* sb2 = reinterpret_cast<const ulonglong2*>(sb);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { const ulonglong2 bb = sb2[q]; acc2[2 * q] = bb.x; acc2[2 * q + 1] = bb.y; }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const f32x2_t xk = pack2(x[k], x[k]);
+      const ulonglong2* wk = reinterpret_cast<const ulonglong2*>(sw + k * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const ulonglong2 w4 = wk[q];
+        ffma2(acc2[2 * q], xk, w4.x);
+        ffma2(acc2[2 * q + 1], xk, w4.y);
+      }
+    }
     __half2 o[16];
 #pragma unroll
-    for (int c = 0; c < 32; c += 2) {
-      float a0 = sb[c], a1 = sb[c + 1];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        a0 = fmaf(x[k], sw[c * 9 + k], a0);
-        a1 = fmaf(x[k], sw[(c + 1) * 9 + k], a1);
-      }
-      o[c / 2] = __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+    for (int c = 0; c < 16; ++c) {
+      float a0, a1;
+      unpack2(acc2[c], a0, a1);
+      o[c] = __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
     }
     uint4* op = reinterpret_cast<uint4*>(out + (((size_t)b * kMel + h) * kFbankFrames + t) * 32);
     const uint4* src = reinterpret_cast<const uint4*>(o);

@@ -160,12 +160,20 @@ __global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wa
   }
 }
 
-__global__ void fbank_mean_kernel(const float* __restrict__ fb, float* __restrict__ fmean) {
-  const int b = blockIdx.x, m = threadIdx.x;
-  if (m >= kMel) return;
+__global__ void __launch_bounds__(640) fbank_mean_kernel(const float* __restrict__ fb, float* __restrict__ fmean) {
+  // 8 groups of 80 threads each sum an eighth of the frames in fp64, combined in group order
+  __shared__ double part[8][kMel];
+  const int b = blockIdx.x, m = threadIdx.x % kMel, g = threadIdx.x / kMel;
   double s = 0.0;
-  for (int t = 0; t < kFbankFrames; ++t) s += (double)fb[((size_t)b * kFbankFrames + t) * kMel + m];
-  fmean[b * kMel + m] = (float)(s / kFbankFrames);
+  for (int t = g; t < kFbankFrames; t += 8) s += (double)fb[((size_t)b * kFbankFrames + t) * kMel + m];
+  part[g][m] = s;
+  __syncthreads();
+  if (g == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += part[k][m];
+    fmean[b * kMel + m] = (float)(tot / kFbankFrames);
+  }
 }
 
 __global__ void fbank_center_kernel(float* __restrict__ fb, const float* __restrict__ fmean, size_t total) {
@@ -206,7 +214,7 @@ int fbank_forward(const EmbWeights& W, const float* wav, const long long* chunk_
   fbank_kernel<<<grid, 256, 0, stream>>>(wav, chunk_off, chunk_valid, W.window, W.twiddle, W.mel_w, W.mel_start,
                                          W.mel_len, W.mel_off, fbank);
   B200_CUDA_OK(cudaGetLastError());
-  fbank_mean_kernel<<<B, 96, 0, stream>>>(fbank, fmean);
+  fbank_mean_kernel<<<B, 640, 0, stream>>>(fbank, fmean);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }
