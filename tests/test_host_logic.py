@@ -175,3 +175,31 @@ def test_oracle_not_imported_by_product():
     for f in root.rglob("*.py"):
         src = f.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+
+
+def test_annotation_integer_labels_relabel_like_object_labels():
+    """Bulk annotations keep integer labels (one table lookup to relabel); same result as the object-label path."""
+    from pyannote_audio_b200.core import Annotation
+    rng = np.random.default_rng(3)
+    n = 500
+    starts = np.sort(rng.uniform(0, 100, n))
+    ends = starts + rng.uniform(0.1, 2.0, n)
+    lab = rng.integers(0, 7, n)
+    a_int = Annotation.from_rows(starts, ends, lab, uri="u")
+    a_obj = Annotation.from_rows(starts, ends, [int(v) for v in lab], uri="u")
+    assert a_int.labels() == a_obj.labels() == sorted(set(lab.tolist()))
+    mapping = {k: f"SPEAKER_{i:02d}" for i, k in enumerate(a_int.labels())}
+    r_int, r_obj = a_int.rename_labels(mapping), a_int.rename_labels(mapping)
+    got = [(s.start, s.end, l) for s, _, l in r_int.itertracks(yield_label=True)]
+    ref = [(s.start, s.end, mapping[int(l)]) for s, _, l in a_obj.itertracks(yield_label=True)]
+    assert got == ref and r_int.labels() == sorted(mapping.values())
+    assert len(r_obj) == n and r_int.to_rttm().count("SPEAKER u 1") == n
+
+
+def test_sparse_true_matches_flatnonzero():
+    from pyannote_audio_b200.pipeline import _sparse_true
+    rng = np.random.default_rng(4)
+    for _ in range(50):
+        x = rng.uniform(size=(int(rng.integers(1, 6)), int(rng.integers(1, 400)))) < rng.uniform(0, 0.3)
+        assert np.array_equal(_sparse_true(x), np.flatnonzero(x))
+    assert _sparse_true(np.zeros((3, 17), dtype=bool)).size == 0
