@@ -300,6 +300,18 @@ int b200_seg_load(b200_ctx* ctx, const b200_seg_weights* w) {
       f[125 * 80 + ch] = ch < 40 ? r[125] : 0.f;
     }
     if ((rc = upload(ctx, f, &S.sinc_f))) return rc;
+    {   // tensor-core layout of the full bank: [k-step][128 rows][16 taps] as fp16 (hi, lo), taps 251..255 zero
+      std::vector<__half> hi((size_t)16 * 128 * 16, __float2half(0.f)), lo(hi.size(), __float2half(0.f));
+      for (int ch = 0; ch < 80; ++ch)
+        for (int k = 0; k < 251; ++k) {
+          const float v = w->sinc_filters[ch * 251 + k];
+          const size_t o = ((size_t)(k / 16) * 128 + ch) * 16 + (k % 16);
+          hi[o] = __float2half(v);
+          lo[o] = __float2half(v - __half2float(hi[o]));
+        }
+      if ((rc = upload(ctx, hi, &S.sinc_tc_hi))) return rc;
+      if ((rc = upload(ctx, lo, &S.sinc_tc_lo))) return rc;
+    }
   }
   const int nch[3] = {80, 60, 60};
   for (int i = 0; i < 3; ++i) {

@@ -8,6 +8,8 @@ struct SegWeights {
   bool loaded = false;
   int lstm_layers = 4;
   float wav_w = 1.f, wav_b = 0.f;   // sincnet.wav_norm1d affine
+  __half* sinc_tc_hi = nullptr;     // [16 k-steps][128 rows (80 filters)][16 taps] fp16 hi for sinc_tc_kernel
+  __half* sinc_tc_lo = nullptr;
   float* sinc_f = nullptr;          // [126][80]: half filters (k=0..124) + centre tap (k=125); cos ch 0..39, sin 40..79
   float* in_gamma[3] = {nullptr, nullptr, nullptr};   // sincnet.norm1d.{0,1,2}.weight
   float* in_beta[3] = {nullptr, nullptr, nullptr};
@@ -53,6 +55,10 @@ int in_apply_split(const float* P, const float2* affine, int NB, int C, int Cpad
 int conv5_tc_forward(const __half* Xh, const __half* Xl, const __half* Wh, const __half* Wl, const float* bias, int NB,
                      int L_in, int L_pool, int ncb, float* Pout, double2* part, int ntiles_part, int num_sms,
                      cudaStream_t stream);
+
+int sinc_tc_forward(const float* wav, const long long* chunk_off, const int* chunk_valid, const float2* affine,
+                    const __half* Ah, const __half* Al, int NB, float* P0, double2* part, int ntiles_part, int num_sms,
+                    cudaStream_t stream);
 
 // SincNet front-end on NB chunks: wav + per-chunk (offset, valid) -> X0 [NB][589][64] fp32 (60 features + 4 zero pad)
 size_t sincnet_workspace_bytes(int NB);

@@ -169,7 +169,8 @@ conv5_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
       if (q < 2) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
         const float bias = s_bias[co & 63];
-        float* orow = p.Pout + ((size_t)b * 60 + (co < 60 ? co : 0)) * p.L_pool;
+        float* s_o = reinterpret_cast<float*>(gbase + 1024 + (size_t)kC5Stages * kC5Stage);   // [64][33]
+        const int nrows = q == 0 ? 32 : 28;                 // channels 32..59 in the second warp
         double s = 0.0, ss = 0.0;
         for (int batch = 0; batch < 3; ++batch) {           // 96 + 96 + 48 columns -> 32 + 32 + 16 pooled values
           uint32_t r[96];
@@ -177,19 +178,27 @@ conv5_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
           tc_ld32(taddr + batch * 96 + 32, r + 32);          // (last batch: columns 240..255 are never written, unused)
           if (batch < 2) tc_ld32(taddr + batch * 96 + 64, r + 64);
           const int npool = batch < 2 ? 32 : 16;
+          const int p0 = tile * kC5Pooled + batch * 32;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             if (i < npool) {
               const float v = fmaxf(fmaxf(__uint_as_float(r[3 * i]), __uint_as_float(r[3 * i + 1])),
                                     __uint_as_float(r[3 * i + 2])) + bias;
-              const int pidx = tile * kC5Pooled + batch * 32 + i;
-              if (co < 60 && pidx < p.L_pool) {
-                orow[pidx] = v;
-                s += v;
-                ss += (double)v * v;
+              if (co < 60) {
+                s_o[co * 33 + i] = v;
+                if (p0 + i < p.L_pool) { s += v; ss += (double)v * v; }
               }
             }
           }
+          __syncwarp();
+          // transposed store: one channel row per instruction, lanes along the positions (coalesced)
+          if (lane < npool && p0 + lane < p.L_pool) {
+            for (int j = 0; j < nrows; ++j) {
+              const int cr = q * 32 + j;
+              p.Pout[((size_t)b * 60 + cr) * p.L_pool + p0 + lane] = s_o[cr * 33 + lane];
+            }
+          }
+          __syncwarp();
         }
         if (co < 60) p.part[((size_t)b * 60 + co) * p.ntiles_part + tile] = make_double2(s, ss);
       }
@@ -246,7 +255,7 @@ int conv5_tc_forward(const __half* Xh, const __half* Xl, const __half* Wh, const
   if ((rc = make_map3(&tmXl, Xl, Cpad, L_in, NB, 16, kC5Rows))) return rc;
   if ((rc = make_map3(&tmWh, Wh, 16, 128, (uint64_t)ncb * 5, 16, 128))) return rc;
   if ((rc = make_map3(&tmWl, Wl, 16, 128, (uint64_t)ncb * 5, 16, 128))) return rc;
-  const size_t smem = 1024 + 1024 + (size_t)kC5Stages * kC5Stage;
+  const size_t smem = 1024 + 1024 + (size_t)kC5Stages * kC5Stage + 64 * 33 * 4;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA_OK(cudaFuncSetAttribute(conv5_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -342,10 +342,19 @@ int sincnet_forward(const SegWeights& W, const float* wav, const long long* chun
     attr = true;
   }
   wav_stats_kernel<<<NB, 512, 0, stream>>>(wav, chunk_off, chunk_valid, W.wav_w, W.wav_b, w.af_wav);
-  sinc_pool_kernel<<<dim3(kTiles0, NB), 128, smem_sinc, stream>>>(wav, chunk_off, chunk_valid, w.af_wav, W.sinc_f,
-                                                                 w.P0, w.part0);
-  in_finalize_kernel<<<ceil_div(NB * 80, 128), 128, 0, stream>>>(w.part0, kTiles0, kPool0, 80, W.in_gamma[0],
-                                                                 W.in_beta[0], w.af0, NB * 80);
+  if (conv_impl == 1) {
+    const int nt0 = ceil_div(kPool0, 80);
+    const int rc0 = sinc_tc_forward(wav, chunk_off, chunk_valid, w.af_wav, W.sinc_tc_hi, W.sinc_tc_lo, NB, w.P0, w.part0,
+                                    nt0, num_sms, stream);
+    if (rc0) return rc0;
+    in_finalize_kernel<<<ceil_div(NB * 80, 128), 128, 0, stream>>>(w.part0, nt0, kPool0, 80, W.in_gamma[0],
+                                                                   W.in_beta[0], w.af0, NB * 80);
+  } else {
+    sinc_pool_kernel<<<dim3(kTiles0, NB), 128, smem_sinc, stream>>>(wav, chunk_off, chunk_valid, w.af_wav, W.sinc_f,
+                                                                   w.P0, w.part0);
+    in_finalize_kernel<<<ceil_div(NB * 80, 128), 128, 0, stream>>>(w.part0, kTiles0, kPool0, 80, W.in_gamma[0],
+                                                                   W.in_beta[0], w.af0, NB * 80);
+  }
   if (conv_impl == 1) {
     // tensor-core path: IN + leaky-relu + split to channels-last fp16 (hi, lo), then the implicit GEMM
     int rc;
