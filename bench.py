@@ -251,7 +251,7 @@ def main():
                          f"synthetic file end-to-end ({t:.1f} s wall)"}
     line = {"metric": METRIC, "value": value, "unit": "audio-hours/sec", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.min_warmup, args.warmup), "ms_per_step": ms_resident, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16 tensor-core trunk (f32 accumulate) + f32 segmentation + f64 clustering",
+            "vs_baseline": None, "dtype": "f16 tensor-core trunk (f32 accumulate) + split-f16x3 tensor-core segmentation (f32-level accuracy) + f64 clustering",
             "data": "synthetic",
             "config": {"workload": f"community-1 diarization pipeline end-to-end, {nfiles} x {args.minutes:g} min "
                                    f"synthetic 16 kHz mono files per GPU (BASELINE.json configs[4] scaled per GPU)",
