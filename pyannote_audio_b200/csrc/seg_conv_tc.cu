@@ -179,6 +179,7 @@ conv5_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
           if (batch < 2) tc_ld32(taddr + batch * 96 + 64, r + 64);
           const int npool = batch < 2 ? 32 : 16;
           const int p0 = tile * kC5Pooled + batch * 32;
+          float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             if (i < npool) {
@@ -186,10 +187,13 @@ conv5_tc_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant_
                                     __uint_as_float(r[3 * i + 2])) + bias;
               if (co < 60) {
                 s_o[co * 33 + i] = v;
-                if (p0 + i < p.L_pool) { s += v; ss += (double)v * v; }
+                if (p0 + i < p.L_pool) { s4[i & 3] += v; q4[i & 3] = fmaf(v, v, q4[i & 3]); }
               }
             }
           }
+          // fp32 partial sums over <= 8 values each, folded into fp64 once per batch (no serial fp64 chain)
+          s += (double)((s4[0] + s4[1]) + (s4[2] + s4[3]));
+          ss += (double)((q4[0] + q4[1]) + (q4[2] + q4[3]));
           __syncwarp();
           // transposed store: one channel row per instruction, lanes along the positions (coalesced)
           if (lane < npool && p0 + lane < p.L_pool) {

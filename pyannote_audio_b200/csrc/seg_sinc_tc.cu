@@ -207,6 +207,7 @@ sinc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
           if (batch < 2) tc_ld32(taddr + batch * 96 + 64, r + 64);
           const int npool = batch < 2 ? 32 : 16;
           const int p0 = tile * kSTPool + batch * 32;
+          float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             if (i < npool) {
@@ -214,10 +215,14 @@ sinc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                                     fabsf(__uint_as_float(r[3 * i + 2])));
               if (f < 80) {
                 s_o[f * 33 + i] = v;
-                if (p0 + i < kPool0) { s += v; ss += (double)v * v; }
+                if (p0 + i < kPool0) { s4[i & 3] += v; q4[i & 3] = fmaf(v, v, q4[i & 3]); }
               }
             }
           }
+          // fp32 partial sums over <= 8 non-negative values each, folded into fp64 once per batch (a serial chain of
+          // 160 dependent fp64 adds per tile kept the epilogue warps -- the bottleneck of this kernel -- busy)
+          s += (double)((s4[0] + s4[1]) + (s4[2] + s4[3]));
+          ss += (double)((q4[0] + q4[1]) + (q4[2] + q4[3]));
           __syncwarp();
           // transposed store: one filter row per instruction, lanes along the positions (coalesced 128-byte rows
           // instead of 32 scattered 4-byte stores)
