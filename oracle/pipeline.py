@@ -236,11 +236,33 @@ def binarize_to_segments(discrete: SWF):
                 if y > 0.5:
                     start = t
                     active = True
-        if active:
+        if active and t > start:      # Segment(start, start) is empty: Annotation.__setitem__ ignores it
             rows.append((start, t, k))
     rows.sort(key=lambda r: (r[0], r[1], r[2]))
     times = [(discrete.sw.middle(a), discrete.sw.middle(b), k) for a, b, k in rows]
     return rows, times
+
+
+def support(times, collar=0.0):
+    """pyannote.core Annotation.support(collar) (called by Binarize when min_duration_off > 0, signal.py:307-310),
+    restated from the published behaviour (parity unpinned, like the rest of pyannote.core): per label in sorted
+    order, walk the label's segments by (start, end) and merge the next one into the current one when they touch /
+    overlap (gap <= 1e-6, an "empty" Segment) or the gap is strictly shorter than ``collar``.
+    ``times`` = [(start_s, end_s, label)]; returns the merged list in itertracks order (start, end, label)."""
+    out = []
+    for lab in sorted({k for _, _, k in times}):
+        segs = sorted((a, b) for a, b, k in times if k == lab)
+        cs, ce = segs[0]
+        for a, b in segs[1:]:
+            gap = a - ce
+            if gap <= 1e-6 or gap < collar:
+                ce = max(ce, b)
+            else:
+                out.append((cs, ce, lab))
+                cs, ce = a, b
+        out.append((cs, ce, lab))
+    out.sort(key=lambda r: (r[0], r[1], r[2]))
+    return out
 
 
 # ----------------------------------------------------------------------------------------
@@ -556,7 +578,8 @@ class OracleOutput:
 
 def apply(seg_model, emb_model, plda: PLDA, waveform: torch.Tensor, threshold=0.6, Fa=0.07, Fb=0.8,
           num_speakers=None, min_speakers=None, max_speakers=None, seg_batch=32, emb_batch=8,
-          share_trunk=True, segmentations: SWF = None, embeddings=None) -> OracleOutput:
+          share_trunk=True, segmentations: SWF = None, embeddings=None, exclude_overlap=False,
+          min_duration_off=0.0) -> OracleOutput:
     """SpeakerDiarization.apply (pipelines/speaker_diarization.py:530-784), powerset + VBx branch."""
     min_speakers = num_speakers or min_speakers or 1
     max_speakers = num_speakers or max_speakers or np.inf
@@ -572,7 +595,7 @@ def apply(seg_model, emb_model, plda: PLDA, waveform: torch.Tensor, threshold=0.
         out.speaker_embeddings = np.zeros((0, 256))
         return out
     emb = embeddings if embeddings is not None else get_embeddings(
-        emb_model, waveform, seg, batch_size=emb_batch, share_trunk=share_trunk)
+        emb_model, waveform, seg, exclude_overlap=exclude_overlap, batch_size=emb_batch, share_trunk=share_trunk)
     out.embeddings = emb
     hard, _, centroids = vbx_clustering(emb, seg.data, plda, threshold, Fa, Fb, num_clusters=num_speakers,
                                         min_clusters=min_speakers, max_clusters=max_speakers)
@@ -586,6 +609,8 @@ def apply(seg_model, emb_model, plda: PLDA, waveform: torch.Tensor, threshold=0.
     count.data = np.minimum(count.data, 1).astype(np.int8)
     out.exclusive = reconstruct(seg, hard, count)
     out.exclusive_segments, xtimes = binarize_to_segments(out.exclusive)
+    if min_duration_off > 0.0:
+        times, xtimes = support(times, min_duration_off), support(xtimes, min_duration_off)
     labels = sorted({k for _, _, k in out.segments})
     mapping = {k: f"SPEAKER_{i:02d}" for i, k in enumerate(labels)}
     out.labels = [mapping[k] for k in labels]

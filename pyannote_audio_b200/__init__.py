@@ -19,6 +19,10 @@ _LAZY = {
 
 
 def __getattr__(name):
+    if name == "synthetic":        # fixtures live in pyannote_audio_b200.testing; old import path kept as an alias
+        import importlib
+
+        return importlib.import_module(".testing.synthetic", __name__)
     if name in _LAZY:
         import importlib
 

@@ -39,6 +39,23 @@ class PLDA:
         self.lda_dimension = lda_dimension
         self._dev = {}
 
+    @classmethod
+    def from_pretrained(cls, checkpoint, subfolder: Optional[str] = None, revision: Optional[str] = None, token=None,
+                        cache_dir=None, **kwargs) -> "PLDA":
+        """core/plda.py:65-135 for local checkpoints: a directory holding ``xvec_transform.npz`` and ``plda.npz``
+        (optionally under ``subfolder``).  Hub identifiers cannot be downloaded here (no network)."""
+        import os
+
+        if not os.path.isdir(checkpoint):
+            if "@" in str(checkpoint):
+                raise ValueError("Revisions must be passed with `revision` keyword argument.")
+            raise ValueError(f"'{checkpoint}' is not a local directory; Hugging Face hub identifiers cannot be "
+                             f"downloaded here (no network)")
+        if revision is not None:
+            raise ValueError("Revisions cannot be used with local checkpoints.")
+        base = Path(checkpoint) / subfolder if subfolder else Path(checkpoint)
+        return cls(base / "xvec_transform.npz", base / "plda.npz", **kwargs)
+
     @property
     def phi(self) -> np.ndarray:
         return self._plda_psi[: self.lda_dimension]
@@ -216,7 +233,6 @@ class VBxClustering(BaseClustering):
         if not todo:
             return results
         # ---- AHC: one batched linkage launch, dendrogram cut on the host ------------------------------------
-        lro = np.array(row_off, copy=True)
         lro_n = np.where(np.isin(np.arange(F), todo), n_f, 0)           # problems not in `todo` get n = 0
         sub_off = np.concatenate([[0], np.cumsum(lro_n)]).astype(np.int32)
         if len(todo) == F and not any(skip):

@@ -59,6 +59,9 @@ class Specifications:
         yield self
 
 
+SEGMENT_PRECISION = 1e-6      # pyannote.core.segment.SEGMENT_PRECISION: shorter segments are "empty"
+
+
 @dataclass(frozen=True, order=True)
 class Segment:
     start: float = 0.0
@@ -76,7 +79,7 @@ class Segment:
         return Segment(max(self.start, other.start), min(self.end, other.end))
 
     def __bool__(self):
-        return (self.end - self.start) > 0.0
+        return (self.end - self.start) > SEGMENT_PRECISION
 
     def __iter__(self):
         yield self.start
@@ -198,6 +201,8 @@ class Annotation:
         self.add(segment, track, label)
 
     def add(self, segment: Segment, track, label):
+        if not segment:            # pyannote.core: "do not add empty track"
+            return
         self._materialise()
         self._tracks.append((segment, track, label))
         self._sorted = False
@@ -242,17 +247,19 @@ class Annotation:
         return out
 
     def support(self, collar: float = 0.0) -> "Annotation":
-        """Merge same-label segments separated by less than `collar` seconds."""
+        """Per label (sorted), merge segments that touch / overlap or whose gap is strictly shorter than `collar`
+        seconds (pyannote.core Timeline.support_iter: ``not gap or gap.duration < collar``)."""
         out = Annotation(uri=self.uri)
         by_label = {}
         for s, _, lab in self.itertracks(yield_label=True):
             by_label.setdefault(lab, []).append(s)
         n = 0
-        for lab, segs in by_label.items():
-            segs.sort()
+        for lab in sorted(by_label, key=lambda v: (str(type(v)), v)):
+            segs = sorted(by_label[lab])
             cur = segs[0]
             for s in segs[1:]:
-                if s.start - cur.end <= collar:      # gap < collar (or touching / overlapping) -> merge
+                gap = s.start - cur.end
+                if gap <= SEGMENT_PRECISION or gap < collar:
                     cur = Segment(cur.start, max(cur.end, s.end))
                 else:
                     out.add(cur, n, lab)

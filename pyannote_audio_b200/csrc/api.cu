@@ -24,7 +24,8 @@ struct b200_ctx {
   int64_t launches = 0;
   SegWeights seg;
   EmbWeights emb;
-  std::vector<void*> owned;     // device allocations holding weights
+  std::vector<void*> owned_seg, owned_emb;   // device allocations holding the weights of each network
+  std::vector<void*>* owned = &owned_seg;    // where upload() records allocations (set by the load entry points)
   void* ws = nullptr;
   size_t ws_cap = 0;
   long long* d_off = nullptr;
@@ -50,7 +51,7 @@ int upload(b200_ctx* ctx, const std::vector<T>& h, T** out) {
   void* p = nullptr;
   B200_CUDA_OK(cudaMalloc(&p, h.size() * sizeof(T) + 16));
   B200_CUDA_OK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
-  ctx->owned.push_back(p);
+  ctx->owned->push_back(p);
   *out = reinterpret_cast<T*>(p);
   return B200_OK;
 }
@@ -79,6 +80,14 @@ struct ScopedTimer {
     if (ctx->profile) { cudaEventRecord(b, st); sink->push_back({a, b}); }
   }
 };
+
+// a reload replaces the previous upload of the same network: free it (after the device drained) instead of leaking
+void release_weights(b200_ctx* ctx, std::vector<void*>* list) {
+  if (!list->empty()) cudaDeviceSynchronize();
+  for (void* p : *list) cudaFree(p);
+  list->clear();
+  ctx->owned = list;
+}
 
 int ensure_ws(b200_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->ws_cap) return B200_OK;
@@ -219,7 +228,8 @@ int b200_ctx_destroy(b200_ctx* ctx) {
   if (!ctx) return B200_OK;
   DeviceGuard g(ctx->device);
   cudaDeviceSynchronize();
-  for (void* p : ctx->owned) cudaFree(p);
+  for (void* p : ctx->owned_seg) cudaFree(p);
+  for (void* p : ctx->owned_emb) cudaFree(p);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->d_off) cudaFree(ctx->d_off);
   if (ctx->d_valid) cudaFree(ctx->d_valid);
@@ -278,6 +288,8 @@ int b200_seg_load(b200_ctx* ctx, const b200_seg_weights* w) {
   SegWeights& S = ctx->seg;
   B200_CHECK(w->lstm_layers >= 1 && w->lstm_layers <= 4, B200_ERR_INVALID, "lstm_layers=%d unsupported",
              (int)w->lstm_layers);
+  S.loaded = false;
+  release_weights(ctx, &ctx->owned_seg);
   S.lstm_layers = w->lstm_layers;
   S.wav_w = w->wav_norm_weight;
   S.wav_b = w->wav_norm_bias;
@@ -426,6 +438,8 @@ int b200_emb_load(b200_ctx* ctx, const b200_emb_weights* w) {
   DeviceGuard g(ctx->device);
   EmbWeights& E = ctx->emb;
   int rc;
+  E.loaded = false;
+  release_weights(ctx, &ctx->owned_emb);
   if ((rc = build_fbank_constants(ctx))) return rc;
   {
     const b200_conv_bn& s = w->stem;

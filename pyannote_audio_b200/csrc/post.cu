@@ -105,11 +105,50 @@ __global__ void __launch_bounds__(128) reconstruct_kernel(const unsigned char* _
   for (int k = 0; k < Kout; ++k) o[k] = (sel >> k) & 1u;
 }
 
+// Many-speaker recordings (33..127 clusters; hard clusters are int8 like the reference's constrained_argmax): same
+// arithmetic with the per-frame activation counters in (thread-local) memory instead of registers.  A chunk votes
+// once for a cluster however many of its local speakers map to it (max over 0/1 values); a selected cluster is
+// marked by the sentinel 0xFF (real activations are <= 11 covering chunks).
+constexpr int kMaxKGeneric = 127;
+
+__global__ void __launch_bounds__(128) reconstruct_generic_kernel(const unsigned char* __restrict__ seg,
+                                                                  const signed char* __restrict__ hard,
+                                                                  const int* __restrict__ sf, int C, int F, int Kout,
+                                                                  const unsigned char* __restrict__ count,
+                                                                  unsigned char* __restrict__ out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  unsigned char act[kMaxKGeneric + 1];
+  for (int k = 0; k < Kout; ++k) act[k] = 0;
+  for (int c = first_chunk(sf, C, f); c < C && sf[c] <= f; ++c) {
+    const unsigned char* p = seg + ((size_t)c * kFrames + (f - sf[c])) * 3;
+    const int h0 = hard[c * 3 + 0], h1 = hard[c * 3 + 1], h2 = hard[c * 3 + 2];
+    const bool v0 = p[0] && h0 >= 0 && h0 < Kout;
+    const bool v1 = p[1] && h1 >= 0 && h1 < Kout && !(v0 && h1 == h0);
+    const bool v2 = p[2] && h2 >= 0 && h2 < Kout && !(v0 && h2 == h0) && !(p[1] && h2 == h1);
+    if (v0) act[h0] += 1;
+    if (v1) act[h1] += 1;
+    if (v2) act[h2] += 1;
+  }
+  const int cnt = count[f];
+  for (int i = 0; i < cnt && i < Kout; ++i) {
+    int best = 0, bv = -1;
+    for (int k = 0; k < Kout; ++k)
+      if (act[k] != 0xFF && (int)act[k] > bv) { bv = act[k]; best = k; }   // ties -> lowest cluster index
+    act[best] = 0xFF;
+  }
+  unsigned char* o = out + (size_t)f * Kout;
+  for (int k = 0; k < Kout; ++k) o[k] = act[k] == 0xFF;
+}
+
 int reconstruct(const unsigned char* seg, const signed char* hard, const int* sf, int C, int F, int Kout,
                 const unsigned char* count, unsigned char* out, cudaStream_t stream) {
-  B200_CHECK(Kout >= 1 && Kout <= kMaxK, B200_ERR_INVALID, "reconstruct: %d clusters unsupported (max %d)", Kout, kMaxK);
+  B200_CHECK(Kout >= 1 && Kout <= kMaxKGeneric, B200_ERR_INVALID,
+             "reconstruct: %d clusters unsupported (1..%d: hard clusters are int8 as in the reference's "
+             "constrained_argmax; cap the speaker count with max_speakers)", Kout, kMaxKGeneric);
   const int grid = ceil_div(F, 128);
-  if (Kout <= 8) reconstruct_kernel<8><<<grid, 128, 0, stream>>>(seg, hard, sf, C, F, Kout, count, out);
+  if (Kout > kMaxK) reconstruct_generic_kernel<<<grid, 128, 0, stream>>>(seg, hard, sf, C, F, Kout, count, out);
+  else if (Kout <= 8) reconstruct_kernel<8><<<grid, 128, 0, stream>>>(seg, hard, sf, C, F, Kout, count, out);
   else if (Kout <= 16) reconstruct_kernel<16><<<grid, 128, 0, stream>>>(seg, hard, sf, C, F, Kout, count, out);
   else reconstruct_kernel<32><<<grid, 128, 0, stream>>>(seg, hard, sf, C, F, Kout, count, out);
   B200_CUDA_OK(cudaGetLastError());

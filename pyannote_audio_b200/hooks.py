@@ -1,18 +1,15 @@
 """Pipeline hooks (mirror of /root/reference/src/pyannote/audio/pipelines/utils/hook.py:37-239).
 
 ``hook(step_name, step_artifact, file=..., total=..., completed=...)`` is called by ``SpeakerDiarization`` with the
-step names "segmentation", "speaker_counting", "embeddings", "discrete_diarization".  Artifacts arrive as lazy
-proxies (materialised -- i.e. copied device->host -- only when a hook touches them).
+step names "segmentation", "speaker_counting", "embeddings", "discrete_diarization", with real
+SlidingWindowFeature / ndarray artifacts (copied device -> host only when a hook is installed) and the reference's
+progress calls (artifact None, total / completed set).
 """
 from __future__ import annotations
 
 import time
 from copy import deepcopy
 from typing import Any, Mapping, Optional, Text
-
-
-def _materialise(artifact):
-    return artifact.get() if hasattr(artifact, "get") and callable(artifact.get) else artifact
 
 
 class ArtifactHook:
@@ -32,7 +29,7 @@ class ArtifactHook:
                  total: Optional[int] = None, completed: Optional[int] = None):
         if (step_artifact is None) or (self.artifacts and step_name not in self.artifacts):
             return
-        file.setdefault(self.file_key, dict())[step_name] = deepcopy(_materialise(step_artifact))
+        file.setdefault(self.file_key, dict())[step_name] = deepcopy(step_artifact)
 
 
 class TimingHook:

@@ -8,6 +8,7 @@ Reference interfaces mirrored (paths relative to /root/reference/src/pyannote/au
 """
 from __future__ import annotations
 
+import itertools
 from functools import cached_property
 from typing import Dict, Optional
 
@@ -20,6 +21,7 @@ from .audio import Audio
 from .core import Problem, Resolution, SlidingWindow, Specifications
 
 _CONTEXTS: Dict[int, "ops.Context"] = {}
+_MODEL_IDS = itertools.count(1)
 
 
 def get_context(device) -> "ops.Context":
@@ -48,8 +50,18 @@ class Model(nn.Module):
         self.hparams.sample_rate = sample_rate
         self.hparams.num_channels = num_channels
         self.audio = Audio(sample_rate=sample_rate, mono="downmix")
-        self._dummy = nn.Parameter(torch.zeros(0), requires_grad=False)
-        self._uploaded_to: Optional[int] = None
+        self.register_buffer("_dummy", torch.zeros(0), persistent=False)      # device tracker, not in state_dict
+        # The library context of a device holds ONE set of segmentation and ONE set of embedding weights.  Each model
+        # stamps the slot it uploads into with (its unique id, its weight version); a forward re-uploads whenever the
+        # slot carries another stamp, so several models on one GPU and load_state_dict() after a forward stay correct.
+        self._model_id = next(_MODEL_IDS)
+        self._weights_version = 0
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._bump_weights())
+
+    _SLOT = ""          # "seg" | "emb": the context slot this model family uploads into
+
+    def _bump_weights(self):
+        self._weights_version += 1
 
     @property
     def device(self) -> torch.device:
@@ -57,18 +69,75 @@ class Model(nn.Module):
 
     def _apply(self, fn, *a, **kw):
         out = super()._apply(fn, *a, **kw)
-        self._uploaded_to = None          # weights may have moved: re-upload lazily
+        self._bump_weights()              # weights may have moved / changed dtype: re-upload lazily
         return out
 
     def _ctx(self) -> "ops.Context":
         ctx = get_context(self.device)
-        if self._uploaded_to != ctx.device.index:
+        stamp = (self._model_id, self._weights_version)
+        if ctx.owners.get(self._SLOT) != stamp:
             self._upload(ctx)
-            self._uploaded_to = ctx.device.index
+            ctx.owners[self._SLOT] = stamp
         return ctx
 
     def _upload(self, ctx):
         raise NotImplementedError
+
+    # ---- checkpoints (core/model.py:497-655 without lightning / the HF hub) -----------------------------------
+    @classmethod
+    def from_pretrained(cls, checkpoint, map_location=None, strict: bool = True, subfolder: Optional[str] = None,
+                        revision: Optional[str] = None, token=None, cache_dir=None, **kwargs) -> "Model":
+        """Load a pyannote.audio (Lightning-format) checkpoint: a local ``pytorch_model.bin``, a directory holding
+        one (optionally under ``subfolder``), or an ``io.BytesIO``.  The file is read with plain ``torch.load``;
+        the pickled ``pyannote.audio.core.task`` objects (Specifications / Problem / Resolution) are mapped onto this
+        package's mirrors, so neither lightning nor pyannote.audio needs to be importable.  The checkpoint names its
+        own architecture (``checkpoint["pyannote.audio"]["architecture"]``); ``kwargs`` override saved
+        hyper-parameters like the reference.  Hub identifiers cannot be resolved offline and raise."""
+        import io
+        import os
+        from pathlib import Path
+
+        if isinstance(checkpoint, io.BytesIO) or os.path.isfile(checkpoint):
+            if revision is not None:
+                raise ValueError("Revisions cannot be used with local checkpoints.")
+            path = checkpoint
+        elif os.path.isdir(checkpoint):
+            if revision is not None:
+                raise ValueError("Revisions cannot be used with local checkpoints.")
+            path = Path(checkpoint) / subfolder / "pytorch_model.bin" if subfolder else \
+                Path(checkpoint) / "pytorch_model.bin"
+        else:
+            if "@" in str(checkpoint):
+                raise ValueError("Revisions must be passed with `revision` keyword argument.")
+            raise ValueError(f"'{checkpoint}' is not a local checkpoint; Hugging Face hub identifiers cannot be "
+                             f"downloaded here (no network): pass the path of a downloaded pytorch_model.bin")
+        if map_location is None:
+            map_location = "cpu"
+        loaded = torch.load(path, map_location=map_location, weights_only=False, pickle_module=_checkpoint_pickle)
+        meta = loaded["pyannote.audio"]
+        class_name = meta["architecture"]["class"]
+        klass = {"PyanNet": PyanNet, "WeSpeakerResNet34": WeSpeakerResNet34}.get(class_name)
+        if klass is None:
+            raise NotImplementedError(f"architecture {meta['architecture']['module']}.{class_name} has no sm_100a "
+                                      f"implementation (community-1 uses PyanNet and WeSpeakerResNet34)")
+        if cls not in (Model, klass) and not issubclass(klass, cls):
+            raise ValueError(f"checkpoint holds a {class_name}, not a {cls.__name__}")
+        hparams = dict(loaded.get("hyper_parameters", {}))
+        hparams.update(kwargs)
+        hparams = {k: v for k, v in hparams.items() if k in klass._HPARAMS}
+        model = klass(**hparams)
+        specs = meta.get("specifications", None)
+        if specs is not None:
+            if isinstance(specs, (tuple, list)):
+                raise NotImplementedError("multi-task checkpoints are not supported")
+            model.specifications = specs
+        sd = loaded["state_dict"]
+        own = set(model.state_dict().keys())
+        if not strict:
+            sd = {k: v for k, v in sd.items() if k in own}
+        model.load_state_dict(sd, strict=strict)
+        model.eval()
+        return model
 
     @cached_property
     def receptive_field(self) -> SlidingWindow:
@@ -79,11 +148,61 @@ class Model(nn.Module):
         return SlidingWindow(start=start / sr, duration=size / sr, step=step / sr)
 
 
+class _CheckpointUnpickler(__import__("pickle").Unpickler):
+    """Resolves the reference's pickled task types to this package's mirrors (core.py)."""
+
+    _MAP = {("pyannote.audio.core.task", "Specifications"): Specifications,
+            ("pyannote.audio.core.task", "Problem"): Problem,
+            ("pyannote.audio.core.task", "Resolution"): Resolution}
+
+    def find_class(self, module, name):
+        hit = self._MAP.get((module, name))
+        if hit is not None:
+            return hit
+        if module.split(".")[0] in ("lightning", "pytorch_lightning", "lightning_fabric"):
+            # e.g. AttributeDict for hyper_parameters: a plain dict subclass is enough
+            return dict
+        return super().find_class(module, name)
+
+
+class _checkpoint_pickle:
+    """``pickle_module`` for torch.load: the stdlib pickle with the class mapping above."""
+
+    import pickle as _p
+
+    Unpickler = _CheckpointUnpickler
+    Pickler = _p.Pickler
+    load = staticmethod(lambda f, **kw: _CheckpointUnpickler(f, **kw).load())
+    loads = staticmethod(_p.loads)
+    dump = staticmethod(_p.dump)
+    dumps = staticmethod(_p.dumps)
+    HIGHEST_PROTOCOL = _p.HIGHEST_PROTOCOL
+    __name__ = "pickle"
+
+
+def _mel_sinc_init(n_filters=80, sample_rate=16000.0, min_low_hz=50, min_band_hz=50):
+    def to_mel(hz):
+        return 2595 * np.log10(1 + hz / 700)
+
+    def to_hz(mel):
+        return 700 * (10 ** (mel / 2595) - 1)
+
+    mel = np.linspace(to_mel(30), to_mel(sample_rate / 2 - (min_low_hz + min_band_hz)),
+                      n_filters // 2 + 1, dtype="float32")
+    hz = to_hz(mel)
+    return torch.from_numpy(hz[:-1]).view(-1, 1), torch.from_numpy(np.diff(hz)).view(-1, 1)
+
+
+def sinc_buffers(kernel_size=251, sample_rate=16000.0):
+    half = kernel_size // 2
+    window_ = torch.from_numpy(np.hamming(kernel_size)[:half]).float()
+    n_ = 2 * np.pi * (torch.arange(-half, 0.0).view(1, -1) / sample_rate)
+    return window_, n_
+
+
 class _ParamSincFB(nn.Module):
     def __init__(self):
         super().__init__()
-        from .synthetic import _mel_sinc_init, sinc_buffers
-
         low, band = _mel_sinc_init()
         self.low_hz_ = nn.Parameter(low, requires_grad=False)
         self.band_hz_ = nn.Parameter(band, requires_grad=False)
@@ -112,6 +231,8 @@ class _SincNetParams(nn.Module):
 class PyanNet(Model):
     """SincNet > LSTM > Feed forward > Classifier, community-1 shape (4 BiLSTM layers of 128, 2x128 linear)."""
 
+    _SLOT = "seg"
+    _HPARAMS = ("sincnet", "lstm", "linear", "sample_rate", "num_channels")
     KERNEL = [251, 3, 5, 3, 5, 3]
     STRIDE = [10, 3, 1, 3, 1, 3]
 
@@ -217,6 +338,10 @@ class _ResNet34Params(nn.Module):
 
 
 class WeSpeakerResNet34(Model):
+    _SLOT = "emb"
+    _HPARAMS = ("sample_rate", "num_channels", "num_mel_bins", "frame_length", "frame_shift", "dither",
+                "window_type", "use_energy")
+
     def __init__(self, sample_rate: int = 16000, num_channels: int = 1, num_mel_bins: int = 80,
                  frame_length: int = 25, frame_shift: int = 10, dither: float = 0.0, window_type: str = "hamming",
                  use_energy: bool = False):

@@ -76,6 +76,7 @@ class Context:
         self._h = h
         self.seg_loaded = False
         self.emb_loaded = False
+        self.owners = {}          # slot ("seg" | "emb") -> stamp of the model whose weights are resident (models.py)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -140,6 +141,7 @@ class Context:
         w.classifier_bias = f("classifier.bias")
         if sd["classifier.weight"].shape[0] != CLASSES:
             raise ValueError("only the 7-class powerset (3 speakers, max 2 simultaneous) head is supported")
+        self.owners.pop("seg", None)          # whoever uploaded before no longer owns the slot
         _lib.check(self.lib.b200_seg_load(self._h, C.byref(w)))
         self.seg_loaded = True
 
@@ -171,6 +173,7 @@ class Context:
                 bi += 1
         w.seg1_weight = f("resnet.seg_1.weight")
         w.seg1_bias = f("resnet.seg_1.bias")
+        self.owners.pop("emb", None)
         _lib.check(self.lib.b200_emb_load(self._h, C.byref(w)))
         self.emb_loaded = True
 

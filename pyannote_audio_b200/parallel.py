@@ -87,4 +87,4 @@ def apply_sharded(pipeline, file, group=None, **kwargs):
     from .pipeline import set_num_speakers
 
     ns, mn, mx = set_num_speakers(kwargs.get("num_speakers"), kwargs.get("min_speakers"), kwargs.get("max_speakers"))
-    return pipeline._finish_file(ctx, file, seg, emb, ns, mn, mx, pipeline.setup_hook(file, kwargs.get("hook")), False)
+    return pipeline._finish_file(ctx, file, seg, emb, ns, mn, mx, kwargs.get("hook"), False)

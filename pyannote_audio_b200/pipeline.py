@@ -140,6 +140,9 @@ def binarize_frames(discrete: Optional[np.ndarray], frames: SlidingWindow, min_d
     on_k, on_t = np.divmod(on, n + 1)
     off_k, off_t = np.divmod(off, n + 1)
     off_t = np.minimum(off_t, n - 1)                           # still active at the end -> last frame
+    keep = off_t > on_t         # an onset at the very last frame is an empty Segment: Annotation.__setitem__ drops it
+    if not keep.all():
+        on_k, on_t, off_t = on_k[keep], on_t[keep], off_t[keep]
     order = np.lexsort((on_k, off_t, on_t))                    # sort by (start, end, k)
     rows = np.stack([on_t[order], off_t[order], on_k[order]], axis=1).astype(np.int64)
     # timestamps = frames[i].middle computed like pyannote.core: start_i = start + i*step; 0.5*(start_i + (start_i+dur))
@@ -376,6 +379,7 @@ class SpeakerDiarization:
         if self._expects_num_speakers and num_speakers is None:
             raise ValueError(f"num_speakers must be provided when using {self.klustering} clustering")
         ctx = get_context(self.device)
+        self.d2h_bytes = 0
         wav_dev, all_off, all_valid, bounds = resident["wav"], resident["off"], resident["valid"], resident["bounds"]
         # ---- device passes over all files at once ------------------------------------------------------------
         self._timer = _StageTimer(ctx.device)
@@ -396,32 +400,38 @@ class SpeakerDiarization:
         if not hasattr(self, "_timer"):
             self._timer = _StageTimer(ctx.device)
         return self._finish_files(ctx, [file], seg, emb, [0, seg.shape[0]], num_speakers, min_speakers, max_speakers,
-                                  None, return_artifacts)[0]
+                                  hook, return_artifacts)[0]
 
     def _finish_files(self, ctx, files, seg, emb, bounds, num_speakers, min_speakers, max_speakers, hook,
                       return_artifacts):
         tm = self._timer
         F = len(files)
         chunks_sw = SlidingWindow(start=0.0, duration=self._segmentation.duration, step=self._segmentation.step)
-        hooks = [self.setup_hook(f, hook) for f in files]
+        # hooks receive real SlidingWindowFeature / ndarray artifacts (copied device -> host only when a hook was given)
+        # plus the reference's progress calls hook(name, None, total=, completed=) (speaker_diarization.py:439-459,
+        # inference.py:287-320); the device passes over all files have already run when they fire
+        hooks = [self.setup_hook(f, hook) for f in files] if hook is not None else None
         grids, counts = [], []
         for fi in range(F):
             c0, c1 = int(bounds[fi]), int(bounds[fi + 1])
             sf, nF, fr = self._grid(c1 - c0)
             grids.append((sf, nF, fr))
             sfile = seg[c0:c1]
-            hooks[fi]("segmentation", _Lazy(lambda sfile=sfile: SlidingWindowFeature(
-                sfile.cpu().numpy().astype(np.float32), chunks_sw)))
             counts.append(ctx.speaker_count(sfile, sf, nF))
-            hooks[fi]("speaker_counting", _Lazy(lambda c=counts[-1], fr=fr: SlidingWindowFeature(
-                c.cpu().numpy()[:, None], fr)))
+            if hooks is not None:
+                hooks[fi]("segmentation", None, total=c1 - c0, completed=0)
+                hooks[fi]("segmentation", None, total=c1 - c0, completed=c1 - c0)
+                hooks[fi]("segmentation", SlidingWindowFeature(sfile.cpu().numpy().astype(np.float32), chunks_sw))
+                hooks[fi]("speaker_counting", SlidingWindowFeature(counts[-1].cpu().numpy()[:, None], fr))
         count_max = torch.stack([c.max() for c in counts]).cpu().numpy().astype(np.int64)        # sync
         tm.mark("speaker_count")
         silent = [int(m) == 0 for m in count_max]
-        for fi in range(F):
-            if not silent[fi]:
-                efile = emb[int(bounds[fi]): int(bounds[fi + 1])]
-                hooks[fi]("embeddings", _Lazy(lambda efile=efile: efile.cpu().numpy()))
+        if hooks is not None:
+            for fi in range(F):
+                if not silent[fi]:
+                    hooks[fi]("embeddings", None, total=1, completed=0)
+                    hooks[fi]("embeddings", None, total=1, completed=1)
+                    hooks[fi]("embeddings", emb[int(bounds[fi]): int(bounds[fi + 1])].cpu().numpy())
         if isinstance(self.clustering, VBxClustering):
             results = self.clustering.cluster_batch(emb, seg, bounds, num_clusters=num_speakers,
                                                     min_clusters=min_speakers, max_clusters=max_speakers, skip=silent)
@@ -496,8 +506,9 @@ class SpeakerDiarization:
                     given audio file is too short to contain {min_speakers} or more speakers.
                     Try to lower the desired minimal number of speakers.
                     """))
-            hooks[fi]("discrete_diarization", _Lazy(lambda d=discrete, fr=fr, kd=kd: SlidingWindowFeature(
-                d.cpu().numpy()[:, :kd].astype(np.float64), fr)))
+            if hooks is not None:
+                hooks[fi]("discrete_diarization",
+                          SlidingWindowFeature(discrete.cpu().numpy()[:, :kd].astype(np.float64), fr))
             diarization, rows = binarize_frames(None, fr, self.min_duration_off, uri=uri, events=(nF,) + ev_d)
             exclusive_diarization, xrows = binarize_frames(None, fr, self.min_duration_off, uri=uri,
                                                            events=(nF,) + ev_x)
@@ -559,18 +570,3 @@ class _StageTimer:
             tot = sum(self.acc.values())
             print("[b200 timing] " + ", ".join(f"{k}={v * 1e3:.1f}ms" for k, v in self.acc.items())
                   + f", total={tot * 1e3:.1f}ms", file=sys.stderr, flush=True)
-
-
-class _Lazy:
-    """Hook artefact materialised (D2H) only if a hook actually looks at it."""
-
-    def __init__(self, fn):
-        self._fn, self._v = fn, None
-
-    def get(self):
-        if self._v is None:
-            self._v = self._fn()
-        return self._v
-
-    def __getattr__(self, name):
-        return getattr(self.get(), name)

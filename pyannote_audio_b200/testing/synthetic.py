@@ -32,24 +32,7 @@ def _uniform(gen, shape, bound):
     return (torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1) * bound
 
 
-def _mel_sinc_init(n_filters=80, sample_rate=16000.0, min_low_hz=50, min_band_hz=50):
-    def to_mel(hz):
-        return 2595 * np.log10(1 + hz / 700)
-
-    def to_hz(mel):
-        return 700 * (10 ** (mel / 2595) - 1)
-
-    mel = np.linspace(to_mel(30), to_mel(sample_rate / 2 - (min_low_hz + min_band_hz)),
-                      n_filters // 2 + 1, dtype="float32")
-    hz = to_hz(mel)
-    return torch.from_numpy(hz[:-1]).view(-1, 1), torch.from_numpy(np.diff(hz)).view(-1, 1)
-
-
-def sinc_buffers(kernel_size=251, sample_rate=16000.0):
-    half = kernel_size // 2
-    window_ = torch.from_numpy(np.hamming(kernel_size)[:half]).float()
-    n_ = 2 * np.pi * (torch.arange(-half, 0.0).view(1, -1) / sample_rate)
-    return window_, n_
+from ..models import _mel_sinc_init, sinc_buffers  # noqa: E402,F401  (ParamSincFB default initialisation)
 
 
 def make_segmentation_state_dict(seed: int = 0, lstm_layers: int = 4, num_classes: int = 7,

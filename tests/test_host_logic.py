@@ -53,11 +53,9 @@ def test_inference_ctor_validation():
 def test_models_have_reference_state_dict_keys():
     seg_sd, emb_sd = syn.make_segmentation_state_dict(0), syn.make_embedding_state_dict(1)
     m = PyanNet()
-    missing, unexpected = m.load_state_dict(seg_sd, strict=False)
-    assert not unexpected and set(missing) <= {"_dummy"}
+    m.load_state_dict(seg_sd, strict=True)            # exactly the reference's keys: nothing missing, nothing extra
     e = WeSpeakerResNet34()
-    missing, unexpected = e.load_state_dict(emb_sd, strict=False)
-    assert not unexpected and set(missing) <= {"_dummy"}
+    e.load_state_dict(emb_sd, strict=True)
     # oracle modules take the very same dicts (same key names as the reference)
     nets.PyanNet().load_state_dict(seg_sd, strict=True)
     nets.WeSpeakerResNet34().load_state_dict(emb_sd, strict=True)
@@ -203,3 +201,155 @@ def test_sparse_true_matches_flatnonzero():
         x = rng.uniform(size=(int(rng.integers(1, 6)), int(rng.integers(1, 400)))) < rng.uniform(0, 0.3)
         assert np.array_equal(_sparse_true(x), np.flatnonzero(x))
     assert _sparse_true(np.zeros((3, 17), dtype=bool)).size == 0
+
+
+# ---- checkpoints (core/model.py:497-655, core/plda.py:65-135) without lightning -------------------------------------
+def _reference_style_checkpoint(kind):
+    """A Lightning-format pytorch_model.bin as the reference writes it (model.py:244-256): state_dict +
+    hyper_parameters + checkpoint["pyannote.audio"] whose `specifications` is pickled under the REFERENCE's module
+    path pyannote.audio.core.task (registered here only while pickling, then removed again)."""
+    import dataclasses
+    import enum
+    import io
+    import sys
+    import types
+
+    names = ("pyannote", "pyannote.audio", "pyannote.audio.core", "pyannote.audio.core.task")
+    saved = {n: sys.modules.get(n) for n in names}
+    mods = {n: types.ModuleType(n) for n in names}
+    sys.modules.update(mods)
+    try:
+        class Problem(enum.Enum):
+            BINARY_CLASSIFICATION = 0
+            MONO_LABEL_CLASSIFICATION = 1
+            MULTI_LABEL_CLASSIFICATION = 2
+            REPRESENTATION = 3
+            REGRESSION = 4
+
+        class Resolution(enum.Enum):
+            FRAME = 1
+            CHUNK = 2
+
+        @dataclasses.dataclass
+        class Specifications:
+            problem: Problem
+            resolution: Resolution
+            duration: float
+            min_duration: float = None
+            warm_up: tuple = (0.0, 0.0)
+            classes: list = None
+            powerset_max_classes: int = None
+            permutation_invariant: bool = False
+
+        for c in (Problem, Resolution, Specifications):
+            c.__module__, c.__qualname__ = "pyannote.audio.core.task", c.__name__
+            setattr(mods["pyannote.audio.core.task"], c.__name__, c)
+        if kind == "seg":
+            ck = {"state_dict": syn.make_segmentation_state_dict(0),
+                  "hyper_parameters": {"sincnet": {"stride": 10}, "linear": {"hidden_size": 128, "num_layers": 2},
+                                       "lstm": {"hidden_size": 128, "num_layers": 4, "bidirectional": True,
+                                                "monolithic": True, "dropout": 0.0},
+                                       "sample_rate": 16000, "num_channels": 1},
+                  "pyannote.audio": {"versions": {"pyannote.audio": "4.0.0"},
+                                     "architecture": {"module": "pyannote.audio.models.segmentation.PyanNet",
+                                                      "class": "PyanNet"},
+                                     "specifications": Specifications(
+                                         Problem.MONO_LABEL_CLASSIFICATION, Resolution.FRAME, 10.0,
+                                         classes=["speaker#1", "speaker#2", "speaker#3"], powerset_max_classes=2,
+                                         permutation_invariant=True)}}
+        else:
+            ck = {"state_dict": syn.make_embedding_state_dict(1),
+                  "hyper_parameters": {"sample_rate": 16000, "num_channels": 1, "num_mel_bins": 80,
+                                       "frame_length": 25, "frame_shift": 10, "dither": 0.0,
+                                       "window_type": "hamming", "use_energy": False},
+                  "pyannote.audio": {"versions": {"pyannote.audio": "4.0.0"},
+                                     "architecture": {"module": "pyannote.audio.models.embedding.wespeaker",
+                                                      "class": "WeSpeakerResNet34"},
+                                     "specifications": Specifications(Problem.REPRESENTATION, Resolution.CHUNK, 10.0)}}
+        ck["pytorch-lightning_version"] = "2.6.1"
+        buf = io.BytesIO()
+        torch.save(ck, buf)
+        return buf.getvalue(), ck["state_dict"]
+    finally:
+        for n in names:
+            if saved[n] is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = saved[n]
+
+
+def test_from_pretrained_reads_reference_checkpoints(tmp_path):
+    import io
+
+    from pyannote_audio_b200.core import Problem, Resolution, Specifications
+    from pyannote_audio_b200.models import Model
+
+    blob, sd = _reference_style_checkpoint("seg")
+    assert "pyannote.audio.core.task" not in __import__("sys").modules        # nothing of the reference is importable
+    m = Model.from_pretrained(io.BytesIO(blob))
+    assert isinstance(m, PyanNet) and isinstance(m.specifications, Specifications)
+    assert m.specifications.problem is Problem.MONO_LABEL_CLASSIFICATION and m.specifications.powerset
+    assert m.specifications.resolution is Resolution.FRAME and m.specifications.num_powerset_classes == 7
+    for k, v in sd.items():
+        assert torch.equal(m.state_dict()[k], v), k
+    # directory form (+ subfolder), class check, kwargs override, hub ids refused offline
+    d = tmp_path / "ckpt" / "segmentation"
+    d.mkdir(parents=True)
+    (d / "pytorch_model.bin").write_bytes(blob)
+    assert isinstance(PyanNet.from_pretrained(tmp_path / "ckpt", subfolder="segmentation"), PyanNet)
+    with pytest.raises(ValueError):
+        WeSpeakerResNet34.from_pretrained(d / "pytorch_model.bin")
+    with pytest.raises(ValueError):
+        Model.from_pretrained("pyannote/segmentation-3.0")
+    with pytest.raises(ValueError):
+        Model.from_pretrained(d / "pytorch_model.bin", revision="main")
+    blob_e, sd_e = _reference_style_checkpoint("emb")
+    e = Model.from_pretrained(io.BytesIO(blob_e))
+    assert isinstance(e, WeSpeakerResNet34) and e.specifications.resolution is Resolution.CHUNK
+    assert torch.equal(e.state_dict()["resnet.seg_1.weight"], sd_e["resnet.seg_1.weight"])
+    # PLDA.from_pretrained: directory with xvec_transform.npz + plda.npz (plda.py:97-105)
+    p = syn.make_plda(2)
+    np.savez(tmp_path / "xvec_transform.npz", mean1=p["mean1"], mean2=p["mean2"], lda=p["lda"])
+    np.savez(tmp_path / "plda.npz", mu=p["mu"], tr=p["tr"], psi=p["psi"])
+    from pyannote_audio_b200.clustering import PLDA
+
+    a, b = PLDA.from_pretrained(tmp_path), PLDA(p)
+    assert np.array_equal(a.phi, b.phi) and np.array_equal(a._plda_tr, b._plda_tr)
+    with pytest.raises(ValueError):
+        PLDA.from_pretrained("pyannote/speaker-diarization-community-1")
+
+
+def test_weight_ownership_stamps():
+    """Two models of one family on the same device share one context slot: the stamp protocol re-uploads whenever
+    the resident weights are not the caller's; load_state_dict and .to() invalidate."""
+    a, b = PyanNet(), PyanNet()
+    assert a._model_id != b._model_id
+    v = a._weights_version
+    a.load_state_dict(syn.make_segmentation_state_dict(0), strict=True)
+    assert a._weights_version == v + 1
+    a.to(torch.device("cpu"))
+    assert a._weights_version == v + 2
+    assert "_dummy" not in a.state_dict()
+
+
+def test_binarize_drops_empty_segments_and_support_is_strict():
+    from pyannote_audio_b200.core import Annotation, Segment, SlidingWindow
+    from pyannote_audio_b200.pipeline import binarize_frames
+
+    fr = SlidingWindow(start=0.0, duration=0.0619375, step=0.016875)
+    d = np.zeros((10, 2), dtype=np.uint8)
+    d[2:5, 0] = 1
+    d[9, 1] = 1                                   # onset at the very last frame: Segment(t, t) is empty -> dropped
+    ann, rows = binarize_frames(d, fr)
+    assert rows.tolist() == [[2, 5, 0]] and ann.labels() == [0]
+    swf = P.SWF(d.astype(np.float64), P.SW(fr.start, fr.duration, fr.step))
+    assert [list(r) for r in P.binarize_to_segments(swf)[0]] == rows.tolist()
+    # support(collar): merge when the gap is < collar (strict) or empty (<= 1e-6), per label in sorted label order
+    ann = Annotation()
+    for s, e, lab in ((0.0, 1.0, "b"), (1.5, 2.0, "b"), (2.2, 3.0, "b"), (0.0, 1.0, "a"), (1.0, 2.0, "a")):
+        ann.add(Segment(s, e), "_", lab)
+    got = [(s.start, s.end, lab) for s, _, lab in ann.support(collar=0.5).itertracks(yield_label=True)]
+    assert got == [(0.0, 1.0, "b"), (0.0, 2.0, "a"), (1.5, 3.0, "b")]         # gap 0.5 is NOT < 0.5; gap 0.2 is
+    assert got == P.support([(0.0, 1.0, "b"), (1.5, 2.0, "b"), (2.2, 3.0, "b"), (0.0, 1.0, "a"), (1.0, 2.0, "a")], 0.5)
+    ann.add(Segment(5.0, 5.0), "_", "c")          # empty segments are never stored
+    assert "c" not in ann.labels()
