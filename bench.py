@@ -3,15 +3,22 @@
 
 A "step" = one pass of the whole pipeline (segmentation -> embeddings -> clustering -> reconstruction -> annotations)
 over a batch of synthetic 10-minute files (12 per GPU by default = BASELINE.json configs[4], 100 x 10 min over
-8 GPUs, scaled to one GPU).  Weak scaling: every rank processes its own files, there is no data-path collective.
+8 GPUs, scaled to one GPU).  Weak scaling.  For N > 1 the default data path is the north star's: the chunks of all
+files form one global pool (each rank computes its share), ONE in-place NCCL all-gather replicates embeddings +
+powerset classes, and file g is clustered / reconstructed on rank g mod N (`--parallelism pool`);
+`--parallelism files` keeps plain file sharding without any data-path collective.
 
   value : audio-hours/sec, waveforms already resident in HBM (CUDA events, max over ranks)
-  e2e   : the same through SpeakerDiarization.apply_batch with HOST waveforms (H2D + D2H inside the timed region)
-  roofline     : ResNet34 trunk conv kernels (~98 % of the FLOPs) measured live with CUDA events
+  e2e   : the same through the public batch API with HOST waveforms (H2D + D2H inside the timed region)
+  roofline     : ResNet34 trunk conv kernels (~98 % of the FLOPs) measured live with CUDA events; `traffic` from the
+                 latest ncu capture of the same kernels (profiles/*_trunk_traffic.json)
   cpu_baseline : the CPU oracle (reference-equivalent: 3 trunk passes per chunk) on a bounded sample, rank 0, N=1
+  eager_cuda_baseline : the same oracle networks in PyTorch-eager CUDA fp32 with TF32 off (what the reference itself
+                 would run on this GPU, utils/reproducibility.py:68-83), batch 32, CUDA events
 
 `--impl reference` times the CPU oracle arm (the reference package itself cannot be imported in this image:
-lightning / pyannote.core / asteroid_filterbanks are absent).
+lightning / pyannote.core / asteroid_filterbanks are absent).  Its sample is one short file per step,
+end to end, normalised to the chunk density of the 10-minute workload (stated in cpu_baseline.sample).
 """
 import argparse
 import json
@@ -39,7 +46,10 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--files-per-gpu", type=int, default=12)
     ap.add_argument("--minutes", type=float, default=10.0)
-    ap.add_argument("--cpu-sample-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-sample-seconds", type=float, default=24.0)
+    ap.add_argument("--parallelism", default="auto", choices=["auto", "pool", "files"],
+                    help="N>1 data path: global chunk pool + one all-gather (default) or collective-free file sharding")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager CUDA fp32 leg")
     ap.add_argument("--min-warmup", type=int, default=3, help="lower only when profiling under ncu")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
     return ap.parse_args()
@@ -98,16 +108,49 @@ def oracle_models():
     return seg.eval(), emb.eval(), P.PLDA(**syn.make_plda(2))
 
 
+def workload_config(args, world):
+    """The `config` object of the JSON line: identical for the GPU arm and the CPU reference arm."""
+    step_chunks = int(round(args.minutes * 60.0)) - 10 + 1
+    par = "single GPU" if world == 1 else (
+        f"global chunk pool x{world} + one NCCL all-gather, per-file stage on rank g mod {world}"
+        if pool_mode(args, world) else f"file-sharded x{world}, no data-path collective")
+    return {"workload": f"community-1 diarization pipeline end-to-end, {args.files_per_gpu} x {args.minutes:g} min "
+                        f"synthetic 16 kHz mono files per GPU (BASELINE.json configs[4] scaled per GPU)",
+            "files_per_gpu": args.files_per_gpu, "chunks_per_gpu": args.files_per_gpu * step_chunks,
+            "audio_hours_per_step_per_gpu": args.files_per_gpu * args.minutes / 60.0, "parallelism": par,
+            "l2": f"inputs larger than L2: {args.files_per_gpu * args.minutes * 60 * 16000 * 4 / 1e6:.0f} MB of "
+                  f"waveform per step"}
+
+
+def pool_mode(args, world):
+    return world > 1 and args.parallelism in ("auto", "pool")
+
+
 def cpu_pass(seconds, models, seed=4242):
-    """One reference-equivalent CPU pass (3 trunk forwards per chunk like the reference) -> wall seconds."""
+    """One reference-equivalent CPU pass (3 trunk forwards per chunk like the reference) -> (wall seconds, chunks)."""
     from oracle import pipeline as P
     from pyannote_audio_b200 import synthetic as syn
 
     seg, emb, plda = models
     wav = syn.make_conversation(seconds, seed=seed)
     t0 = time.perf_counter()
-    P.apply(seg, emb, plda, wav, seg_batch=32, emb_batch=8, share_trunk=False)
-    return time.perf_counter() - t0
+    out = P.apply(seg, emb, plda, wav, seg_batch=32, emb_batch=8, share_trunk=False)
+    return time.perf_counter() - t0, int(out.segmentations.data.shape[0])
+
+
+def cpu_value(args, t, chunks):
+    """audio-hours/sec of the CPU arm on the bench workload: the sample's chunks per second, divided by the chunk
+    density of the workload's files (591 chunks per 600 s: a 10 s window every 1 s) -- per-chunk cost dominates (the
+    three ResNet passes per chunk are > 99 % of the CPU time), so the short sample extrapolates linearly."""
+    file_s = args.minutes * 60.0
+    density = (int(round(file_s)) - 10 + 1) / file_s           # chunks per audio-second of the workload
+    return (chunks / t) / density / 3600.0
+
+
+def cpu_sample_text(args, t, chunks):
+    return (f"CPU oracle (PyTorch CPU fp32, 3 trunk passes per chunk as the reference), one {args.cpu_sample_seconds:g} s "
+            f"synthetic file end-to-end = {chunks} chunks in {t:.1f} s wall, extrapolated linearly to the workload's "
+            f"{int(round(args.minutes * 60)) - 9} chunks per {args.minutes:g}-min file (per-chunk cost)")
 
 
 def run_reference(args, rank, world):
@@ -117,23 +160,74 @@ def run_reference(args, rank, world):
     models = oracle_models()
     secs = args.cpu_sample_seconds
     for _ in range(min(args.warmup, 1)):
-        cpu_pass(min(secs, 12.0), models)
-    times = [cpu_pass(secs, models, seed=4242 + i) for i in range(max(1, args.steps))]
-    t = float(np.mean(times))
-    value = (secs / 3600.0) / t
-    sample = (f"CPU oracle (PyTorch CPU fp32, 3 trunk passes per chunk as the reference), one {secs:g} s synthetic "
-              f"file end-to-end per step")
+        cpu_pass(12.0, models)
+    runs = [cpu_pass(secs, models, seed=4242 + i) for i in range(max(1, args.steps))]
+    t = float(np.mean([r[0] for r in runs]))
+    chunks = runs[0][1]
+    value = cpu_value(args, t, chunks)
     line = {"metric": METRIC, "value": value, "unit": "audio-hours/sec", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"community-1 pipeline, {args.files_per_gpu} x {args.minutes:g} min synthetic files "
-                                   f"per GPU (CPU arm: bounded sample, see cpu_baseline.sample)"},
-            "rtf": t / secs,
+            "config": workload_config(args, world),
+            "rtf": 1.0 / (value * 3600.0),
             "cpu_baseline": {"value": value, "unit": "audio-hours/sec", "cores": torch.get_num_threads(),
-                             "kind": "port", "sample": sample},
+                             "kind": "port", "sample": cpu_sample_text(args, t, chunks)},
             "e2e": {"value": value, "unit": "audio-hours/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def eager_cuda_baseline(args, dev, chunks=64):
+    """The oracle networks (= the reference's modules) in PyTorch-eager CUDA fp32 with TF32 off, batch 32, timed with
+    CUDA events: PyanNet on `chunks` chunks + WeSpeaker on 3 x `chunks` (waveform, mask) pairs, i.e. the reference's
+    GPU work per chunk without its host loops, numpy round trips and clustering (which only flatters this leg)."""
+    from oracle import nets
+    from pyannote_audio_b200 import synthetic as syn
+
+    torch.backends.cuda.matmul.allow_tf32 = False            # utils/reproducibility.py:68-83
+    torch.backends.cudnn.allow_tf32 = False
+    seg, emb = nets.PyanNet(), nets.WeSpeakerResNet34()
+    seg.load_state_dict(syn.make_segmentation_state_dict(0))
+    emb.load_state_dict(syn.make_embedding_state_dict(1))
+    seg, emb = seg.eval().to(dev), emb.eval().to(dev)
+    wav = syn.make_conversation(10.0 + chunks - 1, seed=77)
+    x = wav.unfold(1, 160000, 16000).permute(1, 0, 2).contiguous().to(dev)[:chunks]      # (chunks,1,160000)
+    masks = (torch.rand(chunks, 589, device=dev) < 0.5).float()
+
+    def run():
+        with torch.inference_mode():
+            for c in range(0, chunks, 32):
+                seg(x[c:c + 32])
+            for _ in range(3):                                  # one forward per local speaker, like the reference
+                for c in range(0, chunks, 32):
+                    emb(x[c:c + 32], weights=masks[c:c + 32])
+
+    run()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t = e0.elapsed_time(e1) / 1e3
+    del seg, emb, x
+    torch.cuda.empty_cache()
+    return {"value": cpu_value(args, t, chunks), "unit": "audio-hours/sec", "kind": "oracle modules, PyTorch eager "
+            "CUDA fp32, TF32 off (cuDNN / cuBLAS), batch 32", "sample": f"{chunks} chunks: PyanNet + 3 x WeSpeaker "
+            f"ResNet34 forwards in {t * 1e3:.0f} ms (networks only: no host loops, no clustering), extrapolated per "
+            f"chunk like cpu_baseline"}
+
+
+def trunk_traffic():
+    """DRAM bytes of one 256-segment trunk pass from the newest committed ncu capture (profiles/*_trunk_traffic.json,
+    produced by scripts/ncu_trunk_traffic.py from an `ncu --metrics dram__bytes_*` launch list)."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_trunk_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    return d.get("dram_bytes_per_256_segments"), os.path.basename(files[-1])
 
 
 def main():
@@ -148,6 +242,7 @@ def main():
 
     from pyannote_audio_b200 import synthetic as syn
     from pyannote_audio_b200.models import PyanNet, WeSpeakerResNet34, get_context
+    from pyannote_audio_b200.parallel import ChunkPool
     from pyannote_audio_b200.pipeline import SpeakerDiarization
 
     torch.cuda.set_device(local_rank)
@@ -167,6 +262,8 @@ def main():
         files.append({"waveform": wav.pin_memory(), "sample_rate": 16000, "uri": f"r{rank}_f{i}"})
     audio_hours = nfiles * args.minutes / 60.0
     h2d = sum(f["waveform"].numel() * 4 for f in files)
+    use_pool = pool_mode(args, world)
+    pool = ChunkPool(pipe) if use_pool else None
 
     def sync():
         torch.cuda.synchronize(dev)
@@ -189,18 +286,25 @@ def main():
             ms = float(t.item())
         return ms / steps
 
-    resident = pipe.upload(files)
+    resident = pool.upload(files) if use_pool else pipe.upload(files)
+    done = [0]
+    coll_ms = []
 
     def step_resident():
-        for _ in pipe.run_resident(resident):
-            pass
+        n = 0
+        for _ in (pool.run_resident(resident) if use_pool else pipe.run_resident(resident)):
+            n += 1
+        done[0] = n
+        if use_pool:
+            coll_ms.append(pool._events)
 
     d2h = [0]
 
     def step_e2e():
-        pipe.d2h_bytes = 0
-        for _ in pipe.apply_batch(files):
-            pass
+        n = 0
+        for _ in (pool.apply_batch(files) if use_pool else pipe.apply_batch(files)):
+            n += 1
+        done[0] = n
         d2h[0] = pipe.d2h_bytes
 
     for _ in range(max(args.min_warmup, args.warmup)):
@@ -212,12 +316,27 @@ def main():
     ctx.set_option("profile", 1)
     ctx.timer("trunk"); ctx.timer("seg")
     l0 = ctx.launch_count
+    coll_ms.clear()
     ms_resident = timed(step_resident, args.steps)
     launches = (ctx.launch_count - l0) // max(1, args.steps)
     trunk_ms, trunk_segments = ctx.timer("trunk")
     seg_ms, seg_chunks = ctx.timer("seg")
     ctx.set_option("profile", 0)
     clocks = sampler.stop() if rank == 0 else None
+    collective = None
+    if use_pool:
+        per_step = [ev[0].elapsed_time(ev[1]) for ev in coll_ms if ev is not None]
+        t = torch.tensor([float(np.mean(per_step)) if per_step else 0.0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        collective = {"op": "ncclAllGather (in place, one packed buffer: embeddings f32 | powerset classes u8)",
+                      "bytes_sent_per_rank": pool.last_collective["bytes_sent"],
+                      "bytes_received_per_rank": pool.last_collective["bytes_received"],
+                      "ms_per_step_max_over_ranks": float(t.item()),
+                      "note": "event-timed on the launching stream: includes waiting for the slowest rank's compute"}
+    files_done = torch.tensor([done[0]], device=dev)
+    if world > 1:
+        dist.all_reduce(files_done)
+    assert int(files_done.item()) == world * nfiles, "every file must come out of the per-file stage exactly once"
     ms_e2e = timed(step_e2e, max(1, args.steps))
     value = world * audio_hours / (ms_resident / 1e3)
     e2e = world * audio_hours / (ms_e2e / 1e3)
@@ -228,40 +347,34 @@ def main():
     pk = peaks()
     peak = pk.get("bf16_tflops_sustained", 1400.0)
     achieved = trunk_segments * TRUNK_FLOP_PER_SEGMENT / (trunk_ms / 1e3) / 1e12 if trunk_ms > 0 else 0.0
-    # DRAM traffic of one 256-segment trunk pass (stem + 35 tcgen05 conv launches) from ncu
-    # (profiles/r01_trunk_traffic_256.csv: 29.66 GB read + 18.70 GB written; algorithmic minimum 50.9 GB counting every
-    # activation tensor once per read/write, i.e. no re-read waste; small layers hit L2)
-    traffic_256 = 48.354e9
+    traffic, traffic_src = trunk_traffic()
     roofline = {"bound": "tensor",
-                "kernel": "ResNet34 trunk = conv_tc4/conv_tc3/conv_tc kernels, 36 dependent launches per 256-segment sub-batch",
+                "kernel": "ResNet34 trunk = stem + tcgen05 conv kernels, one dependent chain per 256-segment sub-batch",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "traffic": traffic_256, "traffic_unit": "bytes per 256-segment trunk pass (ncu dram read+write)",
+                "traffic": traffic, "traffic_unit": "bytes per 256-segment trunk pass (ncu dram read+write)",
+                "traffic_source": traffic_src,
                 "algorithmic_flop_per_launch_unit": 256 * TRUNK_FLOP_PER_SEGMENT,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (fp16 = same tensor rate)"
                 if pk else "fallback 1.4 PFLOP/s sustained",
                 "trunk_ms_per_step": trunk_ms / args.steps, "seg_ms_per_step": seg_ms / args.steps}
-    cpu = None
+    cpu = eager = None
+    if world == 1 and not args.no_eager_baseline:
+        eager = eager_cuda_baseline(args, dev)
     if args.gpus == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(min(32, os.cpu_count() or 1))
         models = oracle_models()
-        t = cpu_pass(args.cpu_sample_seconds, models)
-        cpu = {"value": (args.cpu_sample_seconds / 3600.0) / t, "unit": "audio-hours/sec",
-               "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"CPU oracle (3 trunk passes per chunk, as the reference), one {args.cpu_sample_seconds:g} s "
-                         f"synthetic file end-to-end ({t:.1f} s wall)"}
+        t, chunks = cpu_pass(args.cpu_sample_seconds, models)
+        cpu = {"value": cpu_value(args, t, chunks), "unit": "audio-hours/sec", "cores": torch.get_num_threads(),
+               "kind": "port", "sample": cpu_sample_text(args, t, chunks)}
     line = {"metric": METRIC, "value": value, "unit": "audio-hours/sec", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.min_warmup, args.warmup), "ms_per_step": ms_resident, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 tensor-core trunk (f32 accumulate) + split-f16x3 tensor-core segmentation (f32-level accuracy) + f64 clustering",
-            "data": "synthetic",
-            "config": {"workload": f"community-1 diarization pipeline end-to-end, {nfiles} x {args.minutes:g} min "
-                                   f"synthetic 16 kHz mono files per GPU (BASELINE.json configs[4] scaled per GPU)",
-                       "files_per_gpu": nfiles, "chunks_per_gpu": int(sum(len(r[1]) for r in resident["layouts"])),
-                       "audio_hours_per_step_per_gpu": audio_hours, "parallelism": f"file-sharded x{world}",
-                       "l2": f"inputs larger than L2: {h2d / 1e6:.0f} MB of waveform per step"},
+            "data": "synthetic", "config": workload_config(args, world),
             "rtf": (ms_resident / 1e3) / (audio_hours * 3600.0) / world,
             "e2e": {"value": e2e, "unit": "audio-hours/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h[0],
                     "ms_per_step": ms_e2e},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "eager_cuda_baseline": eager, "collective": collective}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -94,6 +94,19 @@ typedef struct b200_emb_weights {
 } b200_emb_weights;
 int b200_emb_load(b200_ctx* ctx, const b200_emb_weights* w);
 
+/* ---- audio ingest: Audio.__call__ / Audio.downmix_and_resample (core/io.py:223-265, 306-351) -----------------
+ * pcm is a DEVICE buffer holding the raw decoded audio: B200_PCM_S16_INTERLEAVED = int16 [frame][channel] (what a
+ * PCM WAV holds; half the PCIe bytes of float32) or B200_PCM_F32_PLANAR = float32 [channel][frame] (the reference's
+ * in-memory {"waveform": (channel, time)} files).  channel >= 0 selects that channel (io.py:232-233), channel < 0
+ * downmixes by the mean over channels (mono="downmix", io.py:241-242); when sr_in != sr_out the signal is resampled
+ * with torchaudio.functional.resample's default polyphase windowed-sinc filter (io.py:246-250).  Writes
+ * b200_audio_num_frames(frames_in, sr_in, sr_out) float32 samples to out (capacity checked). */
+#define B200_PCM_S16_INTERLEAVED 0
+#define B200_PCM_F32_PLANAR 1
+int64_t b200_audio_num_frames(int64_t frames_in, int32_t sr_in, int32_t sr_out);
+int b200_audio_ingest(b200_ctx* ctx, const void* pcm, int32_t format, int32_t channels, int64_t frames_in,
+                      int32_t sr_in, int32_t sr_out, int32_t channel, float* out, int64_t out_capacity, void* stream);
+
 /* ---- segmentation: Inference.infer / Inference.slide hot loop (core/inference.py:182-215, 295-313) --------
  * `wav` is a device fp32 buffer; chunk i covers wav[chunk_off[i] .. chunk_off[i]+160000), of which only the first
  * chunk_valid[i] samples are real (the rest is the zero padding of the last chunk, inference.py:270-278).
@@ -131,10 +144,22 @@ int b200_speaker_count(b200_ctx* ctx, const uint8_t* seg, const int32_t* start_f
                        int32_t num_frames, uint8_t* count, void* stream);
 /* hard_clusters[num_chunks][3] int8 DEVICE (-2 = inactive/unassigned, values >= num_clusters_out are ignored);
  * count[num_frames] u8 device (already capped); out: discrete[num_frames][num_clusters_out] u8 with
- * num_clusters_out >= max(K, max(count)), at most 32. */
+ * num_clusters_out >= max(K, max(count)), at most 127 (hard clusters are int8 like the reference's
+ * constrained_argmax; up to 32 clusters the per-frame counters stay in registers). */
 int b200_reconstruct(b200_ctx* ctx, const uint8_t* seg, const int8_t* hard_clusters, const int32_t* start_frame,
                      int32_t num_chunks, int32_t num_frames, const uint8_t* count, int32_t num_clusters_out,
                      uint8_t* discrete, void* stream);
+
+/* Inference.aggregate (core/inference.py:498-620), the generic float overlap-add behind the aggregated
+ * (skip_aggregation=False) Inference output and the VAD / OSD pipelines: scores[num_chunks][589][K] fp32 (NaN =
+ * missing), hamming / warm_up: DEVICE fp64[589] windows or NULL (= ones) -> out[num_frames][K] fp32, bit-identical to
+ * numpy's mixed float32/float64 arithmetic (see post.cu). */
+int b200_aggregate(b200_ctx* ctx, const float* scores, const int32_t* start_frame, int32_t num_chunks,
+                   int32_t num_frames, int32_t num_classes, const double* hamming, const double* warm_up,
+                   int32_t skip_average, float missing, float epsilon, float* out, void* stream);
+/* VoiceActivityDetection's pre-aggregation step (pipelines/voice_activity_detection.py:111-114: max over the
+ * speakers of the multilabel output) straight from the powerset classes: speech[n] fp32 in {0,1}. */
+int b200_powerset_speech(b200_ctx* ctx, const uint8_t* classes, int64_t n, float* speech, void* stream);
 
 /* Onsets / offsets of a discrete diarization discrete[num_frames][num_clusters] u8 (to_annotation ->
  * Binarize(onset=offset=0.5), pipelines/utils/diarization.py:188-218, utils/signal.py:254-318) as unordered events

@@ -243,6 +243,52 @@ def binarize_to_segments(discrete: SWF):
     return rows, times
 
 
+def binarize_scores(scores: SWF, onset=0.5, offset=0.5, min_duration_on=0.0, min_duration_off=0.0):
+    """Binarize.__call__ (utils/signal.py:254-318) restated literally for float scores (hysteresis thresholds),
+    pad_onset = pad_offset = 0.  Returns [(start_s, end_s, class_index)] in itertracks order."""
+    n, K = scores.data.shape
+    ts = [scores.sw.middle(i) for i in range(n)]
+    out = []
+    for k in range(K):
+        col = scores.data[:, k]
+        start = ts[0]
+        is_active = col[0] > onset
+        t = ts[0]
+        for t, y in zip(ts[1:], col[1:]):
+            if is_active:
+                if y < offset:
+                    if t - start > 1e-6:
+                        out.append((start, t, k))
+                    start = t
+                    is_active = False
+            else:
+                if y > onset:
+                    start = t
+                    is_active = True
+        if is_active and t - start > 1e-6:
+            out.append((start, t, k))
+    out.sort(key=lambda r: (r[0], r[1], r[2]))
+    if min_duration_off > 0.0:
+        out = support(out, min_duration_off)
+    if min_duration_on > 0:
+        out = [r for r in out if r[1] - r[0] >= min_duration_on]
+    return out
+
+
+def vad_scores(seg_model, waveform: torch.Tensor, batch_size=32) -> SWF:
+    """VoiceActivityDetection's `self._segmentation(file)` (pipelines/voice_activity_detection.py:111-115, 196-198):
+    Inference with pre_aggregation_hook = max over speakers, Hamming aggregation, padded tail cropped
+    (core/inference.py:349-369)."""
+    seg = slide(seg_model, waveform, batch_size)
+    speech = SWF(np.max(seg.data, axis=-1, keepdims=True), seg.sw)
+    frames = SW(*nets.sincnet_receptive_field())
+    agg = aggregate(speech, frames, warm_up=(0.0, 0.0), hamming=True, missing=0.0)
+    num_samples = waveform.shape[1]
+    if num_samples < 160000 or (num_samples - 160000) % 16000 > 0:
+        agg = agg.crop_loose((0.0, num_samples / SAMPLE_RATE))
+    return agg
+
+
 def support(times, collar=0.0):
     """pyannote.core Annotation.support(collar) (called by Binarize when min_duration_off > 0, signal.py:307-310),
     restated from the published behaviour (parity unpinned, like the rest of pyannote.core): per label in sorted
@@ -538,6 +584,41 @@ def ahc_cluster(embeddings, method="centroid", threshold=0.0, min_cluster_size=0
         clusters[clusters == small[sk]] = large[lk]
     _, clusters = np.unique(clusters, return_inverse=True)
     return clusters
+
+
+def set_num_clusters(num_embeddings, num_clusters=None, min_clusters=None, max_clusters=None):
+    """BaseClustering.set_num_clusters (pipelines/clustering.py:54-75)."""
+    min_clusters = num_clusters or min_clusters or 1
+    min_clusters = max(1, min(num_embeddings, min_clusters))
+    max_clusters = num_clusters or max_clusters or num_embeddings
+    max_clusters = max(1, min(num_embeddings, max_clusters))
+    if min_clusters > max_clusters:
+        raise ValueError("min_clusters must be smaller than (or equal to) max_clusters")
+    if min_clusters == max_clusters:
+        num_clusters = min_clusters
+    return num_clusters, min_clusters, max_clusters
+
+
+def ahc_call(embeddings, seg_data, threshold, min_cluster_size, method="centroid", num_clusters=None,
+             min_clusters=None, max_clusters=None, constrained=False):
+    """AgglomerativeClustering via BaseClustering.__call__ (pipelines/clustering.py:214-289) +
+    assign_embeddings (:142-212): filter -> cluster -> centroids = mean of train embeddings per cluster ->
+    cosine cdist -> (constrained) argmax.  Returns (hard, soft, centroids)."""
+    train, chunk_idx, speaker_idx = filter_embeddings(embeddings, seg_data)
+    num_chunks, num_speakers, dimension = embeddings.shape
+    num_clusters, min_clusters, max_clusters = set_num_clusters(train.shape[0], num_clusters, min_clusters,
+                                                                max_clusters)
+    if max_clusters < 2:
+        return (np.zeros((num_chunks, num_speakers), dtype=np.int8), np.ones((num_chunks, num_speakers, 1)),
+                np.mean(train, axis=0, keepdims=True))
+    train_clusters = ahc_cluster(train, method=method, threshold=threshold, min_cluster_size=min_cluster_size,
+                                 min_clusters=min_clusters, max_clusters=max_clusters, num_clusters=num_clusters)
+    K = int(np.max(train_clusters)) + 1
+    centroids = np.vstack([np.mean(train[train_clusters == k], axis=0) for k in range(K)])
+    e2k = cdist(embeddings.reshape(-1, dimension), centroids, metric="cosine").reshape(num_chunks, num_speakers, -1)
+    soft = 2 - e2k
+    hard = constrained_argmax(soft) if constrained else np.argmax(soft, axis=2)
+    return hard, soft, centroids
 
 
 # ----------------------------------------------------------------------------------------

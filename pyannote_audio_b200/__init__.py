@@ -14,7 +14,8 @@ _LAZY = {
     "Audio": "audio", "Inference": "inference", "BaseInference": "inference", "Model": "models", "PyanNet": "models",
     "WeSpeakerResNet34": "models", "SpeakerDiarization": "pipeline", "DiarizeOutput": "pipeline",
     "PretrainedSpeakerEmbedding": "pipeline", "VBxClustering": "clustering",
-    "AgglomerativeClustering": "clustering", "PLDA": "clustering",
+    "AgglomerativeClustering": "clustering", "PLDA": "clustering", "VoiceActivityDetection": "vad",
+    "Binarize": "signal",
 }
 
 

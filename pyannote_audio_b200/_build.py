@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libb200diar.so")
-SOURCES = ["err.cu", "api.cu", "sgemm.cu", "seg_sincnet.cu", "seg_lstm.cu", "seg_lstm_tc.cu", "seg_conv_tc.cu", "seg_sinc_tc.cu", "emb_conv.cu", "emb_misc.cu", "post.cu",
+SOURCES = ["err.cu", "api.cu", "sgemm.cu", "seg_sincnet.cu", "seg_lstm.cu", "seg_lstm_tc.cu", "seg_conv_tc.cu", "seg_sinc_tc.cu", "emb_conv.cu", "emb_misc.cu", "post.cu", "audio.cu",
            "cluster.cu", "gemm_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]

@@ -89,6 +89,51 @@ class Audio:
             data = data.astype(np.float32)
         return torch.from_numpy(np.ascontiguousarray(data.T)), int(sr)
 
+    # ---- device ingest (b200_audio_ingest): raw PCM crosses PCIe once, downmix + resample run on the GPU ---------
+    @staticmethod
+    def _read_pcm(path: str):
+        """Raw samples of a WAV file without conversion: int16 (frames, channels) when the file is 16-bit PCM (the
+        common case: half the bytes of float32), otherwise float32 (channels, frames) converted on the host."""
+        from scipy.io import wavfile
+
+        sr, data = wavfile.read(path)
+        if data.ndim == 1:
+            data = data[:, None]
+        if data.dtype == np.int16:
+            return torch.from_numpy(np.ascontiguousarray(data)), int(sr)
+        w, sr = Audio._read_wav(path)
+        return w.contiguous(), sr
+
+    def raw(self, file: AudioFile):
+        """(raw tensor, sample_rate, channel): int16 (frames, channels) or float32 (channels, frames), on the host."""
+        file = self.validate_file(file)
+        if "waveform" in file:
+            w = file["waveform"]
+            return (w if w.dtype == torch.float32 else w.float()), int(file["sample_rate"]), file.get("channel", None)
+        pcm, sr = self._read_pcm(file["audio"])
+        return pcm, sr, file.get("channel", None)
+
+    def num_samples_out(self, raw: torch.Tensor, sample_rate: int) -> int:
+        """Length of the mono waveform the device ingest will produce (ceil(new * len / orig), like torchaudio)."""
+        from . import _lib
+
+        frames = raw.shape[0] if raw.dtype == torch.int16 else raw.shape[1]
+        target = self.sample_rate or sample_rate
+        return int(_lib.load().b200_audio_num_frames(int(frames), int(sample_rate), int(target)))
+
+    def needs_ingest(self, raw: torch.Tensor, sample_rate: int, channel=None) -> bool:
+        mono = raw.dtype == torch.float32 and raw.shape[0] == 1
+        return not (mono and (self.sample_rate in (None, sample_rate)))
+
+    def ingest(self, ctx, raw: torch.Tensor, sample_rate: int, channel=None, out: Optional[torch.Tensor] = None):
+        """H2D of the raw samples + downmix / resample on the device -> float32 mono (samples,) device tensor."""
+        if self.mono == "random" and channel is None and (raw.shape[1] if raw.dtype == torch.int16 else raw.shape[0]) > 1:
+            nch = raw.shape[1] if raw.dtype == torch.int16 else raw.shape[0]
+            channel = int(np.random.randint(nch))
+        dev = raw.contiguous().to(ctx.device, non_blocking=True)
+        return ctx.audio_ingest(dev, sample_rate, self.sample_rate or sample_rate, channel=channel,
+                                downmix=(self.mono == "downmix") or channel is None, out=out)
+
     def get_duration(self, file: AudioFile) -> float:
         file = self.validate_file(file)
         if "waveform" in file:

@@ -1,6 +1,7 @@
 // extern "C" surface of libb200diar.so (declared in include/b200diar.h): context, weight ingestion
 // (BN folding, layout transforms, fp16 conversion on the host), and the forward entry points.
 #include "../../include/b200diar.h"
+#include "audio.cuh"
 #include "cluster.cuh"
 #include "common.cuh"
 #include "emb.cuh"
@@ -36,6 +37,9 @@ struct b200_ctx {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trunk_events, seg_events;
   std::vector<cudaEvent_t> event_pool;
   int64_t trunk_segments = 0, seg_chunks = 0;
+  // polyphase resampling tables, one per (orig, new) ratio seen (device copies, freed with the ctx)
+  struct ResampleTable { int orig, nw, width; float* dev; };
+  std::vector<ResampleTable> resample_tables;
 };
 
 namespace {
@@ -230,6 +234,7 @@ int b200_ctx_destroy(b200_ctx* ctx) {
   cudaDeviceSynchronize();
   for (void* p : ctx->owned_seg) cudaFree(p);
   for (void* p : ctx->owned_emb) cudaFree(p);
+  for (auto& t : ctx->resample_tables) cudaFree(t.dev);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->d_off) cudaFree(ctx->d_off);
   if (ctx->d_valid) cudaFree(ctx->d_valid);
@@ -279,6 +284,48 @@ int b200_ctx_timer(b200_ctx* ctx, const char* name, double* total_ms, int64_t* u
   *units = *u;
   *u = 0;
   return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+static int64_t gcd64(int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return a; }
+
+int64_t b200_audio_num_frames(int64_t frames_in, int32_t sr_in, int32_t sr_out) {
+  if (frames_in <= 0 || sr_in <= 0 || sr_out <= 0) return 0;
+  if (sr_in == sr_out) return frames_in;
+  const int64_t g = gcd64(sr_in, sr_out), orig = sr_in / g, nw = sr_out / g;
+  return (nw * frames_in + orig - 1) / orig;                // ceil(new * length / orig)
+}
+
+int b200_audio_ingest(b200_ctx* ctx, const void* pcm, int32_t format, int32_t channels, int64_t frames_in,
+                      int32_t sr_in, int32_t sr_out, int32_t channel, float* out, int64_t out_capacity, void* stream) {
+  B200_CHECK(ctx && pcm && out && channels >= 1 && frames_in >= 0 && sr_in > 0 && sr_out > 0, B200_ERR_INVALID,
+             "bad arguments");
+  B200_CHECK(format == B200_PCM_S16_INTERLEAVED || format == B200_PCM_F32_PLANAR, B200_ERR_INVALID,
+             "unknown PCM format %d", (int)format);
+  B200_CHECK(channel < channels, B200_ERR_INVALID, "channel %d of a %d-channel file", (int)channel, (int)channels);
+  const int64_t frames_out = b200_audio_num_frames(frames_in, sr_in, sr_out);
+  B200_CHECK(frames_out <= out_capacity, B200_ERR_INVALID, "output holds %lld samples, %lld needed",
+             (long long)out_capacity, (long long)frames_out);
+  if (frames_out == 0) return B200_OK;
+  DeviceGuard g(ctx->device);
+  const int64_t gg = gcd64(sr_in, sr_out);
+  const int orig = (int)(sr_in / gg), nw = (int)(sr_out / gg);
+  const b200_ctx::ResampleTable* tab = nullptr;
+  for (auto& t : ctx->resample_tables)
+    if (t.orig == orig && t.nw == nw) tab = &t;
+  if (!tab) {
+    b200_ctx::ResampleTable t{orig, nw, 0, nullptr};
+    std::vector<float> host;
+    if (orig == nw) { host.assign(1, 1.0f); t.width = 0; }   // same rate: y[i] = 1.0 * x[i] (exact)
+    else resample_table(orig, nw, &t.width, &host);
+    B200_CUDA_OK(cudaMalloc((void**)&t.dev, host.size() * sizeof(float)));
+    B200_CUDA_OK(cudaMemcpy(t.dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->resample_tables.push_back(t);
+    tab = &ctx->resample_tables.back();
+  }
+  ctx->launches += 1;
+  return audio_ingest(pcm, format, channels, frames_in, channel, tab->dev, tab->orig, tab->nw, tab->width, out,
+                      frames_out, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -743,6 +790,25 @@ int b200_reconstruct(b200_ctx* ctx, const uint8_t* seg, const int8_t* hard_clust
   ctx->launches += 1;
   return reconstruct(seg, (const signed char*)hard_clusters, start_frame, num_chunks, num_frames, num_clusters_out,
                      count, discrete, (cudaStream_t)stream);
+}
+
+int b200_aggregate(b200_ctx* ctx, const float* scores, const int32_t* start_frame, int32_t num_chunks,
+                   int32_t num_frames, int32_t num_classes, const double* hamming, const double* warm_up,
+                   int32_t skip_average, float missing, float epsilon, float* out, void* stream) {
+  B200_CHECK(ctx && scores && start_frame && out && num_chunks > 0 && num_frames > 0 && num_classes > 0,
+             B200_ERR_INVALID, "bad arguments");
+  DeviceGuard g(ctx->device);
+  ctx->launches += 1;
+  return aggregate_scores(scores, start_frame, num_chunks, num_frames, num_classes, hamming, warm_up, skip_average,
+                          missing, epsilon, out, (cudaStream_t)stream);
+}
+
+int b200_powerset_speech(b200_ctx* ctx, const uint8_t* classes, int64_t n, float* speech, void* stream) {
+  B200_CHECK(ctx && classes && speech && n >= 0, B200_ERR_INVALID, "bad arguments");
+  if (n == 0) return B200_OK;
+  DeviceGuard g(ctx->device);
+  ctx->launches += 1;
+  return powerset_speech(classes, n, speech, (cudaStream_t)stream);
 }
 
 int b200_frame_transitions(b200_ctx* ctx, const uint8_t* discrete, int32_t num_frames, int32_t num_clusters,

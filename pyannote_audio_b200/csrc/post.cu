@@ -63,6 +63,59 @@ int speaker_count(const unsigned char* seg, const int* sf, int C, int F, unsigne
   return B200_OK;
 }
 
+// ---- generic float overlap-add: Inference.aggregate (core/inference.py:498-620) ------------------------------------
+// One thread per (frame, class) gathers the (<= 11) chunks covering the frame in ascending chunk order, i.e. in the
+// order numpy's per-chunk `+=` scatter visits them, and reproduces numpy's mixed-precision arithmetic exactly: the
+// float32 accumulators are updated as float32(float64(acc) + ((float64(score) * mask) * hamming) * warm_up), the
+// average is a float32 division by max(count, float32(epsilon)), frames no chunk contributed to get `missing`.
+__global__ void __launch_bounds__(256)
+aggregate_kernel(const float* __restrict__ scores, const int* __restrict__ sf, int C, int F, int K,
+                 const double* __restrict__ hamming, const double* __restrict__ warm, int skip_average, float missing,
+                 float epsilon, float* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)F * K) return;
+  const int f = (int)(idx / K), k = (int)(idx - (long long)f * K);
+  float agg = 0.f, cnt = 0.f;
+  bool any = false;
+  for (int c = first_chunk(sf, C, f); c < C && sf[c] <= f; ++c) {
+    const int t = f - sf[c];
+    const float s = scores[((size_t)c * kFrames + t) * K + k];
+    const bool valid = !isnan(s);
+    const double h = hamming ? hamming[t] : 1.0, w = warm ? warm[t] : 1.0;
+    const double m = valid ? 1.0 : 0.0;
+    const double sv = valid ? (double)s : 0.0;
+    agg = (float)__dadd_rn((double)agg, __dmul_rn(__dmul_rn(__dmul_rn(sv, m), h), w));
+    cnt = (float)__dadd_rn((double)cnt, __dmul_rn(__dmul_rn(m, h), w));
+    any |= valid;
+  }
+  float r = skip_average ? agg : __fdiv_rn(agg, fmaxf(cnt, epsilon));
+  if (!any) r = missing;
+  out[idx] = r;
+}
+
+int aggregate_scores(const float* scores, const int* sf, int C, int F, int K, const double* hamming, const double* warm,
+                     int skip_average, float missing, float epsilon, float* out, cudaStream_t stream) {
+  const long long n = (long long)F * K;
+  aggregate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(scores, sf, C, F, K, hamming, warm, skip_average,
+                                                                     missing, epsilon, out);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+// speech score of a powerset frame = max over the speakers of its multilabel row = (class != 0); this is what
+// VoiceActivityDetection's pre_aggregation_hook (np.max(scores, axis=-1, keepdims=True),
+// pipelines/voice_activity_detection.py:111-114) makes of the (C,589,3) multilabel output
+__global__ void powerset_speech_kernel(const unsigned char* __restrict__ cls, long long n, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (cls[i] != 0 && cls[i] < 7) ? 1.f : 0.f;
+}
+
+int powerset_speech(const unsigned char* cls, long long n, float* out, cudaStream_t stream) {
+  powerset_speech_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(cls, n, out);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
 constexpr int kMaxK = 32;
 
 // KMAX is a compile-time bound so that the per-frame activation counters stay in registers (static indexing).

@@ -99,8 +99,9 @@ class Inference(BaseInference):
         cls = torch.argmax(logp, dim=-1).to(torch.uint8).contiguous()
         return ctx.powerset_to_multilabel(cls).cpu().numpy().astype(np.float32)
 
-    def slide_device(self, waveform: torch.Tensor, sample_rate: int):
-        """Device-resident result of the sliding window: (classes (C,589) u8 tensor, wav_dev, off, valid)."""
+    def slide_device(self, waveform: torch.Tensor, sample_rate: int, return_logp: bool = False):
+        """Device-resident result of the sliding window: (classes (C,589) u8 tensor, wav_dev, off, valid);
+        with ``return_logp`` the first entry is the pair (classes, log-probabilities (C,589,7) f32)."""
         window_size = self.model.audio.get_num_samples(self.duration)
         step_size = round(self.step * sample_rate)
         if window_size != ops.CHUNK:
@@ -116,22 +117,22 @@ class Inference(BaseInference):
             src = src.contiguous()
         wav_dev[:num_samples].copy_(src, non_blocking=True)
         try:
-            cls = self.model.forward_chunks(wav_dev, off, valid)
+            cls = self.model.forward_chunks(wav_dev, off, valid, return_logp=return_logp)
         except MemoryError:
             raise MemoryError(f"batch_size ({self.batch_size: d}) is probably too large. "
                               f"Try with a smaller value until memory error disappears.")
         return cls, wav_dev, off, valid
 
     def slide(self, waveform: torch.Tensor, sample_rate: int, hook: Optional[Callable] = None):
-        cls, _, off, _ = self.slide_device(waveform, sample_rate)
+        cls, _, off, _ = self.slide_device(waveform, sample_rate, return_logp=self.conversion != "powerset")
         total = len(off)
         if hook is not None:
             hook(completed=0, total=total)
         ctx = self.model._ctx()
         if self.conversion == "powerset":
             outputs = ctx.powerset_to_multilabel(cls).cpu().numpy().astype(np.float32)
-        else:
-            raise NotImplementedError("skip_conversion=True needs log-probabilities: use Inference.infer on chunks")
+        else:                                   # skip_conversion=True: raw powerset log-probabilities (:130-141)
+            outputs = cls[1].cpu().numpy()
         if hook is not None:
             hook(completed=total, total=total)
         frames = self.model.receptive_field
@@ -142,8 +143,8 @@ class Inference(BaseInference):
             return SlidingWindowFeature(outputs, chunks_sw)
         if self.pre_aggregation_hook is not None:
             outputs = self.pre_aggregation_hook(outputs)
-        aggregated = self.aggregate(SlidingWindowFeature(outputs, chunks_sw), frames, warm_up=self.warm_up,
-                                    hamming=True, missing=0.0)
+        aggregated = self.aggregate_device(SlidingWindowFeature(np.asarray(outputs), chunks_sw), frames,
+                                           warm_up=self.warm_up, hamming=True, missing=0.0)
         _, num_samples = waveform.shape
         has_last = (num_samples < ops.CHUNK) or (num_samples - ops.CHUNK) % round(self.step * sample_rate) > 0
         if has_last:
@@ -174,6 +175,26 @@ class Inference(BaseInference):
             waveform = torch.cat([self.model.audio.crop(file, c)[0] for c in chunk], dim=1)
         return self.infer(waveform[None])[0]
 
+    def aggregate_device(self, scores: SlidingWindowFeature, frames: SlidingWindow,
+                         warm_up: Tuple[float, float] = (0.0, 0.0), epsilon: float = 1e-12, hamming: bool = False,
+                         missing: float = np.nan, skip_average: bool = False) -> SlidingWindowFeature:
+        """Inference.aggregate on the device (b200_aggregate): same arguments, bit-identical result.  ``scores.data``
+        may be a host array or a device tensor of shape (chunks, 589, classes)."""
+        ctx = self.model._ctx()
+        data = scores.data
+        if not isinstance(data, torch.Tensor):
+            data = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32))
+        data = data.to(device=ctx.device, dtype=torch.float32)
+        chunks = scores.sliding_window
+        num_chunks, nfpc, _ = data.shape
+        fr = SlidingWindow(start=chunks.start, duration=frames.duration, step=frames.step)
+        sf = fr.closest_frames(chunks.start + np.arange(num_chunks) * chunks.step + 0.5 * fr.duration).astype(np.int32)
+        num_frames = fr.closest_frame(
+            chunks.start + chunks.duration + (num_chunks - 1) * chunks.step + 0.5 * fr.duration) + 1
+        out = ctx.aggregate(data, sf, num_frames, hamming=hamming, warm_up=warm_up, chunk_duration=chunks.duration,
+                            epsilon=epsilon, missing=missing, skip_average=skip_average)
+        return SlidingWindowFeature(out.cpu().numpy(), fr)
+
     # ---- static helpers, called by name from the diarization mixin (diarization.py:175-176, 241) ---------
     @staticmethod
     def aggregate(scores: SlidingWindowFeature, frames: SlidingWindow, warm_up: Tuple[float, float] = (0.0, 0.0),
@@ -196,14 +217,13 @@ class Inference(BaseInference):
         agg = np.zeros((num_frames, num_classes), dtype=np.float32)
         cnt = np.zeros((num_frames, num_classes), dtype=np.float32)
         msk = np.zeros((num_frames, num_classes), dtype=np.float32)
-        window = hamming_window * warm_up_window
         for c in range(num_chunks):
             score = scores.data[c]
             mask = 1 - np.isnan(score)
             score = np.nan_to_num(score, copy=True, nan=0.0)
             sf = frames.closest_frame(chunks.start + c * chunks.step + 0.5 * frames.duration)
-            agg[sf:sf + nfpc] += score * mask * window
-            cnt[sf:sf + nfpc] += mask * window
+            agg[sf:sf + nfpc] += score * mask * hamming_window * warm_up_window       # the reference's operand order
+            cnt[sf:sf + nfpc] += mask * hamming_window * warm_up_window
             msk[sf:sf + nfpc] = np.maximum(msk[sf:sf + nfpc], mask)
         average = agg if skip_average else agg / np.maximum(cnt, epsilon)
         average[msk == 0.0] = missing

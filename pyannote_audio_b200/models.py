@@ -290,9 +290,9 @@ class PyanNet(Model):
     def _upload(self, ctx):
         ctx.load_segmentation(self.state_dict())
 
-    def forward_chunks(self, wav: torch.Tensor, chunk_off, chunk_valid, return_logp: bool = False):
+    def forward_chunks(self, wav: torch.Tensor, chunk_off, chunk_valid, return_logp: bool = False, out=None):
         """Hot-path entry: chunks addressed inside one resident device waveform (no unfold copy)."""
-        return self._ctx().seg_forward(wav, chunk_off, chunk_valid, return_logp=return_logp)
+        return self._ctx().seg_forward(wav, chunk_off, chunk_valid, return_logp=return_logp, out=out)
 
     def forward(self, waveforms: torch.Tensor) -> torch.Tensor:
         """waveforms (batch, channel, sample) -> log-probabilities (batch, 589, 7)."""
@@ -369,9 +369,9 @@ class WeSpeakerResNet34(Model):
             n = _conv1d_num_frames(n, 3, s, p=1)
         return n
 
-    def forward_chunks(self, wav: torch.Tensor, chunk_off, chunk_valid, masks: torch.Tensor) -> torch.Tensor:
+    def forward_chunks(self, wav: torch.Tensor, chunk_off, chunk_valid, masks: torch.Tensor, out=None) -> torch.Tensor:
         """Hot-path entry: (num_chunks, 3, 589) uint8 masks -> (num_chunks, 3, 256) embeddings, one trunk pass."""
-        return self._ctx().emb_forward(wav, chunk_off, chunk_valid, masks)
+        return self._ctx().emb_forward(wav, chunk_off, chunk_valid, masks, out=out)
 
     def _flat(self, waveforms):
         b, c, s = waveforms.shape

@@ -190,10 +190,19 @@ class Context:
         return off, valid
 
     # ---- segmentation ----------------------------------------------------------------------------
-    def seg_forward(self, wav, chunk_off, chunk_valid, return_logp=False):
+    def _out(self, out: Optional[torch.Tensor], shape, dtype) -> torch.Tensor:
+        """Caller-provided output (e.g. this rank's slice of a collective's buffer) or a fresh tensor."""
+        if out is None:
+            return torch.empty(shape, dtype=dtype, device=self.device)
+        if tuple(out.shape) != tuple(shape) or out.dtype != dtype or out.device != self.device or \
+                not out.is_contiguous():
+            raise ValueError(f"`out` must be a contiguous {dtype} tensor of shape {tuple(shape)} on {self.device}")
+        return out
+
+    def seg_forward(self, wav, chunk_off, chunk_valid, return_logp=False, out: Optional[torch.Tensor] = None):
         off, valid = self._chunks(wav, chunk_off, chunk_valid)
         n = len(off)
-        cls = torch.empty((n, FRAMES), dtype=torch.uint8, device=self.device)
+        cls = self._out(out, (n, FRAMES), torch.uint8)
         logp = torch.empty((n, FRAMES, CLASSES), dtype=torch.float32, device=self.device) if return_logp else None
         with torch.cuda.device(self.device):
             _lib.check(self.lib.b200_seg_forward(self._h, _ptr(wav), off.ctypes.data, valid.ctypes.data, n, _ptr(cls),
@@ -217,12 +226,12 @@ class Context:
         return out
 
     # ---- embeddings ------------------------------------------------------------------------------
-    def emb_forward(self, wav, chunk_off, chunk_valid, masks: torch.Tensor):
+    def emb_forward(self, wav, chunk_off, chunk_valid, masks: torch.Tensor, out: Optional[torch.Tensor] = None):
         off, valid = self._chunks(wav, chunk_off, chunk_valid)
         n = len(off)
         if tuple(masks.shape) != (n, SPEAKERS, FRAMES) or masks.dtype != torch.uint8 or not masks.is_contiguous():
             raise ValueError(f"masks must be a contiguous uint8 tensor of shape ({n}, 3, 589)")
-        emb = torch.empty((n, SPEAKERS, EMB_DIM), dtype=torch.float32, device=self.device)
+        emb = self._out(out, (n, SPEAKERS, EMB_DIM), torch.float32)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.b200_emb_forward(self._h, _ptr(wav), off.ctypes.data, valid.ctypes.data, n, _ptr(masks),
                                                  _ptr(emb), _stream(self.device)))
@@ -321,6 +330,80 @@ class Context:
         on = np.sort(host[2: 2 + n_on].astype(np.int64))
         off = np.sort(host[2 + cap: 2 + cap + n_off].astype(np.int64))
         return on, off
+
+    # ---- audio ingest ------------------------------------------------------------------------------
+    def audio_ingest(self, pcm: torch.Tensor, sample_rate: int, target_rate: Optional[int] = None,
+                     channel: Optional[int] = None, downmix: bool = True, out: Optional[torch.Tensor] = None):
+        """Raw decoded audio on the device -> float32 mono waveform (frames_out,) at ``target_rate``.
+
+        ``pcm``: int16 (frames, channels) interleaved PCM, or float32 (channels, frames) like the reference's
+        in-memory files.  ``channel`` selects one channel, otherwise channels are averaged (mono="downmix").
+        (core/io.py:223-265: downmix, then torchaudio.functional.resample.)"""
+        if pcm.device != self.device or not pcm.is_contiguous() or pcm.dim() != 2:
+            raise ValueError(f"pcm must be a contiguous 2-D tensor on {self.device}")
+        if pcm.dtype == torch.int16:
+            fmt, (frames, channels) = 0, pcm.shape
+        elif pcm.dtype == torch.float32:
+            fmt, (channels, frames) = 1, pcm.shape
+        else:
+            raise ValueError("pcm must be int16 (frames, channels) or float32 (channels, frames)")
+        if channel is None and not downmix and channels > 1:
+            raise ValueError("multi-channel audio needs `channel` or downmix=True")
+        target_rate = int(target_rate or sample_rate)
+        n = int(self.lib.b200_audio_num_frames(int(frames), int(sample_rate), target_rate))
+        if out is None:
+            out = torch.empty((n,), dtype=torch.float32, device=self.device)
+        elif out.dtype != torch.float32 or out.device != self.device or not out.is_contiguous() or out.numel() < n:
+            raise ValueError(f"`out` must be a contiguous float32 tensor with at least {n} elements on {self.device}")
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.b200_audio_ingest(self._h, _ptr(pcm), fmt, int(channels), int(frames),
+                                                  int(sample_rate), target_rate, -1 if channel is None else int(channel),
+                                                  _ptr(out), out.numel(), _stream(self.device)))
+        return out[:n]
+
+    # ---- generic overlap-add (Inference.aggregate) ---------------------------------------------------
+    def _window(self, key, build):
+        cache = self.__dict__.setdefault("_win_cache", {})
+        if key not in cache:
+            cache[key] = torch.from_numpy(np.ascontiguousarray(build(), dtype=np.float64)).to(self.device)
+        return cache[key]
+
+    def aggregate(self, scores: torch.Tensor, start_frame, num_frames: int, hamming: bool = False,
+                  warm_up=(0.0, 0.0), chunk_duration: float = 10.0, epsilon: float = 1e-12,
+                  missing: float = float("nan"), skip_average: bool = False) -> torch.Tensor:
+        """scores (C,589,K) float32 device (NaN = missing) -> (num_frames, K) float32 device, bit-identical to
+        Inference.aggregate's numpy arithmetic (core/inference.py:498-620)."""
+        if scores.dtype != torch.float32 or scores.device != self.device or scores.dim() != 3 or \
+                scores.shape[1] != FRAMES:
+            raise ValueError(f"scores must be a float32 (chunks, {FRAMES}, classes) tensor on {self.device}")
+        scores = scores.contiguous()
+        sf = self.start_frames(start_frame)
+        ham = self._window("hamming", lambda: np.hamming(FRAMES)) if hamming else None
+        wl = round(warm_up[0] / chunk_duration * FRAMES)
+        wr = round(warm_up[1] / chunk_duration * FRAMES)
+        warm = None
+        if wl or wr:
+            def build():
+                w = np.ones(FRAMES)
+                w[:wl] = epsilon
+                w[FRAMES - wr:] = epsilon
+                return w
+            warm = self._window(("warm", wl, wr, epsilon), build)
+        out = torch.empty((num_frames, scores.shape[2]), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.b200_aggregate(self._h, _ptr(scores), _ptr(sf), sf.numel(), int(num_frames),
+                                               int(scores.shape[2]), _ptr(ham), _ptr(warm), int(skip_average),
+                                               float(missing), float(np.float32(epsilon)), _ptr(out),
+                                               _stream(self.device)))
+        return out
+
+    def powerset_speech(self, cls: torch.Tensor) -> torch.Tensor:
+        """(…) uint8 powerset classes -> (…, 1) float32 speech indicator (max over the speakers of the multilabel)."""
+        out = torch.empty(tuple(cls.shape) + (1,), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.b200_powerset_speech(self._h, _ptr(cls.contiguous()), cls.numel(), _ptr(out),
+                                                     _stream(self.device)))
+        return out
 
     def clean_frames(self, seg: torch.Tensor):
         n = seg.shape[0]

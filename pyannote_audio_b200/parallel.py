@@ -1,10 +1,13 @@
 """Multi-GPU sharding of the hot path (one process per GPU, torch.distributed; NCCL on GPUs, gloo in CPU tests).
 
 The reference has no inference-time parallelism at all; the path shards naturally:
-  * many files  -> file-level round-robin, no data-path collective (bench.py, weak scaling);
-  * one long file -> contiguous chunk ranges per rank through segmentation and embedding (chunk c only needs
-    samples [c*step, c*step+160000)), then ONE all-gather of the per-chunk results (powerset classes (C,589) u8 and
-    embeddings (C,3,256) f32) before the per-file clustering barrier.
+  * many files  -> ``ChunkPool``: the chunks of all files form one global pool, every rank runs PyanNet + WeSpeaker on
+    its share and writes the results straight into its slice of ONE packed buffer, a single in-place NCCL all-gather
+    replicates (embeddings (C,3,256) f32 | powerset classes (C,589) u8) on every GPU, then file g is clustered /
+    reconstructed on rank g mod N (hook point core/pipeline.py:497-508).  File-level sharding
+    without any collective stays available (bench.py --parallelism files);
+  * one long file -> ``apply_sharded``: contiguous chunk ranges per rank (chunk c only needs samples
+    [c*step, c*step+160000)), the same all-gather, clustering replicated.
 """
 from __future__ import annotations
 
@@ -50,6 +53,130 @@ def sharded_forward(num_chunks: int, seg_fn: Callable[[int, int], torch.Tensor],
     cls = seg_fn(a, b)
     emb = emb_fn(a, b, cls)
     return all_gather_rows(cls.contiguous(), counts, group), all_gather_rows(emb.contiguous(), counts, group)
+
+
+class ChunkPool:
+    """Global chunk pool over many files with one all-gather before clustering (BASELINE.json configs[4]).
+
+    Every rank holds its own files (their chunks are its share of the pool: the heavy per-chunk work never crosses
+    NVLink), but clustering ownership is global round-robin (file g -> rank g mod N), which is what balances the
+    per-file stage when files differ in length.  One packed buffer [world][emb bytes | class bytes] lives on each
+    GPU; the network kernels write their outputs directly into this rank's slice (no staging copy) and
+    ``all_gather_into_tensor`` runs in place on it.
+    """
+
+    EMB_BYTES = 3 * 256 * 4
+    CLS_BYTES = 589
+
+    def __init__(self, pipeline, group=None):
+        self.pipeline, self.group = pipeline, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.last_collective = dict(bytes_sent=0, bytes_received=0, ms=None)
+        self._events = None
+
+    # ---- planning: per-file chunk counts of every rank (tiny object all-gather, once per batch of files) ----------
+    def plan(self, layouts, uris):
+        mine = [(u, int(len(l[1])), int(l[3])) for u, l in zip(uris, layouts)]
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        files, counts = [], []
+        for r, lst in enumerate(everyone):
+            counts.append(sum(c for _, c, _ in lst))
+            pos = 0
+            for uri, c, T in lst:
+                files.append(dict(uri=uri, rank=r, start=pos, chunks=c, num_samples=T))
+                pos += c
+        cmax = max(counts) if counts else 0
+        blk = -(-(cmax * (self.EMB_BYTES + self.CLS_BYTES)) // 16) * 16
+        return dict(files=files, counts=counts, cmax=cmax, blk=blk)
+
+    def views(self, buf, plan, r):
+        """(embeddings (C_r,3,256) f32, classes (C_r,589) u8) views of rank r's block of the packed buffer."""
+        c, base = plan["counts"][r], r * plan["blk"]
+        emb = buf[base: base + c * self.EMB_BYTES].view(torch.float32).view(c, 3, 256)
+        o = base + plan["cmax"] * self.EMB_BYTES
+        cls = buf[o: o + c * self.CLS_BYTES].view(c, self.CLS_BYTES)
+        return emb, cls
+
+    def upload(self, files):
+        resident = self.pipeline.upload(files)
+        resident["plan"] = self.plan(resident["layouts"], [f.get("uri") for f in resident["files"]])
+        return resident
+
+    def apply_batch(self, files, **kwargs):
+        yield from self.run_resident(self.upload(files), **kwargs)
+
+    def run_resident(self, resident, num_speakers=None, min_speakers=None, max_speakers=None, hook=None,
+                     return_artifacts=False):
+        from .models import get_context
+        from .pipeline import set_num_speakers
+
+        pipe, plan = self.pipeline, resident["plan"]
+        ctx = get_context(pipe.device)
+        num_speakers, min_speakers, max_speakers = set_num_speakers(num_speakers, min_speakers, max_speakers)
+        pipe.d2h_bytes = 0
+        buf = resident.get("pool")
+        if buf is None or buf.numel() != self.world * plan["blk"]:
+            buf = resident["pool"] = torch.zeros(self.world * plan["blk"], dtype=torch.uint8, device=ctx.device)
+        emb_mine, cls_mine = self.views(buf, plan, self.rank)
+        # ---- this rank's share of the pool: outputs land in its slice of the collective's buffer ----------------
+        pipe._segmentation.model.forward_chunks(resident["wav"], resident["off"], resident["valid"], out=cls_mine)
+        seg_mine = ctx.powerset_to_multilabel(cls_mine)
+        pipe.embedding.forward_chunks(resident["wav"], resident["off"], resident["valid"], pipe._masks(seg_mine),
+                                      out=emb_mine)
+        self.exchange(buf, plan)
+        got = self.owned_inputs(buf, plan)
+        if got is None:
+            return
+        emb, cls, bounds, owned = got
+        seg = ctx.powerset_to_multilabel(cls)
+        metas = [dict(uri=plan["files"][g]["uri"], global_index=g, computed_on=plan["files"][g]["rank"])
+                 for g in owned]
+        from .pipeline import _StageTimer
+
+        pipe._timer = _StageTimer(ctx.device)
+        pipe._timer.start()
+        outs = pipe._finish_files(ctx, metas, seg, emb, bounds, num_speakers, min_speakers, max_speakers, hook,
+                                  return_artifacts, classes=cls)
+        for meta, out in zip(metas, outs):
+            yield meta, out
+
+    def exchange(self, buf, plan):
+        """The one exchange step of the path: in-place all-gather of the packed per-rank blocks."""
+        mine = buf[self.rank * plan["blk"]: (self.rank + 1) * plan["blk"]]
+        timed = buf.is_cuda
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        if self.world > 1:
+            src = mine if buf.is_cuda else mine.clone()        # NCCL: in place; gloo (CPU tests) wants no aliasing
+            dist.all_gather_into_tensor(buf, src, group=self.group)
+        if timed:
+            e1.record()
+            self._events = (e0, e1)
+        self.last_collective = dict(bytes_sent=int(plan["blk"]), bytes_received=int(plan["blk"] * (self.world - 1)))
+
+    def owned_inputs(self, buf, plan):
+        """Inputs of the per-file stage for the files this rank owns (file g -> rank g mod world): embeddings and
+        classes of those files back to back, chunk bounds, global file indices."""
+        owned = [g for g in range(len(plan["files"])) if g % self.world == self.rank]
+        if not owned:
+            return None
+        embs, clss, bounds = [], [], [0]
+        views = {r: self.views(buf, plan, r) for r in {plan["files"][g]["rank"] for g in owned}}
+        for g in owned:
+            f = plan["files"][g]
+            e, c = views[f["rank"]]
+            embs.append(e[f["start"]: f["start"] + f["chunks"]])
+            clss.append(c[f["start"]: f["start"] + f["chunks"]])
+            bounds.append(bounds[-1] + f["chunks"])
+        return torch.cat(embs).contiguous(), torch.cat(clss).contiguous(), bounds, owned
+
+    def collective_ms(self):
+        """Device time of the last all-gather (CUDA events on the launching stream; call after a synchronize)."""
+        if self._events is None:
+            return None
+        return float(self._events[0].elapsed_time(self._events[1]))
 
 
 def apply_sharded(pipeline, file, group=None, **kwargs):

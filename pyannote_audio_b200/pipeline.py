@@ -357,16 +357,22 @@ class SpeakerDiarization:
         ctx = get_context(self.device)
         files = [self._audio.validate_file(f) for f in files]
         step_size = round(self._segmentation.step * self._embedding.sample_rate)
-        wavs, layouts, base = [], [], 0
+        raws, layouts, base = [], [], 0
         for f in files:
-            w, sr = self._audio(f)
-            off, valid, _, _ = chunk_layout(w.shape[1], ops.CHUNK, step_size)
-            layouts.append((base, off, valid, w.shape[1]))
-            wavs.append(w)
+            raw, sr, channel = self._audio.raw(f)
+            T = self._audio.num_samples_out(raw, sr)
+            off, valid, _, _ = chunk_layout(T, ops.CHUNK, step_size)
+            layouts.append((base, off, valid, T))
+            raws.append((raw, sr, channel))
             base += int(off[-1]) + ops.CHUNK
         wav_dev = torch.zeros(base, dtype=torch.float32, device=ctx.device)
-        for (b0, off, valid, T), w in zip(layouts, wavs):
-            wav_dev[b0: b0 + T].copy_(w[0], non_blocking=True)
+        for (b0, off, valid, T), (raw, sr, channel) in zip(layouts, raws):
+            if self._audio.needs_ingest(raw, sr, channel):
+                # multi-channel / other sample rate / int16 PCM: raw samples cross PCIe once, downmix + polyphase
+                # resampling run on the device (b200_audio_ingest; reference core/io.py:223-265 does this on the CPU)
+                self._audio.ingest(ctx, raw, sr, channel, out=wav_dev[b0: b0 + T])
+            else:
+                wav_dev[b0: b0 + T].copy_(raw[0], non_blocking=True)
         return dict(files=files, wav=wav_dev, layouts=layouts,
                     off=np.concatenate([b0 + off for b0, off, _, _ in layouts]),
                     valid=np.concatenate([valid for _, _, valid, _ in layouts]),
@@ -391,7 +397,7 @@ class SpeakerDiarization:
         self._timer.mark("embedding")
         # ---- clustering + reconstruction, batched across files -------------------------------------------------
         outs = self._finish_files(ctx, resident["files"], seg, emb, bounds, num_speakers, min_speakers, max_speakers,
-                                  hook, return_artifacts)
+                                  hook, return_artifacts, classes=cls)
         self._timer.report()
         for file, out in zip(resident["files"], outs):
             yield file, out
@@ -403,7 +409,7 @@ class SpeakerDiarization:
                                   hook, return_artifacts)[0]
 
     def _finish_files(self, ctx, files, seg, emb, bounds, num_speakers, min_speakers, max_speakers, hook,
-                      return_artifacts):
+                      return_artifacts, classes=None):
         tm = self._timer
         F = len(files)
         chunks_sw = SlidingWindow(start=0.0, duration=self._segmentation.duration, step=self._segmentation.step)
@@ -479,6 +485,8 @@ class SpeakerDiarization:
             if return_artifacts:
                 c0, c1 = int(bounds[fi]), int(bounds[fi + 1])
                 artifacts = dict(segmentations=seg[c0:c1], count=counts[fi], embeddings=emb[c0:c1])
+                if classes is not None:
+                    artifacts["classes"] = classes[c0:c1]          # powerset class ids (C,589) u8
             if silent[fi]:
                 output = DiarizeOutput(Annotation(uri=uri), Annotation(uri=uri),
                                        np.zeros((0, self._embedding.dimension)))

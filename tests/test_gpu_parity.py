@@ -42,6 +42,21 @@ def oracle_models():
     return seg.eval(), emb.eval()
 
 
+LOW_MARGIN = 1e-4          # top-2 log-probability margin under which an argmax flip is fp32 reordering noise
+
+
+def _class_mismatches(cls, ref_logp):
+    """(mismatch mask, low-margin mask) of CUDA class ids against the oracle's log-probabilities."""
+    top2 = np.sort(ref_logp, axis=-1)
+    low = (top2[..., -1] - top2[..., -2]) < LOW_MARGIN
+    return cls != ref_logp.argmax(-1), low
+
+
+def _report(name, mism, low):
+    print(f"[parity] {name}: {mism.size} frames, {int(low.sum())} low-margin (< {LOW_MARGIN:g}), "
+          f"{int(mism.sum())} class mismatches ({int((mism & low).sum())} of them low-margin)")
+
+
 def _device_wave(wav, dev):
     from pyannote_audio_b200.inference import chunk_layout
 
@@ -89,13 +104,13 @@ def test_segmentation_parity(ctx, dev, oracle_models):
     np.testing.assert_allclose(sinc, ref_sinc, atol=2e-4, rtol=0)
     cls, logp = ctx.seg_forward(buf, off, valid, return_logp=True)
     np.testing.assert_allclose(logp.cpu().numpy(), ref_logp, atol=2e-4, rtol=0)
-    ref_cls = ref_logp.argmax(-1)
-    top2 = np.sort(ref_logp, axis=-1)
-    margin = top2[..., -1] - top2[..., -2]
-    mism = cls.cpu().numpy() != ref_cls
-    # bit-identical decisions wherever the oracle's own top-2 margin is above fp32 reordering noise
-    assert not (mism & (margin > 1e-3)).any()
-    assert mism.mean() < 1e-3
+    # bit-identical class decisions; frames whose oracle top-2 log-prob margin is below LOW_MARGIN (fp32
+    # summation-order noise, SURVEY.md section 7 hard part 1) are reported separately and are the ONLY place a
+    # difference is tolerated
+    mism, low = _class_mismatches(cls.cpu().numpy(), ref_logp)
+    _report("segmentation_parity 37.3 s", mism, low)
+    assert not (mism & ~low).any(), "class decision differs from the oracle on a frame with a clear margin"
+    assert mism.sum() == 0 or mism.sum() <= low.sum()
     # a chunk computed inside a batch equals the same chunk computed alone (bitwise: deterministic kernels)
     alone = ctx.seg_forward(buf, off[5:6], valid[5:6])
     assert torch.equal(alone[0], cls[5])
@@ -288,37 +303,111 @@ def pipeline(dev):
     return SpeakerDiarization(segmentation=seg, embedding=emb, plda=syn.make_plda(2), device=dev)
 
 
-def test_pipeline_end_to_end_vs_oracle(pipeline, oracle_models):
+def _rows(x):
+    return [tuple(int(v) for v in r) for r in x]
+
+
+def _compare_with_oracle(art, out, ref, independent):
+    """Integer outputs of the CUDA pipeline against an oracle run (bit-exact)."""
+    assert np.array_equal(art["count"].cpu().numpy(), ref.count.data[:, 0])
+    assert np.array_equal(art["hard_clusters"], ref.hard_clusters), ("independent" if independent else "re-fed")
+    assert np.array_equal(art["discrete"][:, : ref.discrete.data.shape[1]], ref.discrete.data.astype(np.uint8))
+    assert not art["discrete"][:, ref.discrete.data.shape[1]:].any()
+    assert np.array_equal(art["exclusive"][:, : ref.exclusive.data.shape[1]], ref.exclusive.data.astype(np.uint8))
+    assert _rows(art["segments"]) == _rows(ref.segments)                          # integer frame boundaries
+    assert _rows(art["exclusive_segments"]) == _rows(ref.exclusive_segments)
+    got = [(s.start, s.end, lab) for s, _, lab in out.speaker_diarization.itertracks(yield_label=True)]
+    assert got == ref.times
+    gotx = [(s.start, s.end, lab) for s, _, lab in out.exclusive_speaker_diarization.itertracks(yield_label=True)]
+    assert gotx == ref.exclusive_times
+
+
+def _e2e_case(pipeline, oracle_models, wav, name, exclude_overlap=False, min_duration_off=0.0, emb_oracle=True):
+    """Runs one file through apply_batch and through the oracle.  The comparison is with the fully INDEPENDENT
+    oracle run (its own segmentation, its own fp32 embeddings); only if a low-margin frame flipped (reported) the
+    integer stages are compared with the oracle re-fed with the CUDA segmentation instead."""
     seg_model, emb_model = oracle_models
     plda = P.PLDA(**syn.make_plda(2))
-    wav = syn.make_conversation(75.0, seed=1234)
-    file = {"waveform": wav, "sample_rate": 16000, "uri": "synthetic"}
-    seen = []
-    (_, (out, art)), = list(pipeline.apply_batch([file], hook=lambda name, *a, **k: seen.append(name),
-                                                 return_artifacts=True))
-    assert seen[:3] == ["segmentation", "speaker_counting", "embeddings"] and "discrete_diarization" in seen
-    ref = P.apply(seg_model, emb_model, plda, wav)
+    file = {"waveform": wav, "sample_rate": 16000, "uri": name}
+    pipeline.embedding_exclude_overlap = exclude_overlap
+    pipeline.min_duration_off = min_duration_off
+    try:
+        seen = []
+        (_, (out, art)), = list(pipeline.apply_batch(
+            [file], hook=lambda step, artifact, **k: seen.append((step, artifact is None)), return_artifacts=True))
+    finally:
+        pipeline.embedding_exclude_overlap = False
+        pipeline.min_duration_off = 0.0
+    names = [n for n, progress in seen if not progress]
+    assert names == ["segmentation", "speaker_counting", "embeddings", "discrete_diarization"]
+    assert ("segmentation", True) in seen and ("embeddings", True) in seen            # progress calls fire too
+    ref_seg, ref_logp = P.slide(seg_model, wav, return_logp=True)
     seg = art["segmentations"].cpu().numpy().astype(np.float32)
-    assert seg.shape == ref.segmentations.data.shape
-    mism = (seg != ref.segmentations.data).any(-1).mean()
-    assert mism < 1e-3
+    assert seg.shape == ref_seg.data.shape
+    cls = art["classes"].cpu().numpy()
+    mism, low = _class_mismatches(cls, ref_logp)
+    _report(name, mism, low)
+    assert not (mism & ~low).any()
+    identical = not mism.any()
+    assert identical == bool((seg == ref_seg.data).all())
     emb = art["embeddings"].cpu().numpy()
-    cos = (emb * ref.embeddings).sum(-1) / (np.linalg.norm(emb, axis=-1) * np.linalg.norm(ref.embeddings, axis=-1))
-    assert (1 - cos).max() <= 1e-3
-    # downstream of the networks everything is exact: feed the CUDA segmentations/embeddings to the oracle's
-    # clustering + reconstruction and require bit-identical integer outputs
-    ref2 = P.apply(seg_model, emb_model, plda, wav, segmentations=P.SWF(seg, P.SW(0.0, 10.0, 1.0)), embeddings=emb)
-    assert np.array_equal(art["count"].cpu().numpy(), ref2.count.data[:, 0])
-    assert _same_partition(art["hard_clusters"].ravel().tolist(), ref2.hard_clusters.ravel().tolist())
-    assert np.array_equal(art["hard_clusters"], ref2.hard_clusters)
-    assert np.array_equal(art["discrete"][:, : ref2.discrete.data.shape[1]], ref2.discrete.data.astype(np.uint8))
-    assert [tuple(r) for r in art["segments"]] == ref2.segments                  # integer frame boundaries
-    assert [tuple(r) for r in art["exclusive_segments"]] == ref2.exclusive_segments
-    got = [(s.start, s.end, lab) for s, _, lab in out.speaker_diarization.itertracks(yield_label=True)]
-    assert got == ref2.times
+    if emb_oracle:
+        ref = P.apply(seg_model, emb_model, plda, wav, segmentations=ref_seg if identical else P.SWF(seg, ref_seg.sw),
+                      exclude_overlap=exclude_overlap, min_duration_off=min_duration_off)
+        cos = (emb * ref.embeddings).sum(-1) / (np.linalg.norm(emb, axis=-1) * np.linalg.norm(ref.embeddings, axis=-1))
+        assert (1 - cos).max() <= 1e-3, f"embedding cosine distance {np.nanmax(1 - cos)}"
+        _compare_with_oracle(art, out, ref, independent=identical)
+        a, b = out.speaker_embeddings, ref.speaker_embeddings
+        assert a.shape == b.shape
+        if a.size:
+            ccos = (a * b).sum(-1) / np.maximum(np.linalg.norm(a, axis=-1) * np.linalg.norm(b, axis=-1), 1e-30)
+            assert (1 - ccos).max() <= 1e-3
+    # and with the CUDA embeddings fed to the oracle's clustering: everything downstream is exact arithmetic
+    ref2 = P.apply(seg_model, emb_model, plda, wav, segmentations=P.SWF(seg, ref_seg.sw), embeddings=emb,
+                   exclude_overlap=exclude_overlap, min_duration_off=min_duration_off)
+    _compare_with_oracle(art, out, ref2, independent=False)
     np.testing.assert_allclose(out.speaker_embeddings, ref2.speaker_embeddings, rtol=1e-6, atol=1e-8)
-    if mism == 0:   # whole pipeline identical to the fully independent oracle run as well
-        assert np.array_equal(art["count"].cpu().numpy(), ref.count.data[:, 0])
+    return out, art
+
+
+def test_pipeline_end_to_end_vs_oracle(pipeline, oracle_models):
+    _e2e_case(pipeline, oracle_models, syn.make_conversation(75.0, seed=1234), "e2e-75s")
+
+
+def test_pipeline_exclude_overlap_and_min_duration_off(pipeline, oracle_models):
+    """embedding_exclude_overlap=True (the setting published pipelines ship with, speaker_diarization.py:375-391)
+    and segmentation.min_duration_off > 0 (Binarize -> Annotation.support, utils/signal.py:307-310)."""
+    wav = syn.make_conversation(48.0, seed=77)
+    _e2e_case(pipeline, oracle_models, wav, "exclude-overlap", exclude_overlap=True)
+    out, art = _e2e_case(pipeline, oracle_models, wav, "min-duration-off", min_duration_off=0.5)
+    assert len(out.speaker_diarization) <= len(art["segments"])
+    # the overlap-free masks differ from the plain ones on this file (otherwise the first case proves nothing)
+    seg = art["segmentations"]
+    assert bool((seg.sum(dim=2) > 1).any())
+
+
+def test_bench_workload_file_vs_oracle(pipeline, oracle_models):
+    """BASELINE.json configs[4]: one 10-minute file of the bench workload (bench.py seed 1000) through apply_batch;
+    591 chunks of segmentation against the oracle, then clustering + reconstruction + segments exact with the CUDA
+    embeddings fed to the oracle (its ResNet would need ~15 min of CPU for 1773 embeddings)."""
+    wav = syn.make_conversation(600.0, seed=1000)
+    _, art = _e2e_case(pipeline, oracle_models, wav, "bench-file-600s", emb_oracle=False)
+    assert art["segmentations"].shape[0] == 591
+    # a sample of the embeddings against the fp32 oracle (cosine <= 1e-3)
+    _, emb_model = oracle_models
+    seg = art["segmentations"].cpu().numpy().astype(np.float32)
+    pick = [0, 137, 590]
+    sub = P.SWF(seg, P.SW(0.0, 10.0, 1.0))
+    masks = P.embedding_masks(sub)
+    with torch.inference_mode():
+        for c in pick:
+            chunk = P.crop_pad(wav, float(c), float(c) + 10.0)[None]
+            ref = emb_model.forward_embedding(emb_model.forward_frames(chunk), weights=torch.from_numpy(masks[c:c + 1]))
+            got = art["embeddings"][c].cpu().numpy()
+            r = ref[0].numpy()
+            ok = np.linalg.norm(r, axis=-1) > 0
+            cos = (got * r).sum(-1)[ok] / (np.linalg.norm(got, axis=-1) * np.linalg.norm(r, axis=-1))[ok]
+            assert (1 - cos).max() <= 1e-3
 
 
 def test_pipeline_edge_cases(pipeline):
@@ -332,30 +421,80 @@ def test_pipeline_edge_cases(pipeline):
     assert len(one.speaker_diarization.labels()) <= 1
 
 
-def test_full_size_properties(ctx, dev):
-    """BASELINE.json configs[2]/[3] sizes through size-independent properties (oracle would take hours on CPU)."""
-    wav = syn.make_conversation(3600.0, seed=99)
+def test_cfg2_sincnet_frontend_1024_chunks(ctx, dev, oracle_models):
+    """BASELINE.json configs[1]: SincNet + Conv1d front-end on a 1024-chunk batch against the oracle (full size)."""
+    seg_model, _ = oracle_models
+    wav = syn.make_conversation(10.0 + 1023.0, seed=2024)
     buf, off, valid = _device_wave(wav, dev)
-    assert len(off) == 3591
-    cls = ctx.seg_forward(buf, off, valid)
-    assert cls.shape == (3591, 589) and int(cls.max()) <= 6
-    assert torch.equal(cls, ctx.seg_forward(buf, off, valid))                       # deterministic / idempotent
-    sub = ctx.seg_forward(buf, off[1000:1010], valid[1000:1010])
-    assert torch.equal(sub, cls[1000:1010])                                          # batch invariance
-    seg = ctx.powerset_to_multilabel(cls)
-    sf = P.chunk_start_frames(3591, FRAMES)
-    F = FRAMES.closest_frame(10.0 + 3590 * 1.0 + 0.5 * FRAMES.duration) + 1
-    assert F == 213334                                                               # SURVEY.md section 8 a9
-    count = ctx.speaker_count(seg, sf, F)
-    assert int(count.max()) <= 2                                                     # powerset: at most 2 simultaneous
-    masks = seg.permute(0, 2, 1).contiguous()
-    emb = ctx.emb_forward(buf, off, valid, masks)
+    assert len(off) == 1024
+    got = ctx.sincnet_forward(buf, off, valid)
+    assert got.shape == (1024, 589, 60)
+    chunks = P.chunk_waveform(wav)
+    worst = 0.0
+    with torch.inference_mode():
+        for c0 in range(0, 1024, 64):
+            ref = seg_model.sincnet(chunks[c0:c0 + 64]).transpose(1, 2)
+            worst = max(worst, float((got[c0:c0 + 64].cpu() - ref).abs().max()))
+    print(f"[parity] cfg2: 1024 chunks, max |sincnet - oracle| = {worst:.2e}")
+    assert worst <= 2e-4
+    assert torch.equal(got[100:108], ctx.sincnet_forward(buf, off[100:108], valid[100:108]))     # batch invariance
+
+
+def test_cfg3_cfg4_one_hour_file_vs_oracle(pipeline, ctx, dev, oracle_models):
+    """BASELINE.json configs[2] + configs[3] at full size.  One synthetic hour (3591 chunks, 10 773 embedding slots):
+    * PyanNet sliding window: class ids of all 3591 x 589 frames against the oracle (bit-identical outside the
+      reported low-margin set), speaker count on the 213 334-frame grid;
+    * embeddings -> clean-frame filter -> centroid linkage at n > 4096 (the global-memory state path) -> fcluster ->
+      PLDA -> VBx -> cosine cdist -> constrained assignment -> reconstruction -> segments, all bit-exact against the
+      oracle (scipy linkage / fcluster / cdist / linear_sum_assignment, the reference's VBx) fed with the same
+      embeddings; a sample of the embeddings and the full 10 773^2 cosine-distance matrix against the oracle."""
+    from scipy.cluster.hierarchy import fcluster, linkage
+    from scipy.spatial.distance import cdist
+
+    from pyannote_audio_b200 import ops
+
+    _, emb_model = oracle_models
+    wav = syn.make_conversation(3600.0, seed=99)
+    out, art = _e2e_case(pipeline, oracle_models, wav, "cfg3-one-hour", emb_oracle=False)
+    assert art["segmentations"].shape == (3591, 589, 3) and art["count"].shape == (213334,)     # SURVEY section 8 a9
+    assert int(art["count"].max()) <= 2                                                          # powerset: <= 2
+    emb = art["embeddings"]
     assert emb.shape == (3591, 3, 256) and bool(torch.isfinite(emb).all())
-    sub = ctx.emb_forward(buf, off[2000:2003], valid[2000:2003], masks[2000:2003])
-    assert torch.equal(sub, emb[2000:2003])
-    # cosine-distance matrix on ~10k embeddings: symmetric, zero diagonal, within [0, 2]
+    # cfg4: cosine-distance matrix of the ~10k embeddings against scipy
     x = emb.reshape(-1, 256).double()
-    d = ctx.cdist_cosine(x, x)
+    d = ctx.cdist_cosine(x, x).cpu().numpy()
+    xn = x.cpu().numpy()
     assert d.shape == (10773, 10773)
-    assert float((d - d.T).abs().max()) < 1e-12 and float(d.diagonal().abs().max()) < 1e-9
-    assert float(d.min()) > -1e-9 and float(d.max()) <= 2.0 + 1e-9
+    for r0 in range(0, 10773, 2048):
+        np.testing.assert_allclose(d[r0:r0 + 2048], cdist(xn[r0:r0 + 2048], xn, "cosine"), rtol=0, atol=1e-12)
+    del d
+    # cfg4: a sample of the embeddings against the fp32 oracle network (cosine <= 1e-3)
+    seg = art["segmentations"].cpu().numpy().astype(np.float32)
+    masks = P.embedding_masks(P.SWF(seg, P.SW(0.0, 10.0, 1.0)))
+    pick = list(range(0, 3591, 449))
+    with torch.inference_mode():
+        chunks = torch.stack([P.crop_pad(wav, float(c), float(c) + 10.0) for c in pick])
+        ref = emb_model.forward_embedding(emb_model.forward_frames(chunks), weights=torch.from_numpy(masks[pick])).numpy()
+    got = emb[pick].cpu().numpy()
+    ok = np.linalg.norm(ref, axis=-1) > 0
+    cos = (got * ref).sum(-1)[ok] / (np.linalg.norm(got, axis=-1) * np.linalg.norm(ref, axis=-1))[ok]
+    print(f"[parity] cfg4: {int(ok.sum())} sampled embeddings, max cosine distance to the fp32 oracle {float((1 - cos).max()):.2e}")
+    assert (1 - cos).max() <= 1e-3
+    # cfg4: the linkage itself at n > 4096 against scipy (heights + partitions at several thresholds)
+    train, _, _ = P.filter_embeddings(emb.cpu().numpy(), seg)
+    n = train.shape[0]
+    assert n > 4096, f"only {n} training embeddings: the large-n linkage path is not exercised"
+    tn = train.astype(np.float64)
+    tn = tn / np.linalg.norm(tn, axis=1, keepdims=True)
+    Zref = linkage(tn, "centroid", "euclidean")
+    Z = ctx.linkage_centroid(torch.from_numpy(train.astype(np.float64)).to(dev), normalize=True).cpu().numpy()
+    np.testing.assert_allclose(np.sort(Z[:, 2]), np.sort(Zref[:, 2]), rtol=1e-9, atol=1e-12)
+    for t in (0.3, 0.6, 0.9):
+        assert _same_partition(fcluster(Zref, t, "distance"), ops.fcluster_distance(Z, t))
+    print(f"[parity] cfg4: linkage n={n} heights and partitions identical to scipy")
+    # size-independent properties on top: idempotence and batch invariance at this size
+    buf, off, valid = _device_wave(wav, dev)
+    cls = art["classes"]
+    assert torch.equal(cls[1000:1010], ctx.seg_forward(buf, off[1000:1010], valid[1000:1010]))
+    m = art["segmentations"].permute(0, 2, 1).contiguous()
+    assert torch.equal(ctx.emb_forward(buf, off[2000:2003], valid[2000:2003], m[2000:2003]), emb[2000:2003])

@@ -59,3 +59,54 @@ def test_sharded_forward_all_gather_world2(C):
         assert p.exitcode == 0
     results = sorted(q.get(timeout=10) for _ in range(2))
     assert results == [(0, True), (1, True)]
+
+
+def _pool_worker(rank, world, port, q):
+    """ChunkPool host logic on gloo: ragged files per rank, packed in-place all-gather, round-robin ownership."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pyannote_audio_b200.parallel import ChunkPool
+
+    per_rank = {0: [5, 1, 17], 1: [9, 4]}                   # chunks per file; rank 1 has fewer chunks in total
+    g = torch.Generator().manual_seed(1)
+    truth = {}
+    for r in range(world):
+        for i, c in enumerate(per_rank[r]):
+            truth[(r, i)] = (torch.randn(c, 3, 256, generator=g), torch.randint(0, 7, (c, 589), generator=g,
+                                                                                dtype=torch.uint8))
+    pool = ChunkPool(pipeline=None)
+    layouts = [(0, np.zeros(c), None, 160000 + 16000 * (c - 1)) for c in per_rank[rank]]
+    plan = pool.plan(layouts, [f"r{rank}_f{i}" for i in range(len(layouts))])
+    ok = plan["counts"] == [23, 13] and plan["cmax"] == 23 and plan["blk"] % 16 == 0
+    ok = ok and [f["uri"] for f in plan["files"]] == ["r0_f0", "r0_f1", "r0_f2", "r1_f0", "r1_f1"]
+    buf = torch.zeros(world * plan["blk"], dtype=torch.uint8)
+    emb, cls = pool.views(buf, plan, rank)
+    pos = 0
+    for i, c in enumerate(per_rank[rank]):                  # "the kernels write into this rank's slice"
+        emb[pos: pos + c] = truth[(rank, i)][0]
+        cls[pos: pos + c] = truth[(rank, i)][1]
+        pos += c
+    pool.exchange(buf, plan)
+    e, c, bounds, owned = pool.owned_inputs(buf, plan)
+    ok = ok and owned == [gi for gi in range(5) if gi % world == rank]
+    keys = [(0, 0), (0, 1), (0, 2), (1, 0), (1, 1)]
+    for j, gi in enumerate(owned):
+        te, tc = truth[keys[gi]]
+        ok = ok and torch.equal(e[bounds[j]: bounds[j + 1]], te) and torch.equal(c[bounds[j]: bounds[j + 1]], tc)
+    ok = ok and pool.last_collective["bytes_sent"] == plan["blk"]
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_chunk_pool_all_gather_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_pool_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert sorted(q.get(timeout=10) for _ in range(2)) == [(0, True), (1, True)]
