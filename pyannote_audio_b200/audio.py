@@ -33,14 +33,12 @@ class Audio:
                     raise ValueError("'waveform' must be provided as a (channel, time) torch Tensor.")
                 if file.get("sample_rate", None) is None:
                     raise ValueError("'waveform' must be provided with their 'sample_rate'.")
-                file = dict(file)
-                file.setdefault("uri", "waveform")
-                return file
+                file.setdefault("uri", "waveform")       # in place like the reference (io.py:193): hooks store
+                return file                              # their artifacts in the caller's mapping
             if "audio" in file:
                 path = Path(file["audio"])
                 if not path.is_file():
                     raise ValueError(f"File {path} does not exist")
-                file = dict(file)
                 file.setdefault("uri", path.stem)
                 return file
             raise ValueError("Neither 'waveform' nor 'audio' is available for this file.")
