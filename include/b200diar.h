@@ -174,7 +174,11 @@ int b200_frame_transitions(b200_ctx* ctx, const uint8_t* discrete, int32_t num_f
 int b200_clean_frames(b200_ctx* ctx, const uint8_t* seg, int32_t num_chunks, int32_t* clean, uint8_t* active,
                       void* stream);
 /* linkage(X, "centroid", "euclidean") (scipy, called at clustering.py:600-602 and :374-376): x[n][dim] fp64 device;
- * rows are L2-normalised first when normalize != 0; Z[n-1][4] fp64 device in scipy's format. */
+ * normalize: 0 = rows as given, 1 = L2-normalised in fp64, 2 = rows hold float32 values and are normalised exactly as
+ * numpy does on float32 embeddings (x / np.linalg.norm(x, axis=1, keepdims=True): float32 pairwise sum, float32
+ * sqrt and division; clustering.py:597-599) before widening; Z[n-1][4] fp64 device in scipy's format.
+ * Limits: n <= 32768 observations per problem (a dense n x n fp64 distance matrix lives in the ctx workspace: 8 n^2
+ * bytes, 8.6 GB at the limit); longer recordings must be clustered in windows by the caller. */
 int b200_linkage_centroid(b200_ctx* ctx, const double* x, int32_t n, int32_t dim, int32_t normalize, double* Z,
                           void* stream);
 /* the same for num_problems independent problems in ONE launch (one CTA each): rows of problem f are
@@ -184,6 +188,15 @@ int b200_linkage_centroid_batched(b200_ctx* ctx, const double* x, const int32_t*
                                   int32_t dim, int32_t normalize, double* Z, void* stream);
 /* fcluster(Z, t, criterion="distance") (clustering.py:604, 385): HOST arrays, labels[n] 1-based like scipy. */
 int b200_fcluster_distance(const double* Z, int32_t n, double t, int32_t* labels);
+/* PLDA.__call__ (core/plda.py:50-63; xvec_tf / plda_tf of utils/vbx.py:211-217): x[n][Din] fp64 device ->
+ * fea[n][L]; mean1[Din], mean2[Dout], lda[Din][Dout], mu[Dout], trT[Dout][L] (= plda_tr^T[:, :L]) fp64 device. */
+int b200_plda_transform(b200_ctx* ctx, const double* x, int32_t n, int32_t Din, int32_t Dout, int32_t L,
+                        const double* mean1, const double* mean2, const double* lda, const double* mu,
+                        const double* trT, double* fea, void* stream);
+/* VBx centroids (clustering.py:620-621): W = q[:, kept]; centroids[K][dim] = W^T train / sum(W): q[n][S], kept[K]
+ * (DEVICE int32 column indices), train[n][dim], all fp64 device. */
+int b200_weighted_centroids(b200_ctx* ctx, const double* q, int32_t n, int32_t S, const int32_t* kept, int32_t K,
+                            const double* train, int32_t dim, double* centroids, void* stream);
 /* cdist(a, b, "cosine") (clustering.py:645-655): a[m][dim], b[k][dim] fp64 device -> d[m][k] fp64 device. */
 int b200_cdist_cosine(b200_ctx* ctx, const double* a, int32_t m, const double* b, int32_t k, int32_t dim, double* d,
                       void* stream);

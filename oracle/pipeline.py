@@ -529,8 +529,8 @@ def vbx_clustering(embeddings, seg_data, plda: PLDA, threshold=0.6, Fa=0.07, Fb=
 def ahc_cluster(embeddings, method="centroid", threshold=0.0, min_cluster_size=0,
                 min_clusters=1, max_clusters=None, num_clusters=None, metric="cosine"):
     """AgglomerativeClustering.cluster (pipelines/clustering.py:330-480), legacy 3.1 path."""
-    embeddings = np.array(embeddings, dtype=np.float64)
-    num_embeddings, _ = embeddings.shape
+    embeddings = np.array(embeddings)          # a copy in the caller's dtype: the reference normalises IN PLACE, i.e.
+    num_embeddings, _ = embeddings.shape       # in float32 when called through BaseClustering.__call__ (:371-373)
     max_clusters = max_clusters if max_clusters is not None else num_embeddings
     min_cluster_size = min(min_cluster_size, max(1, round(0.1 * num_embeddings)))
     if num_embeddings == 1:

@@ -69,14 +69,9 @@ class PLDA:
         return self._dev[key]
 
     def transform(self, x: torch.Tensor) -> torch.Tensor:
-        """(n, 256) float64 device tensor -> (n, lda_dimension) (vbx.py:211-217)."""
+        """(n, 256) float64 device tensor -> (n, lda_dimension) (vbx.py:211-217), one kernel (b200_plda_transform)."""
         c = self._consts(x.device)
-        din, dout = c["lda"].shape
-        y = x - c["mean1"]
-        y = np.sqrt(din) * (y / torch.linalg.norm(y, dim=1, keepdim=True))
-        y = y @ c["lda"] - c["mean2"]
-        y = np.sqrt(dout) * (y / torch.linalg.norm(y, dim=1, keepdim=True))
-        return (y - c["mu"]) @ c["trT"]
+        return get_context(x.device).plda_transform(x.double(), c["mean1"], c["mean2"], c["lda"], c["mu"], c["trT"])
 
     def __call__(self, embeddings) -> np.ndarray:
         if isinstance(embeddings, torch.Tensor):
@@ -240,7 +235,8 @@ class VBxClustering(BaseClustering):
         else:
             x_link = torch.cat([train_all[row_off[f]: row_off[f + 1]] for f in todo])
             link_off = sub_off
-        Z_all = ctx.linkage_centroid_batched(x_link, link_off, normalize=True).cpu().numpy()   # sync
+        # embeddings are float32 network outputs: normalise them exactly as numpy does on float32 (clustering.py:597-599)
+        Z_all = ctx.linkage_centroid_batched(x_link, link_off, normalize="float32").cpu().numpy()   # sync
         tick("linkage")
         ahcs, S_f, zpos = {}, {}, 0
         for f in todo:
@@ -278,8 +274,7 @@ class VBxClustering(BaseClustering):
             train = x_link[rpos: rpos + n]
             gpos, spos, rpos = gpos + n * S, spos + S, rpos + n
             kept = np.nonzero(sp > 1e-7)[0]
-            W = q[:, torch.as_tensor(kept, device=dev)]
-            centroids = (W.T @ train) / W.sum(0, keepdim=True).T
+            centroids = ctx.weighted_centroids(q, torch.as_tensor(kept, dtype=torch.int32), train)
             constrained = self.constrained_assignment
             auto_num = centroids.shape[0]
             nc = num_clusters
@@ -291,10 +286,11 @@ class VBxClustering(BaseClustering):
                 from sklearn.cluster import KMeans
 
                 constrained = False
-                normed = (train / torch.linalg.norm(train, dim=1, keepdim=True)).cpu().numpy()
+                tr = train.cpu().numpy().astype(np.float32)       # the float32 rows the reference works on (:629-642)
+                normed = tr / np.linalg.norm(tr, axis=1, keepdims=True)
                 km = KMeans(n_clusters=int(nc), n_init=3, random_state=42, copy_x=False).fit_predict(normed)
-                tr = train.cpu().numpy()
-                centroids = torch.from_numpy(np.vstack([np.mean(tr[km == k], axis=0) for k in range(int(nc))])).to(dev)
+                centroids = torch.from_numpy(np.vstack([np.mean(tr[km == k], axis=0)
+                                                        for k in range(int(nc))]).astype(np.float64)).to(dev)
             hard, soft = self._assign(ctx, emb64_all[c0:c1], centroids.contiguous(), active_all[c0:c1], constrained)
             results[f].update(hard=hard, soft=soft, centroids=centroids, active=active_all[c0:c1], q=q, sp=sp,
                               train=train, fea=fea[rpos - n: rpos], trivial=False)
@@ -338,14 +334,17 @@ class AgglomerativeClustering(BaseClustering):
         if self.method != "centroid":
             raise NotImplementedError("device linkage implements method='centroid' (the pyannote default)")
         ctx = self._ctx()
-        embeddings = np.array(embeddings, dtype=np.float64)
+        embeddings = np.array(embeddings)                   # copy; the reference normalises in the caller's dtype
+        if embeddings.dtype not in (np.float32, np.float64):
+            embeddings = embeddings.astype(np.float64)
+        f32 = embeddings.dtype == np.float32
         num_embeddings, _ = embeddings.shape
         max_clusters = max_clusters if max_clusters is not None else num_embeddings
         min_cluster_size = min(self.min_cluster_size, max(1, round(0.1 * num_embeddings)))
         if num_embeddings == 1:
             return np.zeros((1,), dtype=np.uint8)
-        x = torch.from_numpy(embeddings).to(ctx.device)
-        dendrogram = ctx.linkage_centroid(x, normalize=True).cpu().numpy()
+        x = torch.from_numpy(embeddings.astype(np.float64)).to(ctx.device)
+        dendrogram = ctx.linkage_centroid(x, normalize="float32" if f32 else True).cpu().numpy()
         with np.errstate(divide="ignore", invalid="ignore"):
             embeddings /= np.linalg.norm(embeddings, axis=-1, keepdims=True)
         clusters = ops.fcluster_distance(dendrogram, self.threshold) - 1
@@ -384,7 +383,8 @@ class AgglomerativeClustering(BaseClustering):
             return clusters
         large_c = np.vstack([np.mean(embeddings[clusters == k], axis=0) for k in large])
         small_c = np.vstack([np.mean(embeddings[clusters == k], axis=0) for k in small])
-        d = ctx.cdist_cosine(torch.from_numpy(large_c).to(ctx.device), torch.from_numpy(small_c).to(ctx.device))
+        d = ctx.cdist_cosine(torch.from_numpy(large_c.astype(np.float64)).to(ctx.device),
+                             torch.from_numpy(small_c.astype(np.float64)).to(ctx.device))
         for sk, lk in enumerate(torch.argmin(d, dim=0).cpu().numpy()):
             clusters[clusters == small[sk]] = large[lk]
         _, clusters = np.unique(clusters, return_inverse=True)
@@ -405,10 +405,12 @@ class AgglomerativeClustering(BaseClustering):
             hard = np.zeros((num_chunks, num_speakers), dtype=np.int8)
             soft = np.ones((num_chunks, num_speakers, 1))
             return hard, soft, train.mean(dim=0, keepdim=True).cpu().numpy()
-        train_clusters = self.cluster(train.cpu().numpy(), min_clusters=min_clusters, max_clusters=max_clusters,
+        train32 = train.cpu().numpy().astype(np.float32)     # exact: the rows are float32 network outputs
+        train_clusters = self.cluster(train32, min_clusters=min_clusters, max_clusters=max_clusters,
                                       num_clusters=num_clusters)
         K = int(train_clusters.max()) + 1
-        lab = torch.from_numpy(train_clusters.astype(np.int64)).to(ctx.device)
-        centroids = torch.stack([train[lab == k].mean(dim=0) for k in range(K)])
+        # centroids = float32 means of the float32 rows, like assign_embeddings (clustering.py:182-188)
+        centroids = torch.from_numpy(np.vstack([np.mean(train32[train_clusters == k], axis=0)
+                                                for k in range(K)]).astype(np.float64)).to(ctx.device)
         hard, soft = self._assign(ctx, emb64, centroids.contiguous(), active, self.constrained_assignment)
         return hard.cpu().numpy(), soft.cpu().numpy(), centroids.cpu().numpy()

@@ -191,10 +191,12 @@ int make_conv(b200_ctx* ctx, const b200_conv_bn& src, int cin, int cout, int k, 
             w4[(((size_t)kw * 3 + kh) * C + co) * C + ci] = w[((size_t)(kh * 3 + kw) * cout + co) * cin + ci];
     if ((rc = upload(ctx, w4, &L->w4))) return rc;
   }
-  if (k == 3 && stride == 1 && cout >= 128) {   // copy for the channels-as-M kernel (rows padded to 128)
+  if ((k == 3 && stride == 1 && cout >= 128) || stride == 2) {
+    // copy for the channels-as-M kernel (rows padded to 128): wide stride-1 convs, the stride-2 convs and the
+    // 1x1 stride-2 shortcuts
     const int rows = (cout + 127) / 128 * 128;
-    std::vector<__half> w3((size_t)9 * rows * cin, __float2half(0.f));
-    for (int t = 0; t < 9; ++t)
+    std::vector<__half> w3((size_t)k * k * rows * cin, __float2half(0.f));
+    for (int t = 0; t < k * k; ++t)
       for (int co = 0; co < cout; ++co)
         for (int ci = 0; ci < cin; ++ci) w3[((size_t)t * rows + co) * cin + ci] = w[((size_t)t * cout + co) * cin + ci];
     if ((rc = upload(ctx, w3, &L->w3))) return rc;
@@ -835,7 +837,9 @@ int b200_linkage_centroid_batched(b200_ctx* ctx, const double* x, const int32_t*
   B200_CHECK(ctx && x && row_offsets && Z && num_problems >= 1 && dim >= 1, B200_ERR_INVALID, "bad arguments");
   for (int f = 0; f < num_problems; ++f)
     B200_CHECK(row_offsets[f + 1] >= row_offsets[f] && row_offsets[f + 1] - row_offsets[f] <= 32768, B200_ERR_INVALID,
-               "linkage: bad row offsets / problem too large");
+               "linkage: problem %d has %d observations (row offsets must be non-decreasing, at most 32768 per problem "
+               "= about 3 h of audio at a 1 s step: cluster longer recordings in windows)", f,
+               (int)(row_offsets[f + 1] - row_offsets[f]));
   DeviceGuard g(ctx->device);
   int rc = ensure_ws(ctx, linkage_workspace_bytes_batched(row_offsets, num_problems, dim));
   if (rc) return rc;
@@ -853,6 +857,27 @@ int b200_linkage_centroid(b200_ctx* ctx, const double* x, int32_t n, int32_t dim
 int b200_fcluster_distance(const double* Z, int32_t n, double t, int32_t* labels) {
   B200_CHECK(Z && labels && n >= 1, B200_ERR_INVALID, "bad arguments");
   return fcluster_distance(Z, n, t, labels);
+}
+
+int b200_plda_transform(b200_ctx* ctx, const double* x, int32_t n, int32_t Din, int32_t Dout, int32_t L,
+                        const double* mean1, const double* mean2, const double* lda, const double* mu,
+                        const double* trT, double* fea, void* stream) {
+  B200_CHECK(ctx && x && mean1 && mean2 && lda && mu && trT && fea && n >= 0 && Din >= 1 && Dout >= 1 && L >= 1 &&
+                 L <= Dout && Din + Dout <= 4096, B200_ERR_INVALID, "bad arguments");
+  if (n == 0) return B200_OK;
+  DeviceGuard g(ctx->device);
+  ctx->launches += 1;
+  return plda_transform(x, n, Din, Dout, L, mean1, mean2, lda, mu, trT, fea, (cudaStream_t)stream);
+}
+
+int b200_weighted_centroids(b200_ctx* ctx, const double* q, int32_t n, int32_t S, const int32_t* kept, int32_t K,
+                            const double* train, int32_t dim, double* centroids, void* stream) {
+  B200_CHECK(ctx && q && kept && train && centroids && n >= 1 && S >= 1 && K >= 0 && dim >= 1, B200_ERR_INVALID,
+             "bad arguments");
+  if (K == 0) return B200_OK;
+  DeviceGuard g(ctx->device);
+  ctx->launches += 1;
+  return weighted_centroids(q, n, S, kept, K, train, dim, centroids, (cudaStream_t)stream);
 }
 
 int b200_cdist_cosine(b200_ctx* ctx, const double* a, int32_t m, const double* b, int32_t k, int32_t dim, double* d,

@@ -36,6 +36,45 @@ __global__ void normalize_rows_kernel(const double* __restrict__ x, double* __re
   for (int d = threadIdx.x; d < dim; d += blockDim.x) y[(size_t)i * dim + d] = x[(size_t)i * dim + d] / nrm;
 }
 
+// numpy's float32 `add.reduce` along a contiguous axis (pairwise summation, numpy/_core/src/umath/loops_utils.h.src):
+// blocks of <= 128 elements are summed with 8 interleaved accumulators combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)),
+// longer runs are split in halves (rounded down to a multiple of 8) recursively.  Elements here are float(x[i])^2.
+__device__ float np_pairwise_sumsq_f32(const double* __restrict__ x, int n) {
+  if (n < 8) {
+    float res = 0.f;
+    for (int i = 0; i < n; ++i) { const float v = (float)x[i]; res = __fadd_rn(res, __fmul_rn(v, v)); }
+    return res;
+  }
+  if (n <= 128) {
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float v = (float)x[j]; r[j] = __fmul_rn(v, v); }
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float v = (float)x[i + j]; r[j] = __fadd_rn(r[j], __fmul_rn(v, v)); }
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (; i < n; ++i) { const float v = (float)x[i]; res = __fadd_rn(res, __fmul_rn(v, v)); }
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return __fadd_rn(np_pairwise_sumsq_f32(x, n2), np_pairwise_sumsq_f32(x + n2, n - n2));
+}
+
+// rows holding float32 values (embeddings come out of the network as float32): exactly
+//   x / np.linalg.norm(x, axis=1, keepdims=True)   in float32, as the reference computes it (pipelines/clustering.py:
+// 597-599, 371-373 on float32 embeddings), then widened to the fp64 the linkage works in
+__global__ void normalize_rows_np_f32_kernel(const double* __restrict__ x, double* __restrict__ y, int n, int dim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* r = x + (size_t)i * dim;
+  const float nrm = __fsqrt_rn(np_pairwise_sumsq_f32(r, dim));
+  for (int d = 0; d < dim; ++d) y[(size_t)i * dim + d] = (double)__fdiv_rn((float)r[d], nrm);
+}
+
 __global__ void pdist_kernel(const double* __restrict__ x, double* __restrict__ D, int n, int dim) {
   // 16x16 tile of pairs per block, operands staged through shared memory in chunks of 32 dims
   __shared__ double xi[16][33], xj[16][33];
@@ -499,7 +538,8 @@ int linkage_centroid_batched(const double* x, const int* row_offsets, int nfiles
   B200_CUDA_OK(cudaMemcpyAsync(djobs, jobs.data(), sizeof(LinkJob) * nfiles, cudaMemcpyHostToDevice, st));
   const double* src = x;
   if (normalize && ntot > 0) {
-    normalize_rows_kernel<<<ntot, 128, 0, st>>>(x, xn, ntot, dim);
+    if (normalize == 2) normalize_rows_np_f32_kernel<<<ceil_div(ntot, 64), 64, 0, st>>>(x, xn, ntot, dim);
+    else normalize_rows_kernel<<<ntot, 128, 0, st>>>(x, xn, ntot, dim);
     src = xn;
   }
   for (int f = 0; f < nfiles; ++f) {
@@ -516,6 +556,97 @@ int linkage_centroid_batched(const double* x, const int* row_offsets, int nfiles
     link_attr = true;
   }
   linkage_centroid_kernel<<<nfiles, 1024, link_smem_bytes, st>>>(djobs, D, Z, nn_d, nn_i, size, id, alive, todo);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// PLDA transform (core/plda.py:50-63 over utils/vbx.py:211-217): one CTA per embedding
+//   y  = sqrt(Din)  * l2(x - mean1);   z = sqrt(Dout) * l2(lda^T y - mean2);   fea = (z - mu) . plda_tr^T [:, :L]
+// lda is [Din][Dout] row-major, trT is [Dout][L] row-major (= plda_tr.T[:, :L]); everything fp64 like numpy.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_256(double v, double* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(256) plda_transform_kernel(const double* __restrict__ x, int Din, int Dout, int L,
+                                                              const double* __restrict__ mean1,
+                                                              const double* __restrict__ mean2,
+                                                              const double* __restrict__ lda,
+                                                              const double* __restrict__ mu,
+                                                              const double* __restrict__ trT,
+                                                              double* __restrict__ fea) {
+  extern __shared__ double plda_sm[];
+  double* y = plda_sm;            // [Din]
+  double* z = plda_sm + Din;      // [Dout]
+  __shared__ double red[8];
+  const int i = blockIdx.x, tid = threadIdx.x;
+  double s = 0.0;
+  for (int d = tid; d < Din; d += blockDim.x) {
+    const double v = x[(size_t)i * Din + d] - mean1[d];
+    y[d] = v;
+    s += v * v;
+  }
+  const double n1 = sqrt(block_sum_256(s, red));
+  const double sc1 = sqrt((double)Din);
+  for (int d = tid; d < Din; d += blockDim.x) y[d] = sc1 * (y[d] / n1);
+  __syncthreads();
+  s = 0.0;
+  for (int j = tid; j < Dout; j += blockDim.x) {
+    double a = 0.0;
+    for (int d = 0; d < Din; ++d) a += lda[(size_t)d * Dout + j] * y[d];
+    a -= mean2[j];
+    z[j] = a;
+    s += a * a;
+  }
+  const double n2 = sqrt(block_sum_256(s, red));
+  const double sc2 = sqrt((double)Dout);
+  for (int j = tid; j < Dout; j += blockDim.x) z[j] = sc2 * (z[j] / n2) - mu[j];
+  __syncthreads();
+  for (int k = tid; k < L; k += blockDim.x) {
+    double a = 0.0;
+    for (int j = 0; j < Dout; ++j) a += z[j] * trT[(size_t)j * L + k];
+    fea[(size_t)i * L + k] = a;
+  }
+}
+
+int plda_transform(const double* x, int n, int Din, int Dout, int L, const double* mean1, const double* mean2,
+                   const double* lda, const double* mu, const double* trT, double* fea, cudaStream_t st) {
+  plda_transform_kernel<<<n, 256, (size_t)(Din + Dout) * sizeof(double), st>>>(x, Din, Dout, L, mean1, mean2, lda, mu,
+                                                                             trT, fea);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// VBx centroids (pipelines/clustering.py:620-621):  W = q[:, kept];  centroids = W^T train / sum_i W
+// one CTA per kept speaker, threads over the embedding dimension (coalesced rows of `train`)
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) weighted_centroids_kernel(const double* __restrict__ q, int n, int S,
+                                                                  const int* __restrict__ kept,
+                                                                  const double* __restrict__ train, int dim,
+                                                                  double* __restrict__ centroids) {
+  const int k = blockIdx.x, col = kept[k];
+  __shared__ double red[8];
+  double wsum = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) wsum += q[(size_t)i * S + col];
+  wsum = block_sum_256(wsum, red);
+  for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+    double a = 0.0;
+    for (int i = 0; i < n; ++i) a += q[(size_t)i * S + col] * train[(size_t)i * dim + d];
+    centroids[(size_t)k * dim + d] = a / wsum;
+  }
+}
+
+int weighted_centroids(const double* q, int n, int S, const int* kept, int K, const double* train, int dim,
+                       double* centroids, cudaStream_t st) {
+  weighted_centroids_kernel<<<K, 256, 0, st>>>(q, n, S, kept, train, dim, centroids);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }

@@ -471,7 +471,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // shared memory to keep NHWC stores (and residual loads) 16-byte vectorised.
 // ------------------------------------------------------------------------------------------------
 struct ConvV3Params {
-  int B, H, W, C_in, C_out;
+  int B, H, W, C_in, C_out;                // H, W: OUTPUT size (the input size only lives in the tensor map)
+  int stride, pad, ksize;                  // 3x3 pad 1 (stride 1 or 2) or 1x1 pad 0 (stride 2: the block shortcuts)
   int Ck, ncc, kblocks, bw, bh, tiles_w, tiles_h, m_tiles, num_items, relu;
   const float* bias;
   const __half* residual;
@@ -479,25 +480,28 @@ struct ConvV3Params {
   uint32_t a_bytes, b_bytes, stage_bytes, nstages, idesc, swizzle;
 };
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+constexpr int kV3Threads = 320;          // TMA warp, MMA warp, 2 x 4 epilogue warps (alternate 32-pixel chunks)
+constexpr uint32_t kV3Staging = 32768;   // 8 epilogue warps x (2 KB out + 2 KB residual) transpose buffers
+
+__global__ void __launch_bounds__(kV3Threads, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvV3Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
   // [0,64) full  [64,128) empty  [128,144) tfull  [144,160) tempty  [192] tmem slot  [1024,2048) bias
-  // [2048, 2048+16K) epilogue transpose staging (4 warps x (2 KB out + 2 KB residual))  then the stages
+  // [2048, 2048+32K) epilogue transpose staging (8 warps x (2 KB out + 2 KB residual))  then the stages
   const uint32_t bar_full = base, bar_empty = base + 64, bar_tfull = base + 128, bar_tempty = base + 144;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + 192);
   float* s_bias = reinterpret_cast<float*>(gbase + 1024);
   uint8_t* s_stage_ep = gbase + 2048;
-  const uint32_t stage0 = base + 2048 + 16384;
+  const uint32_t stage0 = base + 2048 + kV3Staging;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < p.C_out; i += blockDim.x) s_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.C_out && i < 256; i += blockDim.x) s_bias[i] = p.bias[i];
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < p.nstages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -539,11 +543,13 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           mbar_expect_tx(bar_full + 8 * stage, p.b_bytes);   // bytes delivered by the two boxes
           const uint32_t sa = stage0 + stage * p.stage_bytes;
           tma_load_3d(&tmW, bar_full + 8 * stage, sa, cc * p.Ck, mt * 128, tap);
-          tma_load_4d(&tmX, bar_full + 8 * stage, sa + p.a_bytes, cc * p.Ck, w0 + kw - 1, h0 + kh - 1, b);
+          // stride 2: the tensor map steps 2 elements along W and H, coordinates stay in input pixels
+          tma_load_4d(&tmX, bar_full + 8 * stage, sa + p.a_bytes, cc * p.Ck, w0 * p.stride + kw - p.pad,
+                      h0 * p.stride + kh - p.pad, b);
         }
         __syncwarp();
         if (++stage == p.nstages) { stage = 0; phase ^= 1; }
-        if (++cc == p.ncc) { cc = 0; ++tap; if (++kw == 3) { kw = 0; ++kh; } }
+        if (++cc == p.ncc) { cc = 0; ++tap; if (++kw == p.ksize) { kw = 0; ++kh; } }
       }
     }
   } else if (warp == 1) {
@@ -577,17 +583,21 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    const int q = warp & 3;                                // TMEM lane quadrant = block of 32 output channels
-    __half* s_out = reinterpret_cast<__half*>(s_stage_ep + q * 4096);          // [32 px][32 ch]
-    __half* s_res = reinterpret_cast<__half*>(s_stage_ep + q * 4096 + 2048);   // [32 px][32 ch]
+    // two warps per TMEM lane quadrant (= block of 32 output channels) take alternate 32-pixel chunks of the tile:
+    // with four warps the transposing epilogue of a residual conv took as long as the tile's MMAs
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    __half* s_out = reinterpret_cast<__half*>(s_stage_ep + (half * 4 + q) * 4096);          // [32 px][32 ch]
+    __half* s_res = reinterpret_cast<__half*>(s_stage_ep + (half * 4 + q) * 4096 + 2048);   // [32 px][32 ch]
     const int prow = lane >> 2, ppart = lane & 3;          // cooperative 16-byte I/O: 8 pixels x 4 parts per pass
     uint32_t acc = 0, acc_phase = 0;
     const int npix = p.bw * p.bh;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       int b, h0, w0, mt;
       decode(item, b, h0, w0, mt);
-      const int c0 = mt * 128 + q * 32;                    // first channel of this warp (C_out is a multiple of 128)
-      const float bias = s_bias[c0 + lane];
+      const int c0 = mt * 128 + q * 32;                    // first channel of this warp
+      const bool ch_ok = c0 < p.C_out;                     // C_out = 64: the upper two quadrants are zero padding
+      const float bias = ch_ok ? s_bias[c0 + lane] : 0.f;
       // global pixel index of the 4 pixels this lane moves per chunk (16-byte pieces), -1 when outside the image
       long long gp[4], gpn[4];
       uint4 rpre[4];
@@ -596,7 +606,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         for (int i = 0; i < 4; ++i) {
           const int n = n0 + i * 8 + prow;
           const int rr = n / p.bw, x = n - rr * p.bw;
-          const bool ok = n < npix && (h0 + rr) < p.H && (w0 + x) < p.W;
+          const bool ok = ch_ok && n < npix && (h0 + rr) < p.H && (w0 + x) < p.W;
           dst[i] = ok ? (((long long)b * p.H + h0 + rr) * p.W + w0 + x) : -1;
         }
       };
@@ -606,19 +616,22 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           rpre[i] = g[i] >= 0 ? __ldg(reinterpret_cast<const uint4*>(p.residual + g[i] * p.C_out + c0 + ppart * 8))
                               : make_uint4(0, 0, 0, 0);
       };
-      pixels(0, gp);
-      if (p.residual) load_res(gp);                        // independent of the MMAs: issue before waiting
+      const int first = half * 32;
+      if (first < npix) {
+        pixels(first, gp);
+        if (p.residual) load_res(gp);                      // independent of the MMAs: issue before waiting
+      }
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u;
-      for (int n0 = 0; n0 < npix; n0 += 32) {
+      for (int n0 = first; n0 < npix; n0 += 64) {
         uint32_t r[32];
         tc_ld32(taddr + n0, r);
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias;
-        const bool more = n0 + 32 < npix;
-        if (more) pixels(n0 + 32, gpn);
+        const bool more = n0 + 64 < npix;
+        if (more) pixels(n0 + 64, gpn);
         if (p.residual) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(s_res + (i * 8 + prow) * 32 + ppart * 8) = rpre[i];
@@ -1486,39 +1499,49 @@ int conv_block32_forward(const ConvLayer& L1, const ConvLayer& L2, const __half*
   return B200_OK;
 }
 
-static int conv3_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H, int W,
-                         int relu, int num_sms, cudaStream_t stream) {
+static int conv3_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H_in,
+                         int W_in, int relu, int num_sms, cudaStream_t stream) {
   B200_CHECK(L.w3 != nullptr, B200_ERR_STATE, "conv v3: padded weights missing");
+  B200_CHECK((L.ksize == 3 || L.ksize == 1) && (L.stride == 1 || L.stride == 2), B200_ERR_STATE,
+             "conv v3: %dx%d stride %d unsupported", L.ksize, L.ksize, L.stride);
   ConvV3Params p{};
+  p.stride = L.stride; p.ksize = L.ksize; p.pad = L.ksize / 2;
+  const int H = (H_in + 2 * p.pad - L.ksize) / L.stride + 1, W = (W_in + 2 * p.pad - L.ksize) / L.stride + 1;
   p.B = B; p.H = H; p.W = W; p.C_in = L.C_in; p.C_out = L.C_out; p.relu = relu;
   p.bias = L.bias; p.residual = residual; p.out = out;
   p.Ck = (L.C_in >= 64) ? 64 : 32;
   p.ncc = L.C_in / p.Ck;
-  p.kblocks = 9 * p.ncc;
+  p.kblocks = L.ksize * L.ksize * p.ncc;
   p.swizzle = (p.Ck == 64) ? 128 : 64;
-  // pixel tile: up to 256 pixels of one image; several rows when the image is narrower than 256
-  if (W >= 256) { p.bw = 256; p.bh = 1; }
-  else { p.bw = W; p.bh = 256 / W; if (p.bh > H) p.bh = H; }
+  // pixel tile: up to 256 output pixels of one image; several rows when the image is narrower.  A TMA box dimension
+  // is at most 256 elements, and a strided box spans bw * stride input pixels: stride 2 -> at most 128 per row
+  const int max_bw = 256 / L.stride;
+  if (W >= max_bw) { p.bw = max_bw; p.bh = 256 / max_bw; }
+  else { p.bw = W; p.bh = 256 / W; }
+  if (p.bh > H) p.bh = H;
+  if (p.bh * L.stride > 256) p.bh = 256 / L.stride;
   p.tiles_w = ceil_div(W, p.bw);
   p.tiles_h = ceil_div(H, p.bh);
   p.m_tiles = ceil_div(L.C_out, 128);
   p.num_items = B * p.tiles_h * p.tiles_w * p.m_tiles;
   p.a_bytes = 128u * p.Ck * 2;
-  p.b_bytes = (uint32_t)align_up((size_t)p.bw * p.bh * p.Ck * 2, 1024);
   const uint32_t b_full = 256u * p.Ck * 2;                 // the MMA reads N = 256 rows: keep the slot that large
-  p.stage_bytes = p.a_bytes + (uint32_t)p.bw * p.bh * p.Ck * 2;   // bytes the two TMA boxes deliver
+  const uint32_t delivered = p.a_bytes + (uint32_t)p.bw * p.bh * p.Ck * 2;   // bytes the two TMA boxes deliver
   const uint32_t slot = p.a_bytes + b_full;
-  p.nstages = (200u * 1024 - 16384) / slot;
+  p.stage_bytes = slot;                                     // the kernel addresses stage s at stage0 + s * stage_bytes
+  p.b_bytes = delivered;                                    // bytes to expect per stage
+  p.nstages = (200u * 1024 - kV3Staging) / slot;
   if (p.nstages > 8) p.nstages = 8;
   p.idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   PFN_encodeTiled enc = get_encode();
   B200_CHECK(enc != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   CUtensorMap tmX, tmW;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)L.C_in, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)L.C_in * 2, (cuuint64_t)W * L.C_in * 2, (cuuint64_t)H * W * L.C_in * 2};
-    cuuint32_t box[4] = {(cuuint32_t)p.Ck, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint64_t dims[4] = {(cuuint64_t)L.C_in, (cuuint64_t)W_in, (cuuint64_t)H_in, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)L.C_in * 2, (cuuint64_t)W_in * L.C_in * 2,
+                             (cuuint64_t)H_in * W_in * L.C_in * 2};
+    cuuint32_t box[4] = {(cuuint32_t)p.Ck, (cuuint32_t)(p.bw * L.stride), (cuuint32_t)(p.bh * L.stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)L.stride, (cuuint32_t)L.stride, 1};
     CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(in), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE,
                      p.swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -1527,7 +1550,7 @@ static int conv3_forward(const ConvLayer& L, const __half* in, const __half* res
   }
   {
     const int rows = p.m_tiles * 128;                       // padded output-channel rows
-    cuuint64_t dims[3] = {(cuuint64_t)L.C_in, (cuuint64_t)rows, 9};
+    cuuint64_t dims[3] = {(cuuint64_t)L.C_in, (cuuint64_t)rows, (cuuint64_t)(L.ksize * L.ksize)};
     cuuint64_t strides[2] = {(cuuint64_t)L.C_in * 2, (cuuint64_t)rows * L.C_in * 2};
     cuuint32_t box[3] = {(cuuint32_t)p.Ck, 128, 1};
     cuuint32_t estr[3] = {1, 1, 1};
@@ -1537,21 +1560,14 @@ static int conv3_forward(const ConvLayer& L, const __half* in, const __half* res
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(W, v3) failed: %d", (int)r);
   }
-  // the kernel addresses stage s at stage0 + s * stage_bytes: make that the full slot so that N = 256 rows exist
-  const uint32_t delivered = p.stage_bytes;
-  p.stage_bytes = slot;
-  p.b_bytes = delivered - p.a_bytes;                        // (kept for reference) bytes of the activation box
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA_OK(cudaFuncSetAttribute(conv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const size_t smem = 1024 + 2048 + 16384 + (size_t)p.nstages * slot;
+  const size_t smem = 1024 + 2048 + kV3Staging + (size_t)p.nstages * slot;
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
-  // expect_tx must equal the delivered bytes, the slot stride is `slot`: pass both
-  ConvV3Params q = p;
-  q.b_bytes = delivered;                                    // reuse field: bytes to expect per stage
-  conv_tc3_kernel<<<grid, kTcThreads, smem, stream>>>(tmX, tmW, q);
+  conv_tc3_kernel<<<grid, kV3Threads, smem, stream>>>(tmX, tmW, p);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }
@@ -1644,7 +1660,8 @@ int conv_forward(const ConvLayer& L, const __half* in, const __half* residual, _
   if (impl == 7 || impl == 8) {
     // channels-as-M tcgen05 conv for stride-1 3x3 with C_out >= 128 (N = 256 pixels balances the A-operand read);
     // impl 8 (default): narrower layers use the strip-streaming pixels-as-M kernel, impl 7: the per-tap kernel
-    if (L.ksize == 3 && L.stride == 1 && L.C_out >= 128)
+    // (impl 8 also sends the stride-2 3x3 convs and the 1x1 stride-2 shortcuts there: TMA element strides)
+    if ((L.ksize == 3 && L.stride == 1 && L.C_out >= 128) || (impl == 8 && L.stride == 2 && L.w3))
       return conv3_forward(L, in, residual, out, B, H_in, W_in, relu, num_sms, stream);
     if (impl == 8 && L.ksize == 3 && L.stride == 1 && L.C_in == L.C_out && L.C_in <= 64 && L.w4)
       return conv4_forward(L, in, residual, out, B, H_in, W_in, relu, num_sms, stream);   // vertical taps folded into N

@@ -421,14 +421,48 @@ def _ctx_method(fn):
     return fn
 
 
+def _norm_mode(normalize) -> int:
+    """False/0: rows as given; True/1: fp64 L2 normalisation; "float32"/2: numpy's float32 normalisation of rows that
+    hold float32 values (what the reference does to float32 embeddings before scipy's linkage)."""
+    if normalize in ("float32", 2):
+        return 2
+    return int(bool(normalize))
+
+
 @_ctx_method
-def linkage_centroid(self, x: torch.Tensor, normalize: bool = True) -> torch.Tensor:
+def plda_transform(self, x: torch.Tensor, mean1, mean2, lda, mu, trT) -> torch.Tensor:
+    """PLDA.__call__ on the device: x (n, Din) float64 -> (n, L) float64 (core/plda.py:50-63)."""
+    x = x.contiguous()
+    n, din = x.shape
+    dout, L = trT.shape
+    fea = torch.empty((n, L), dtype=torch.float64, device=self.device)
+    with torch.cuda.device(self.device):
+        _lib.check(self.lib.b200_plda_transform(self._h, _ptr(x), n, din, dout, L, _ptr(mean1), _ptr(mean2),
+                                                _ptr(lda.contiguous()), _ptr(mu), _ptr(trT.contiguous()), _ptr(fea),
+                                                _stream(self.device)))
+    return fea
+
+
+@_ctx_method
+def weighted_centroids(self, q: torch.Tensor, kept: torch.Tensor, train: torch.Tensor) -> torch.Tensor:
+    """(W.T @ train) / W.sum(0).T with W = q[:, kept] (clustering.py:620-621): q (n,S), train (n,dim) float64."""
+    q, train = q.contiguous(), train.contiguous()
+    kept = kept.to(device=self.device, dtype=torch.int32).contiguous()
+    out = torch.empty((kept.numel(), train.shape[1]), dtype=torch.float64, device=self.device)
+    with torch.cuda.device(self.device):
+        _lib.check(self.lib.b200_weighted_centroids(self._h, _ptr(q), q.shape[0], q.shape[1], _ptr(kept), kept.numel(),
+                                                    _ptr(train), train.shape[1], _ptr(out), _stream(self.device)))
+    return out
+
+
+@_ctx_method
+def linkage_centroid(self, x: torch.Tensor, normalize=True) -> torch.Tensor:
     """x (n, dim) float64 on device -> Z (n-1, 4) float64 on device (scipy linkage format)."""
     n, dim = x.shape
     x = x.contiguous()
     Z = torch.empty((n - 1, 4), dtype=torch.float64, device=self.device)
     with torch.cuda.device(self.device):
-        _lib.check(self.lib.b200_linkage_centroid(self._h, _ptr(x), n, dim, int(normalize), _ptr(Z),
+        _lib.check(self.lib.b200_linkage_centroid(self._h, _ptr(x), n, dim, _norm_mode(normalize), _ptr(Z),
                                                   _stream(self.device)))
     return Z
 
@@ -481,7 +515,7 @@ def assign(self, soft: torch.Tensor, constrained: bool = True) -> torch.Tensor:
 
 
 @_ctx_method
-def linkage_centroid_batched(self, x: torch.Tensor, row_offsets, normalize: bool = True) -> torch.Tensor:
+def linkage_centroid_batched(self, x: torch.Tensor, row_offsets, normalize=True) -> torch.Tensor:
     """x (sum n_f, dim) f64; row_offsets host int array (F+1,) -> concatenated Z ((sum max(n_f-1,0)), 4) f64."""
     x = x.contiguous()
     ro = np.ascontiguousarray(row_offsets, dtype=np.int32)
@@ -489,7 +523,7 @@ def linkage_centroid_batched(self, x: torch.Tensor, row_offsets, normalize: bool
     Z = torch.empty((nz, 4), dtype=torch.float64, device=self.device)
     with torch.cuda.device(self.device):
         _lib.check(self.lib.b200_linkage_centroid_batched(self._h, _ptr(x), ro.ctypes.data, len(ro) - 1, x.shape[1],
-                                                          int(normalize), _ptr(Z), _stream(self.device)))
+                                                          _norm_mode(normalize), _ptr(Z), _stream(self.device)))
     return Z
 
 

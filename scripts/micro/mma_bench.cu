@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128, 1) bench(int mode, int N, int iters, long
   const uint64_t bd0 = kdesc(b_s, 512, 4), bd1 = kdesc(b_s + 32, 512, 4);
   long long t0 = 0, t1 = 0;
   if (threadIdx.x == 0) {
-    if (mode == 1 || mode == 3) {                          // A tile (2 k-steps) into TMEM once
+    if (mode == 1 || mode == 3 || mode == 5) {             // A tile (2 k-steps) into TMEM once
       cp_128x256b(a_t, ad0);
       cp_128x256b(a_t + 8, ad1);
       commit(bar);
@@ -98,6 +98,14 @@ __global__ void __launch_bounds__(128, 1) bench(int mode, int N, int iters, long
       } else if (mode == 1) {
         mma_ts(d_t, a_t, bd0, idesc, it > 0);
         mma_ts(d_t, a_t + 8, bd1, idesc, 1);
+      } else if (mode == 4 || mode == 5) {               // SS / TS rotating over several accumulators
+        const int nacc = 256 / N < 1 ? 1 : (256 / N > 4 ? 4 : 256 / N);
+        const uint32_t d = d_t + (uint32_t)((it % nacc) * N);
+        if (mode == 4) { mma_ss(d, ad0, bd0, idesc, it >= nacc); mma_ss(d, ad1, bd1, idesc, 1); }
+        else { mma_ts(d, a_t, bd0, idesc, it >= nacc); mma_ts(d, a_t + 8, bd1, idesc, 1); }
+      } else if (mode == 6) {                            // SS, the two k-steps go to different accumulators
+        mma_ss(d_t, ad0, bd0, idesc, it > 0);
+        mma_ss(d_t + (uint32_t)N, ad1, bd1, idesc, it > 0);
       } else if (mode == 2) {
         cp_128x256b(a_t + 16, ad0);
         cp_128x256b(a_t + 24, ad1);
@@ -171,11 +179,13 @@ int main() {
     printf("numerics %s: max |D - ref| = %g\n", mode == 0 ? "SS" : "TS (A via tcgen05.cp)", maxerr);
   }
   const int iters = 2000;
-  const char* names[4] = {"SS  mma x2", "TS  mma x2", "cp  x2    ", "TS mma x2 + cp x1"};
-  for (int mode = 0; mode < 4; ++mode)
+  const char* names[7] = {"SS  mma x2", "TS  mma x2", "cp  x2    ", "TS mma x2 + cp x1", "SS rotating D", "TS rotating D",
+                          "SS k-steps to 2 D"};
+  for (int mode = 0; mode < 7; ++mode)
     for (int N : {32, 64, 96, 128, 192, 256}) {
       if (mode == 2 && N != 32) continue;
-      for (int grid : {1, 148}) {
+      if (mode >= 4 && N > 128) continue;
+      for (int grid : {1}) {
         bench<<<grid, 128, smem>>>(mode, N, iters, dc, nullptr, dA, dB);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("mode %d N %d failed: %s\n", mode, N, cudaGetErrorString(e)); return 1; }
