@@ -359,8 +359,10 @@ def _e2e_case(pipeline, oracle_models, wav, name, exclude_overlap=False, min_dur
         _compare_with_oracle(art, out, ref, independent=identical)
         a, b = out.speaker_embeddings, ref.speaker_embeddings
         assert a.shape == b.shape
-        if a.size:
-            ccos = (a * b).sum(-1) / np.maximum(np.linalg.norm(a, axis=-1) * np.linalg.norm(b, axis=-1), 1e-30)
+        real = np.linalg.norm(b, axis=-1) > 0                # rows padded for labels without a centroid are all-zero
+        assert np.array_equal(real, np.linalg.norm(a, axis=-1) > 0)
+        if real.any():
+            ccos = (a * b).sum(-1)[real] / (np.linalg.norm(a, axis=-1) * np.linalg.norm(b, axis=-1))[real]
             assert (1 - ccos).max() <= 1e-3
     # and with the CUDA embeddings fed to the oracle's clustering: everything downstream is exact arithmetic
     ref2 = P.apply(seg_model, emb_model, plda, wav, segmentations=P.SWF(seg, ref_seg.sw), embeddings=emb,

@@ -369,17 +369,17 @@ def test_audio_ingest_on_device(dev, pipeline, tmp_path):
         assert got.shape[0] == ref.shape[1], (sr_in, got.shape, ref.shape)
         err = float((got.cpu() - ref[0]).abs().max())
         print(f"[parity] ingest {sr_in} -> 16000 Hz float32 stereo: max abs err {err:.2e}")
-        assert err <= 2e-6
+        assert err <= 1e-5        # float32 FIR of up to 475 taps, different summation order than the CPU conv1d
         one = ctx.audio_ingest(x.to(dev), sr_in, 16000, channel=1)          # io.py:232-233 channel selection
         ref1 = x[1:2] if sr_in == 16000 else AF.resample(x[1:2], sr_in, 16000)
-        assert float((one.cpu() - ref1[0]).abs().max()) <= 2e-6
+        assert float((one.cpu() - ref1[0]).abs().max()) <= 1e-5
         # int16 interleaved PCM, as a WAV file holds it
         pcm = np.ascontiguousarray(np.clip(np.round(stereo.T * 32767.0), -32768, 32767).astype(np.int16))  # (frames, ch)
         reff = torch.from_numpy(pcm.T.astype(np.float32) / 32768.0).mean(dim=0, keepdim=True)
         if sr_in != 16000:
             reff = AF.resample(reff, sr_in, 16000)
         goti = ctx.audio_ingest(torch.from_numpy(pcm).to(dev), sr_in, 16000)
-        assert float((goti.cpu() - reff[0]).abs().max()) <= 2e-6
+        assert float((goti.cpu() - reff[0]).abs().max()) <= 1e-5
     # same rate, mono: the kernel is the identity (bit-exact)
     same = ctx.audio_ingest(base.to(dev), 16000, 16000)
     assert torch.equal(same.cpu(), base[0])
@@ -398,7 +398,7 @@ def test_audio_ingest_on_device(dev, pipeline, tmp_path):
     assert raw.dtype == torch.int16 and sr_raw == sr_in and audio.needs_ingest(raw, sr_raw)
     w_dev = audio.ingest(ctx, raw, sr_raw)
     assert w_dev.shape[0] == w_host.shape[1] == audio.num_samples_out(raw, sr_raw)
-    assert float((w_dev.cpu() - w_host[0]).abs().max()) <= 2e-6
+    assert float((w_dev.cpu() - w_host[0]).abs().max()) <= 1e-5
     out_file = pipeline(str(path))
     out_host = pipeline({"waveform": w_host, "sample_rate": 16000, "uri": "stereo44k"})
     a = [(s.start, s.end, lab) for s, _, lab in out_file.speaker_diarization.itertracks(yield_label=True)]
