@@ -845,24 +845,31 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int R = h1 - h0;
       const int w = wt * kTileM + q * 32 + lane;
       const bool valid = w < p.W;
-      for (int r = 0; r < R; ++r) {
+      // residual rows are software-pipelined one row of this group ahead (registers): with the load issued right
+      // before the accumulator wait the epilogue stalled on it for 16 % of its samples and the MMA warp waited for
+      // TMEM blocks a third of the time (ncu, layer2 conv2)
+      uint4 rpre[8], rnext[8];
+      auto res_row = [&](int r) { return (((size_t)b * p.H + (h0 + r)) * p.W + (valid ? w : 0)) * (size_t)C; };
+      auto load_res = [&](int r, uint4 (&dst)[8]) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + res_row(r));
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          if (j4 * 8 < C) dst[j4] = valid ? __ldg(rp + j4) : make_uint4(0, 0, 0, 0);
+      };
+      const int r_first = (int)((grp - (grow & 1u)) & 1u);   // first row of this item handled by this warpgroup
+      if (p.residual && r_first < R) load_res(r_first, rpre);
+      for (int r = r_first; r < R; r += 2) {
         const uint32_t g = grow + (uint32_t)r;
-        if ((g & 1u) != grp) continue;
         const uint32_t blk = g & nb_mask;
-        const size_t pix = (((size_t)b * p.H + (h0 + r)) * p.W + (valid ? w : 0)) * (size_t)C;
-        uint4 rpre[8];
+        const size_t pix = res_row(r);
         if (p.residual) {
-          // the residual streams from HBM: pull the rows this group will need next into L2 (one 64/128-byte pixel per
-          // thread), so that the register prefetch below only pays L2 latency
+          // rows further ahead: pull them into L2 (one 64/128-byte pixel per thread)
           if (p.res_pf && valid && r + p.res_pf < R) {
             const __half* nxt = p.residual + pix + (size_t)p.res_pf * p.W * C;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
             if (C == 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 32));
           }
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix);
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4)
-            if (j4 * 8 < C) rpre[j4] = valid ? __ldg(rp + j4) : make_uint4(0, 0, 0, 0);
+          if (r + 2 < R) load_res(r + 2, rnext);
         }
         mbar_wait(bar_tfull + 8 * blk, (g >> p.nb_shift) & 1u);
         tc_fence_after();
@@ -908,6 +915,10 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
         }
+        if (p.residual && r + 2 < R) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) rpre[j4] = rnext[j4];
+        }
       }
       grow += (uint32_t)R;
     }
@@ -942,7 +953,7 @@ struct ConvBlkParams {
   uint32_t slot_bytes, w1_off, w2_off, i_off, m_off;
 };
 
-constexpr int kBlkThreads = 576;   // TMA warp, MMA warp, 2 x 4 epilogue-1 warps, 2 x 4 epilogue-2 warps
+constexpr int kBlkThreads = 608;   // TMA warp, conv1 MMA warp, 2 x 4 epilogue-1 warps, 2 x 4 epilogue-2 warps, conv2 MMA warp
 
 __global__ void __launch_bounds__(kBlkThreads, 1)
 conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
@@ -983,7 +994,7 @@ conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (warp >= 2) {                                          // both rings start at zero (every MMA accumulates)
+  if (warp >= 2 && warp < 18) {                             // both rings start at zero (every MMA accumulates)
     const uint32_t grp = (uint32_t)(warp - 2) >> 2;         // 4 warpgroups x 128 columns
     const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * 128u;
 #pragma unroll
@@ -1030,8 +1041,11 @@ conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (++is == (uint32_t)p.n_islots) { is = 0; iph ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ---- MMA issuer: conv1 on input rows, conv2 `lag` rows behind on the intermediate rows ---------------------
+  } else if (warp == 1 || warp == 18) {
+    // ---- MMA issuers: warp 1 runs conv1 over the input rows, warp 18 runs conv2 over the intermediate rows.  One warp
+    // issuing both convs spent as long on its own scalar bookkeeping as the tensor pipe needs for the MMAs (ncu: pipe
+    // 31 % active, the issuing warp back-pressured only 37 % of the time); the two instruction streams are independent
+    // (different rings, the data dependency conv1 -> epilogue 1 -> conv2 goes through the mfull barriers).
     const bool leader = elect_one_sync();
     const uint32_t dhi = desc_hi(512u, 4u);                 // 64-byte rows, SWIZZLE_64B
     const uint32_t idesc0 = (1u << 4) | ((uint32_t)(kTileM >> 4) << 24);
@@ -1061,14 +1075,13 @@ conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         ra = rb - 1;
       }
     };
-    uint32_t is = 0, iph = 0, grow1 = 0, grow2 = 0;       // intermediate row g lives in slot g % 8
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      int b, wt, h0, h1;
-      decode(item, b, wt, h0, h1);
-      const int R = h1 - h0, R1 = R + 2;                    // output rows, intermediate rows
-      for (int step = 0; step < R + 4 + p.lag; ++step) {
-        const int t = step;                                 // input row h0 - 2 + t feeds intermediate rows t, t-1, t-2
-        if (t < R + 4) {
+    if (warp == 1) {
+      uint32_t is = 0, iph = 0, grow1 = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        int b, wt, h0, h1;
+        decode(item, b, wt, h0, h1);
+        const int R1 = h1 - h0 + 2;                           // intermediate rows
+        for (int t = 0; t < R1 + 2; ++t) {                    // input row h0 - 2 + t feeds intermediate rows t, t-1, t-2
           mbar_wait(bar_ifull + 8 * is, iph);
           tc_fence_after();
           if (t < R1) {
@@ -1084,8 +1097,15 @@ conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           __syncwarp();
           if (++is == (uint32_t)p.n_islots) { is = 0; iph ^= 1; }
         }
-        const int u = step - p.lag;                         // intermediate row h0 - 1 + u feeds output rows u, u-1, u-2
-        if (u >= 0 && u < R1) {
+        grow1 += (uint32_t)R1;
+      }
+    } else {
+      uint32_t grow1 = 0, grow2 = 0;                          // intermediate row g lives in slot g % 8
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        int b, wt, h0, h1;
+        decode(item, b, wt, h0, h1);
+        const int R = h1 - h0, R1 = R + 2;                    // output rows, intermediate rows
+        for (int u = 0; u < R1; ++u) {                        // intermediate row h0 - 1 + u feeds output rows u, u-1, u-2
           const uint32_t gm = grow1 + (uint32_t)u, ms = gm & 7u, mph = (gm >> 3) & 1u;
           mbar_wait(bar_mfull + 8 * ms, mph);
           tc_fence_after();
@@ -1101,9 +1121,9 @@ conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           __syncwarp();
         }
+        grow1 += (uint32_t)R1;
+        grow2 += (uint32_t)R;
       }
-      grow1 += (uint32_t)R1;
-      grow2 += (uint32_t)R;
     }
   } else if (warp < 10) {
     // ---- epilogue 1 (two warpgroups, alternate rows): ring 1 -> relu(. + b1) -> fp16 -> intermediate slot ----------
@@ -1171,17 +1191,20 @@ conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int R = h1 - h0;
       const int w = wt * 126 - 1 + m;
       const bool valid = m >= 1 && m <= 126 && w < p.W;
-      for (int r = 0; r < R; ++r) {
-        const uint32_t g = grow2 + (uint32_t)r;
-        if ((g & 1u) != grp) continue;
-        const uint32_t blk = g & nb_mask;
-        const size_t pix = (((size_t)b * p.H + (h0 + r)) * p.W + (valid ? w : 0)) * 32;
-        uint4 rpre[4];
-        {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.in + pix);   // residual = block input (L2: just streamed)
+      uint4 rpre[4], rnext[4];                               // residual = block input (L2: just streamed), one row ahead
+      auto res_row = [&](int r) { return (((size_t)b * p.H + (h0 + r)) * p.W + (valid ? w : 0)) * 32; };
+      auto load_res = [&](int r, uint4 (&dst)[4]) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.in + res_row(r));
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) rpre[j4] = valid ? __ldg(rp + j4) : make_uint4(0, 0, 0, 0);
-        }
+        for (int j4 = 0; j4 < 4; ++j4) dst[j4] = valid ? __ldg(rp + j4) : make_uint4(0, 0, 0, 0);
+      };
+      const int r_first = (int)((grp - (grow2 & 1u)) & 1u);
+      if (r_first < R) load_res(r_first, rpre);
+      for (int r = r_first; r < R; r += 2) {
+        const uint32_t g = grow2 + (uint32_t)r;
+        const uint32_t blk = g & nb_mask;
+        const size_t pix = res_row(r);
+        if (r + 2 < R) load_res(r + 2, rnext);
         mbar_wait(bar_t2full + 8 * blk, (g >> nb_shift) & 1u);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (nb_mask - blk) * 32u;
@@ -1213,6 +1236,10 @@ conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             op[j4] = u;
           }
+        }
+        if (r + 2 < R) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) rpre[j4] = rnext[j4];
         }
       }
       grow2 += (uint32_t)R;
