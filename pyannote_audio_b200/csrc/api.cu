@@ -19,6 +19,7 @@ struct b200_ctx {
   int seg_conv_impl = 1;   // 1 = SincNet Conv1d(k=5) layers on tcgen05 (split fp16), 0 = fp32 CUDA-core kernel
   int seg_rec_impl = 1;    // 1 = LSTM recurrence on the tensor cores (needs seg_gemm_impl = 1), 0 = fp32 SIMT cluster kernel
   int conv_fuse = 1;       // 1 = layer1 BasicBlocks as one fused kernel (conv_block32_kernel) when conv_impl == 8
+  int conv_ghost = 1;      // 1 = TMEM rings with ghost blocks (no seam-split MMAs) in conv_tc4 / conv_block32
   int conv_impl = 8;   // channels-as-M conv for C_out >= 128, strip-streaming conv for the narrow stride-1 3x3, per-tap conv otherwise
   int seg_max_batch = 4736;     // chunks per segmentation sub-batch (37 LSTM tiles of 128 sequences x 2 directions = 74 clusters)
   int emb_max_batch = 256;      // chunks per embedding sub-batch
@@ -255,6 +256,7 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value) {
   else if (k == "seg_rec_impl") ctx->seg_rec_impl = (int)value;
   else if (k == "seg_conv_impl") ctx->seg_conv_impl = (int)value;
   else if (k == "conv_fuse") ctx->conv_fuse = (int)value;
+  else if (k == "conv_ghost") ctx->conv_ghost = (int)value;
   else B200_CHECK(false, B200_ERR_INVALID, "unknown option '%s'", key);
   B200_CHECK(ctx->seg_max_batch >= 1 && ctx->emb_max_batch >= 1 && ctx->conv_impl >= 0 && ctx->conv_impl <= 8,
              B200_ERR_INVALID, "option '%s' value %lld out of range", key, (long long)value);
@@ -643,14 +645,14 @@ static int block_run(b200_ctx* ctx, const BlockWeights& B, __half* A, __half* Bf
   const int impl_s1 = ctx->conv_impl == 2 ? 1 : ctx->conv_impl;
   const int Ho = (H + 2 - 3) / s + 1, Wo = (Wd + 2 - 3) / s + 1;
   int rc;
-  if ((rc = conv_forward(B.conv1, A, nullptr, Bf, nb, H, Wd, 1, impl1, ctx->num_sms, st))) return rc;
+  if ((rc = conv_forward(B.conv1, A, nullptr, Bf, nb, H, Wd, 1, impl1, ctx->num_sms, st, ctx->conv_ghost))) return rc;
   const __half* res = A;
   if (B.has_shortcut) {
-    if ((rc = conv_forward(B.shortcut, A, nullptr, Cf, nb, H, Wd, 0, impl1, ctx->num_sms, st))) return rc;
+    if ((rc = conv_forward(B.shortcut, A, nullptr, Cf, nb, H, Wd, 0, impl1, ctx->num_sms, st, ctx->conv_ghost))) return rc;
     res = Cf;
     ctx->launches += 1;
   }
-  if ((rc = conv_forward(B.conv2, Bf, res, A, nb, Ho, Wo, 1, impl_s1, ctx->num_sms, st))) return rc;
+  if ((rc = conv_forward(B.conv2, Bf, res, A, nb, Ho, Wo, 1, impl_s1, ctx->num_sms, st, ctx->conv_ghost))) return rc;
   ctx->launches += 2;
   return B200_OK;
 }
@@ -672,7 +674,7 @@ static int trunk_run(b200_ctx* ctx, const EmbWs& w, int nb, cudaStream_t st, con
     if (ctx->conv_impl == 8 && ctx->conv_fuse && !B.has_shortcut && s == 1 && B.conv1.C_in == 32 && B.conv1.w4 &&
         B.conv2.w4) {
       // layer1: the whole block in one kernel, intermediate activation kept in shared memory
-      if ((rc = conv_block32_forward(B.conv1, B.conv2, cur, s1, nb, H, Wd, ctx->num_sms, st))) return rc;
+      if ((rc = conv_block32_forward(B.conv1, B.conv2, cur, s1, nb, H, Wd, ctx->num_sms, st, ctx->conv_ghost))) return rc;
       ctx->launches += 1;
       __half* t = cur; cur = s1; s1 = t;
       continue;

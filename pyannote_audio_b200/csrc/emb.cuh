@@ -48,10 +48,10 @@ struct EmbWeights {
 
 // impl: 0 = SIMT reference conv, 1 = tcgen05 tensor-core conv
 int conv_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H_in, int W_in,
-                 int relu, int impl, int num_sms, cudaStream_t stream);
+                 int relu, int impl, int num_sms, cudaStream_t stream, int ghost = 1);
 // fused BasicBlock of layer1 (two 32->32 stride-1 convs + identity shortcut), out must not alias in
 int conv_block32_forward(const ConvLayer& L1, const ConvLayer& L2, const __half* in, __half* out, int B, int H, int W,
-                         int num_sms, cudaStream_t stream);
+                         int num_sms, cudaStream_t stream, int ghost = 1);
 int conv1_forward(const float* fbank, const float* fmean, const float* w, const float* bias, __half* out, int B,
                   cudaStream_t stream);
 

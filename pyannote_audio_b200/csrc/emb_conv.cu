@@ -693,7 +693,6 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 // ------------------------------------------------------------------------------------------------
 struct ConvV4Params {
   int B, H, W, C, tiles_w, R, nhseg, num_items, relu, n_aslots;
-  int nb_shift;                      // ring of NB = 512 / C accumulator blocks
   int res_pf;                        // residual L2 prefetch distance in rows (0 = off)
   const float* bias;
   const __half* residual;
@@ -703,8 +702,26 @@ struct ConvV4Params {
 
 constexpr int kV4Threads = 320;   // TMA warp, MMA warp, 2 x 4 epilogue warps (alternate rows)
 
+// Ring geometry.  The 512 TMEM columns hold P = 512 / C blocks of C columns.  GHOST = false: all P blocks form the
+// ring and a run of rows that crosses the ring seam is issued as two narrower MMAs (25 % more MMAs for C = 64, and
+// an MMA costs ~105 cycles whatever its N <= 192: scripts/micro/mma_bench.cu).  GHOST = true: the ring has P - 2
+// logical blocks; the two positions after the last real block are "ghosts" of the two blocks at the other end of the
+// ring, so a run that would wrap simply continues into them and EVERY input row is one MMA per (kw, k-step); the
+// epilogue adds the ghost block of the two affected ring slots to the real one (fp32) and zeroes both.
+template <uint32_t P, bool GHOST>
+struct TmemRing {
+  static constexpr uint32_t NBL = GHOST ? P - 2 : P;
+  __device__ static __forceinline__ uint32_t idx(uint32_t g) { return g % NBL; }
+  __device__ static __forceinline__ uint32_t phase(uint32_t g) { return (g / NBL) & 1u; }
+  __device__ static __forceinline__ uint32_t pos(uint32_t i) { return NBL - 1u - i; }          // descending rows
+  __device__ static __forceinline__ uint32_t ghost_pos(uint32_t i) { return 2u * NBL - 1u - i; }   // i >= NBL - 2
+};
+
+template <int C, bool GHOST>
 __global__ void __launch_bounds__(kV4Threads, 1)
 conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvV4Params p) {
+  using Ring = TmemRing<512 / C, GHOST>;
+  constexpr uint32_t NBL = Ring::NBL;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -716,14 +733,12 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + 512);
   float* s_bias = reinterpret_cast<float*>(gbase + 1024);
   const uint32_t w_smem = base + p.w_off, a_smem = base + p.a_off;
-  const int C = p.C;
-  const uint32_t NB = 1u << p.nb_shift, nb_mask = NB - 1u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((int)threadIdx.x < C) s_bias[threadIdx.x] = p.bias[threadIdx.x];
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.n_aslots; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
-    for (uint32_t a = 0; a < NB; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+    for (uint32_t a = 0; a < NBL; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
     mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -781,9 +796,10 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     const bool leader = elect_one_sync();
-    const uint32_t dhi = desc_hi((p.swizzle == 128) ? 1024u : 512u, (p.swizzle == 128) ? 2u : 4u);
-    const uint32_t rowbytes = (uint32_t)C * 2u, row_units = rowbytes >> 4;
-    const int ksteps = C / 16;
+    constexpr uint32_t kSwz128 = (C == 64);
+    const uint32_t dhi = desc_hi(kSwz128 ? 1024u : 512u, kSwz128 ? 2u : 4u);
+    constexpr uint32_t rowbytes = (uint32_t)C * 2u, row_units = rowbytes >> 4;
+    constexpr int ksteps = C / 16;
     const uint32_t idesc0 = (1u << 4) | ((uint32_t)(kTileM >> 4) << 24);
     mbar_wait(bar_w, 0);
     tc_fence_after();
@@ -797,29 +813,31 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         if (t < R) {                                       // output row t receives its first contribution
           const uint32_t g = grow + (uint32_t)t;
-          mbar_wait(bar_tempty + 8 * (g & nb_mask), ((g >> p.nb_shift) & 1u) ^ 1u);
+          mbar_wait(bar_tempty + 8 * Ring::idx(g), Ring::phase(g) ^ 1u);
           tc_fence_after();
         }
         const uint32_t alo0 = desc_lo(a_smem + as * p.a_slot_bytes);
         const int r_lo = max(t - 2, 0);
         int ra = min(t, R - 1);
         while (ra >= r_lo) {                               // runs of rows whose blocks are contiguous in TMEM
-          int rb = ra;
-          while (rb > r_lo && ((grow + (uint32_t)rb) & nb_mask) != 0u) --rb;
+          int rb = r_lo;
+          if (!GHOST) {                                    // the ring seam splits the run
+            rb = ra;
+            while (rb > r_lo && Ring::idx(grow + (uint32_t)rb) != 0u) --rb;
+          }
           const uint32_t N = (uint32_t)(ra - rb + 1) * (uint32_t)C;
-          const uint32_t d_tmem = tmem_base + (nb_mask - ((grow + (uint32_t)ra) & nb_mask)) * (uint32_t)C;
+          // GHOST: a run that wraps continues into the ghost positions behind the last real block
+          const uint32_t d_tmem = tmem_base + Ring::pos(Ring::idx(grow + (uint32_t)ra)) * (uint32_t)C;
           const uint32_t idesc = idesc0 | ((N >> 3) << 17);
           const uint32_t bofs = (uint32_t)(t - ra) * (uint32_t)C * rowbytes;   // first vertical tap of this run
           if (leader) {
+#pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
               const uint32_t alo = alo0 + kw * row_units;  // absolute-address swizzle: base_offset stays 0
               const uint32_t blo = desc_lo(w_smem + kw * p.wkw_bytes + bofs);
-              tc_mma_f16(d_tmem, desc_from(dhi, alo), desc_from(dhi, blo), idesc, 1);
-              tc_mma_f16(d_tmem, desc_from(dhi, alo + 2), desc_from(dhi, blo + 2), idesc, 1);
-              if (ksteps == 4) {
-                tc_mma_f16(d_tmem, desc_from(dhi, alo + 4), desc_from(dhi, blo + 4), idesc, 1);
-                tc_mma_f16(d_tmem, desc_from(dhi, alo + 6), desc_from(dhi, blo + 6), idesc, 1);
-              }
+#pragma unroll
+              for (int ks = 0; ks < ksteps; ++ks)
+                tc_mma_f16(d_tmem, desc_from(dhi, alo + 2 * ks), desc_from(dhi, blo + 2 * ks), idesc, 1);
             }
           }
           __syncwarp();
@@ -827,7 +845,7 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         if (leader) {
           tc_commit(bar_aempty + 8 * as);
-          if (t >= 2) tc_commit(bar_tfull + 8 * ((grow + (uint32_t)(t - 2)) & nb_mask));   // row t-2 complete
+          if (t >= 2) tc_commit(bar_tfull + 8 * Ring::idx(grow + (uint32_t)(t - 2)));   // row t-2 complete
         }
         __syncwarp();
         if (++as == (uint32_t)p.n_aslots) { as = 0; aph ^= 1; }
@@ -838,6 +856,7 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // two epilogue warpgroups (warps 2-5 and 6-9) take alternate rows so that a scheduler always has a second warp
     const int q = warp & 3;
     const uint32_t grp = (uint32_t)(warp - 2) >> 2;
+    constexpr int NJ = C / 8;                              // 16-byte pieces per pixel
     uint32_t grow = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       int b, wt, h0, h1;
@@ -848,19 +867,18 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // residual rows are software-pipelined one row of this group ahead (registers): with the load issued right
       // before the accumulator wait the epilogue stalled on it for 16 % of its samples and the MMA warp waited for
       // TMEM blocks a third of the time (ncu, layer2 conv2)
-      uint4 rpre[8], rnext[8];
+      uint4 rpre[NJ], rnext[NJ];
       auto res_row = [&](int r) { return (((size_t)b * p.H + (h0 + r)) * p.W + (valid ? w : 0)) * (size_t)C; };
-      auto load_res = [&](int r, uint4 (&dst)[8]) {
+      auto load_res = [&](int r, uint4 (&dst)[NJ]) {
         const uint4* rp = reinterpret_cast<const uint4*>(p.residual + res_row(r));
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4)
-          if (j4 * 8 < C) dst[j4] = valid ? __ldg(rp + j4) : make_uint4(0, 0, 0, 0);
+        for (int j4 = 0; j4 < NJ; ++j4) dst[j4] = valid ? __ldg(rp + j4) : make_uint4(0, 0, 0, 0);
       };
       const int r_first = (int)((grp - (grow & 1u)) & 1u);   // first row of this item handled by this warpgroup
       if (p.residual && r_first < R) load_res(r_first, rpre);
       for (int r = r_first; r < R; r += 2) {
         const uint32_t g = grow + (uint32_t)r;
-        const uint32_t blk = g & nb_mask;
+        const uint32_t blk = Ring::idx(g);
         const size_t pix = res_row(r);
         if (p.residual) {
           // rows further ahead: pull them into L2 (one 64/128-byte pixel per thread)
@@ -871,30 +889,42 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           if (r + 2 < R) load_res(r + 2, rnext);
         }
-        mbar_wait(bar_tfull + 8 * blk, (g >> p.nb_shift) & 1u);
+        mbar_wait(bar_tfull + 8 * blk, Ring::phase(g));
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (nb_mask - blk) * (uint32_t)C;
-        uint32_t acc[64];
-        tc_ld32(taddr, acc);
-        if (C == 64) tc_ld32(taddr + 32, acc + 32);
-        tc_st32_zero(taddr);                               // hand the block back zeroed
-        if (C == 64) tc_st32_zero(taddr + 32);
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * blk);
-        if (valid) {
-          uint4* op = reinterpret_cast<uint4*>(p.out + pix);
-          const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+        const uint32_t lanes = (uint32_t)(q * 32) << 16;
+        const uint32_t taddr = tmem_base + lanes + Ring::pos(blk) * (uint32_t)C;
+        const bool has_ghost = GHOST && blk >= NBL - 2u;   // warp-uniform
+        const uint32_t gaddr = tmem_base + lanes + Ring::ghost_pos(blk) * (uint32_t)C;
+        uint4* op = reinterpret_cast<uint4*>(p.out + pix);
+        const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            if (j4 * 8 < C) {
+        for (int hb = 0; hb < C / 32; ++hb) {              // 32 columns at a time (register budget)
+          uint32_t acc[32];
+          tc_ld32(taddr + hb * 32, acc);
+          tc_st32_zero(taddr + hb * 32);                   // hand the block back zeroed
+          if (has_ghost) {
+            uint32_t gacc[32];
+            tc_ld32(gaddr + hb * 32, gacc);
+            tc_st32_zero(gaddr + hb * 32);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(gacc[j]));
+          }
+          if (hb == C / 32 - 1) {
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * blk);
+          }
+          if (valid) {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j4 = hb * 4 + jj;
               const float4 b0 = reinterpret_cast<const float4*>(s_bias)[2 * j4];
               const float4 b1 = reinterpret_cast<const float4*>(s_bias)[2 * j4 + 1];
-              float v[8] = {__uint_as_float(acc[j4 * 8 + 0]) + b0.x, __uint_as_float(acc[j4 * 8 + 1]) + b0.y,
-                            __uint_as_float(acc[j4 * 8 + 2]) + b0.z, __uint_as_float(acc[j4 * 8 + 3]) + b0.w,
-                            __uint_as_float(acc[j4 * 8 + 4]) + b1.x, __uint_as_float(acc[j4 * 8 + 5]) + b1.y,
-                            __uint_as_float(acc[j4 * 8 + 6]) + b1.z, __uint_as_float(acc[j4 * 8 + 7]) + b1.w};
+              float v[8] = {__uint_as_float(acc[jj * 8 + 0]) + b0.x, __uint_as_float(acc[jj * 8 + 1]) + b0.y,
+                            __uint_as_float(acc[jj * 8 + 2]) + b0.z, __uint_as_float(acc[jj * 8 + 3]) + b0.w,
+                            __uint_as_float(acc[jj * 8 + 4]) + b1.x, __uint_as_float(acc[jj * 8 + 5]) + b1.y,
+                            __uint_as_float(acc[jj * 8 + 6]) + b1.z, __uint_as_float(acc[jj * 8 + 7]) + b1.w};
               if (p.residual) {
                 const __half2* h2 = reinterpret_cast<const __half2*>(&rpre[j4]);
 #pragma unroll
@@ -917,7 +947,7 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         if (p.residual && r + 2 < R) {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) rpre[j4] = rnext[j4];
+          for (int j4 = 0; j4 < NJ; ++j4) rpre[j4] = rnext[j4];
         }
       }
       grow += (uint32_t)R;
@@ -955,9 +985,13 @@ struct ConvBlkParams {
 
 constexpr int kBlkThreads = 608;   // TMA warp, conv1 MMA warp, 2 x 4 epilogue-1 warps, 2 x 4 epilogue-2 warps, conv2 MMA warp
 
+template <bool GHOST>
 __global__ void __launch_bounds__(kBlkThreads, 1)
 conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB1,
                     const __grid_constant__ CUtensorMap tmB2, ConvBlkParams p) {
+  // two TMEM rings of 8 positions x 32 columns: 8 logical blocks, or 6 + 2 ghost positions (see TmemRing)
+  using Ring = TmemRing<8, GHOST>;
+  constexpr uint32_t NBL = Ring::NBL;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -971,7 +1005,6 @@ conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t w1_smem = base + p.w1_off, w2_smem = base + p.w2_off;
   const uint32_t i_smem = base + p.i_off, m_smem = base + p.m_off;
   constexpr uint32_t kWkw = 3u * 32 * 32 * 2;               // one horizontal tap of a conv: [(kh, co) = 96][ci = 32] fp16
-  constexpr uint32_t NB = 8, nb_mask = 7, nb_shift = 3;     // two TMEM rings of 8 x 32 columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < 32) { s_b1[threadIdx.x] = p.bias1[threadIdx.x]; s_b2[threadIdx.x] = p.bias2[threadIdx.x]; }
@@ -1056,10 +1089,13 @@ conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t alo0 = desc_lo(slot_addr);
       int ra = hi;
       while (ra >= lo) {
-        int rb = ra;
-        while (rb > lo && ((grow + (uint32_t)rb) & nb_mask) != 0u) --rb;
+        int rb = lo;
+        if (!GHOST) {                                       // the ring seam splits the run
+          rb = ra;
+          while (rb > lo && Ring::idx(grow + (uint32_t)rb) != 0u) --rb;
+        }
         const uint32_t N = (uint32_t)(ra - rb + 1) * 32u;
-        const uint32_t d_tmem = tmem_base + ring_col + (nb_mask - ((grow + (uint32_t)ra) & nb_mask)) * 32u;
+        const uint32_t d_tmem = tmem_base + ring_col + Ring::pos(Ring::idx(grow + (uint32_t)ra)) * 32u;
         const uint32_t idesc = idesc0 | ((N >> 3) << 17);
         const uint32_t bofs = (uint32_t)(src - ra) * 32u * 64u;
         if (leader) {
@@ -1086,13 +1122,13 @@ conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_fence_after();
           if (t < R1) {
             const uint32_t g = grow1 + (uint32_t)t;
-            mbar_wait(bar_t1empty + 8 * (g & nb_mask), ((g >> nb_shift) & 1u) ^ 1u);
+            mbar_wait(bar_t1empty + 8 * Ring::idx(g), Ring::phase(g) ^ 1u);
             tc_fence_after();
           }
           fold(i_smem + is * p.slot_bytes, w1_smem, 0u, grow1, t, max(t - 2, 0), min(t, R1 - 1));
           if (leader) {
             tc_commit(bar_iempty + 8 * is);
-            if (t >= 2) tc_commit(bar_t1full + 8 * ((grow1 + (uint32_t)(t - 2)) & nb_mask));
+            if (t >= 2) tc_commit(bar_t1full + 8 * Ring::idx(grow1 + (uint32_t)(t - 2)));
           }
           __syncwarp();
           if (++is == (uint32_t)p.n_islots) { is = 0; iph ^= 1; }
@@ -1111,13 +1147,13 @@ conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_fence_after();
           if (u < R) {
             const uint32_t g = grow2 + (uint32_t)u;
-            mbar_wait(bar_t2empty + 8 * (g & nb_mask), ((g >> nb_shift) & 1u) ^ 1u);
+            mbar_wait(bar_t2empty + 8 * Ring::idx(g), Ring::phase(g) ^ 1u);
             tc_fence_after();
           }
           fold(m_smem + ms * p.slot_bytes, w2_smem, 256u, grow2, u, max(u - 2, 0), min(u, R - 1));
           if (leader) {
             tc_commit(bar_mempty + 8 * ms);
-            if (u >= 2) tc_commit(bar_t2full + 8 * ((grow2 + (uint32_t)(u - 2)) & nb_mask));
+            if (u >= 2) tc_commit(bar_t2full + 8 * Ring::idx(grow2 + (uint32_t)(u - 2)));
           }
           __syncwarp();
         }
@@ -1140,16 +1176,24 @@ conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int u = 0; u < R1; ++u) {
         const uint32_t g = grow1 + (uint32_t)u;
         if ((g & 1u) != grp) continue;
-        const uint32_t blk = g & nb_mask;
+        const uint32_t blk = Ring::idx(g);
         const uint32_t ms = g & 7u, mph = (g >> 3) & 1u;
         const int row_img = h0 - 1 + u;
         const bool keep = col_ok && row_img >= 0 && row_img < p.H;    // zero padding of conv2's input
-        mbar_wait(bar_t1full + 8 * blk, (g >> nb_shift) & 1u);
+        mbar_wait(bar_t1full + 8 * blk, Ring::phase(g));
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (nb_mask - blk) * 32u;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + Ring::pos(blk) * 32u;
         uint32_t acc[32];
         tc_ld32(taddr, acc);
         tc_st32_zero(taddr);
+        if (GHOST && blk >= NBL - 2u) {                     // warp-uniform: add the ghost block of this ring slot
+          const uint32_t gaddr = tmem_base + ((uint32_t)(q * 32) << 16) + Ring::ghost_pos(blk) * 32u;
+          uint32_t gacc[32];
+          tc_ld32(gaddr, gacc);
+          tc_st32_zero(gaddr);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(gacc[j]));
+        }
         tc_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -1202,15 +1246,23 @@ conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (r_first < R) load_res(r_first, rpre);
       for (int r = r_first; r < R; r += 2) {
         const uint32_t g = grow2 + (uint32_t)r;
-        const uint32_t blk = g & nb_mask;
+        const uint32_t blk = Ring::idx(g);
         const size_t pix = res_row(r);
         if (r + 2 < R) load_res(r + 2, rnext);
-        mbar_wait(bar_t2full + 8 * blk, (g >> nb_shift) & 1u);
+        mbar_wait(bar_t2full + 8 * blk, Ring::phase(g));
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (nb_mask - blk) * 32u;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + Ring::pos(blk) * 32u;
         uint32_t acc[32];
         tc_ld32(taddr, acc);
         tc_st32_zero(taddr);
+        if (GHOST && blk >= NBL - 2u) {
+          const uint32_t gaddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + Ring::ghost_pos(blk) * 32u;
+          uint32_t gacc[32];
+          tc_ld32(gaddr, gacc);
+          tc_st32_zero(gaddr);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(gacc[j]));
+        }
         tc_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -1408,13 +1460,12 @@ PFN_encodeTiled get_encode() {
 }
 
 static int conv4_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H, int W,
-                         int relu, int num_sms, cudaStream_t stream) {
+                         int relu, int ghost, int num_sms, cudaStream_t stream) {
   const int C = L.C_in;
   B200_CHECK(L.w4 != nullptr && L.C_in == L.C_out && (C == 32 || C == 64), B200_ERR_STATE,
              "conv v4: folded weights missing");
   ConvV4Params p{};
   p.B = B; p.H = H; p.W = W; p.C = C; p.relu = relu; p.bias = L.bias; p.residual = residual; p.out = out;
-  p.nb_shift = (C == 32) ? 4 : 3;
   { const char* e = getenv("B200_RES_PF"); p.res_pf = e ? atoi(e) : 4; }
   p.swizzle = (C == 64) ? 128 : 64;
   p.tiles_w = ceil_div(W, kTileM);
@@ -1457,21 +1508,21 @@ static int conv4_forward(const ConvLayer& L, const __half* in, const __half* res
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(B, v4) failed: %d", (int)r);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA_OK(cudaFuncSetAttribute(conv_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   const size_t smem = 1024 + p.a_off + (size_t)p.n_aslots * p.a_slot_bytes;
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
-  conv_tc4_kernel<<<grid, kV4Threads, smem, stream>>>(tmA, tmB, p);
-  B200_CUDA_OK(cudaGetLastError());
-  return B200_OK;
+  auto launch = [&](auto kernel) -> int {
+    B200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    kernel<<<grid, kV4Threads, smem, stream>>>(tmA, tmB, p);
+    B200_CUDA_OK(cudaGetLastError());
+    return B200_OK;
+  };
+  if (C == 32) return ghost ? launch(conv_tc4_kernel<32, true>) : launch(conv_tc4_kernel<32, false>);
+  return ghost ? launch(conv_tc4_kernel<64, true>) : launch(conv_tc4_kernel<64, false>);
 }
 
 // fused BasicBlock (conv_block32_kernel): in -> out, out must not alias in (tiles read their neighbours' halo)
 int conv_block32_forward(const ConvLayer& L1, const ConvLayer& L2, const __half* in, __half* out, int B, int H, int W,
-                         int num_sms, cudaStream_t stream) {
+                         int num_sms, cudaStream_t stream, int ghost) {
   B200_CHECK(L1.w4 && L2.w4 && L1.C_in == 32 && L1.C_out == 32 && L2.C_in == 32 && L2.C_out == 32 && in != out,
              B200_ERR_STATE, "conv block: needs two folded 32->32 convs and distinct buffers");
   ConvBlkParams p{};
@@ -1514,16 +1565,15 @@ int conv_block32_forward(const ConvLayer& L1, const ConvLayer& L2, const __half*
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(B, block) failed: %d", (int)r);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA_OK(cudaFuncSetAttribute(conv_block32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   const size_t smem = 1024 + p.m_off + (size_t)p.n_mslots * p.slot_bytes;
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
-  conv_block32_kernel<<<grid, kBlkThreads, smem, stream>>>(tmA, tmB1, tmB2, p);
-  B200_CUDA_OK(cudaGetLastError());
-  return B200_OK;
+  auto launch = [&](auto kernel) -> int {
+    B200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    kernel<<<grid, kBlkThreads, smem, stream>>>(tmA, tmB1, tmB2, p);
+    B200_CUDA_OK(cudaGetLastError());
+    return B200_OK;
+  };
+  return ghost ? launch(conv_block32_kernel<true>) : launch(conv_block32_kernel<false>);
 }
 
 static int conv3_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H_in,
@@ -1683,7 +1733,7 @@ static int conv2_forward(const ConvLayer& L, const __half* in, const __half* res
 }
 
 int conv_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H_in, int W_in,
-                 int relu, int impl, int num_sms, cudaStream_t stream) {
+                 int relu, int impl, int num_sms, cudaStream_t stream, int ghost) {
   if (impl == 7 || impl == 8) {
     // channels-as-M tcgen05 conv for stride-1 3x3 with C_out >= 128 (N = 256 pixels balances the A-operand read);
     // impl 8 (default): narrower layers use the strip-streaming pixels-as-M kernel, impl 7: the per-tap kernel
@@ -1691,7 +1741,7 @@ int conv_forward(const ConvLayer& L, const __half* in, const __half* residual, _
     if ((L.ksize == 3 && L.stride == 1 && L.C_out >= 128) || (impl == 8 && L.stride == 2 && L.w3))
       return conv3_forward(L, in, residual, out, B, H_in, W_in, relu, num_sms, stream);
     if (impl == 8 && L.ksize == 3 && L.stride == 1 && L.C_in == L.C_out && L.C_in <= 64 && L.w4)
-      return conv4_forward(L, in, residual, out, B, H_in, W_in, relu, num_sms, stream);   // vertical taps folded into N
+      return conv4_forward(L, in, residual, out, B, H_in, W_in, relu, ghost, num_sms, stream);   // vertical taps folded into N
     impl = (impl == 8) ? 6 : 1;
   }
   if (impl >= 3) {

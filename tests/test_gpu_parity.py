@@ -176,11 +176,19 @@ def test_embedding_parity(ctx, dev, oracle_models):
     ctx.set_option("conv_impl", 8)
     for impl in (1, 6, 8):
         assert np.abs(out[impl] - out[0]).max() <= 2e-2 * np.abs(out[0]).max()
-    # fused layer1 BasicBlocks (default) are bit-identical to the two-kernel path: same MMAs, same rounding points
+    # fused layer1 BasicBlocks are bit-identical to the two-kernel path when both use plain TMEM rings (same MMAs,
+    # same rounding points); the default ghost-block rings (no seam-split MMAs) add two fp32 partial sums for two
+    # ring slots, which moves results by fp32 rounding only
+    ctx.set_option("conv_ghost", 0)
+    plain = ctx.emb_trunk(ref_fb.to(dev)).cpu().numpy()
     ctx.set_option("conv_fuse", 0)
     unfused = ctx.emb_trunk(ref_fb.to(dev)).cpu().numpy()
     ctx.set_option("conv_fuse", 1)
-    assert np.array_equal(unfused, out[8])
+    ctx.set_option("conv_ghost", 1)
+    assert np.array_equal(unfused, plain)
+    assert np.abs(plain - out[8]).max() <= 2e-3 * np.abs(plain).max()
+    rel = np.abs(plain - ref_frames.numpy()).max() / np.abs(ref_frames.numpy()).max()
+    assert rel < 2e-2
     rng = np.random.default_rng(0)
     masks = (rng.uniform(size=(n, 3, 589)) < 0.5).astype(np.uint8)
     masks[0, 2] = 0                                        # all-zero weights (test_stats_pool.py:111-131 case)
