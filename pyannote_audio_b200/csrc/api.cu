@@ -19,7 +19,8 @@ struct b200_ctx {
   int seg_conv_impl = 1;   // 1 = SincNet Conv1d(k=5) layers on tcgen05 (split fp16), 0 = fp32 CUDA-core kernel
   int seg_rec_impl = 1;    // 1 = LSTM recurrence on the tensor cores (needs seg_gemm_impl = 1), 0 = fp32 SIMT cluster kernel
   int conv_fuse = 1;       // 1 = layer1 BasicBlocks as one fused kernel (conv_block32_kernel) when conv_impl == 8
-  int conv_ghost = 1;      // 1 = TMEM rings with ghost blocks (no seam-split MMAs) in conv_tc4 / conv_block32
+  int conv_ghost = 0;      // 1 = TMEM rings with ghost blocks (no seam-split MMAs) in conv_tc4 / conv_block32
+  int conv_fold = 1;       // 1 = conv_tc3 loads one pixel box per (kh, channel block), kw taps are descriptor shifts
   int conv_impl = 8;   // channels-as-M conv for C_out >= 128, strip-streaming conv for the narrow stride-1 3x3, per-tap conv otherwise
   int seg_max_batch = 4736;     // chunks per segmentation sub-batch (37 LSTM tiles of 128 sequences x 2 directions = 74 clusters)
   int emb_max_batch = 256;      // chunks per embedding sub-batch
@@ -257,6 +258,7 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value) {
   else if (k == "seg_conv_impl") ctx->seg_conv_impl = (int)value;
   else if (k == "conv_fuse") ctx->conv_fuse = (int)value;
   else if (k == "conv_ghost") ctx->conv_ghost = (int)value;
+  else if (k == "conv_fold") ctx->conv_fold = (int)value;
   else B200_CHECK(false, B200_ERR_INVALID, "unknown option '%s'", key);
   B200_CHECK(ctx->seg_max_batch >= 1 && ctx->emb_max_batch >= 1 && ctx->conv_impl >= 0 && ctx->conv_impl <= 8,
              B200_ERR_INVALID, "option '%s' value %lld out of range", key, (long long)value);
@@ -637,6 +639,10 @@ static size_t carve_emb(int NB, void* base, EmbWs* w) {
   return align_up(off, 1024);
 }
 
+static int conv_flags(const b200_ctx* ctx) {
+  return (ctx->conv_ghost ? kConvGhost : 0) | (ctx->conv_fold ? kConvFold : 0);
+}
+
 // one BasicBlock on nb segments: A -> (Bf, Cf) -> A, in place on the residual
 static int block_run(b200_ctx* ctx, const BlockWeights& B, __half* A, __half* Bf, __half* Cf, int nb, int H, int Wd,
                      cudaStream_t st) {
@@ -645,14 +651,14 @@ static int block_run(b200_ctx* ctx, const BlockWeights& B, __half* A, __half* Bf
   const int impl_s1 = ctx->conv_impl == 2 ? 1 : ctx->conv_impl;
   const int Ho = (H + 2 - 3) / s + 1, Wo = (Wd + 2 - 3) / s + 1;
   int rc;
-  if ((rc = conv_forward(B.conv1, A, nullptr, Bf, nb, H, Wd, 1, impl1, ctx->num_sms, st, ctx->conv_ghost))) return rc;
+  if ((rc = conv_forward(B.conv1, A, nullptr, Bf, nb, H, Wd, 1, impl1, ctx->num_sms, st, conv_flags(ctx)))) return rc;
   const __half* res = A;
   if (B.has_shortcut) {
-    if ((rc = conv_forward(B.shortcut, A, nullptr, Cf, nb, H, Wd, 0, impl1, ctx->num_sms, st, ctx->conv_ghost))) return rc;
+    if ((rc = conv_forward(B.shortcut, A, nullptr, Cf, nb, H, Wd, 0, impl1, ctx->num_sms, st, conv_flags(ctx)))) return rc;
     res = Cf;
     ctx->launches += 1;
   }
-  if ((rc = conv_forward(B.conv2, Bf, res, A, nb, Ho, Wo, 1, impl_s1, ctx->num_sms, st, ctx->conv_ghost))) return rc;
+  if ((rc = conv_forward(B.conv2, Bf, res, A, nb, Ho, Wo, 1, impl_s1, ctx->num_sms, st, conv_flags(ctx)))) return rc;
   ctx->launches += 2;
   return B200_OK;
 }

@@ -46,9 +46,12 @@ struct EmbWeights {
   float* twiddle = nullptr;      // [256][2] cos/sin(-2 pi k / 512)
 };
 
+// flags of conv_forward / conv_block32_forward
+constexpr int kConvGhost = 1;   // TMEM rings with ghost blocks (conv_tc4 / conv_block32)
+constexpr int kConvFold = 2;    // conv_tc3: horizontal taps as descriptor shifts of one pixel box per (kh, channel block)
 // impl: 0 = SIMT reference conv, 1 = tcgen05 tensor-core conv
 int conv_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H_in, int W_in,
-                 int relu, int impl, int num_sms, cudaStream_t stream, int ghost = 1);
+                 int relu, int impl, int num_sms, cudaStream_t stream, int flags = kConvGhost | kConvFold);
 // fused BasicBlock of layer1 (two 32->32 stride-1 convs + identity shortcut), out must not alias in
 int conv_block32_forward(const ConvLayer& L1, const ConvLayer& L2, const __half* in, __half* out, int B, int H, int W,
                          int num_sms, cudaStream_t stream, int ghost = 1);

@@ -473,6 +473,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 struct ConvV3Params {
   int B, H, W, C_in, C_out;                // H, W: OUTPUT size (the input size only lives in the tensor map)
   int stride, pad, ksize;                  // 3x3 pad 1 (stride 1 or 2) or 1x1 pad 0 (stride 2: the block shortcuts)
+  int fold;                                // 1: a stage holds one (kh, channel block): 3 weight taps + ONE pixel box with
+                                           //    a one-pixel halo, the kw taps are descriptor shifts (stride-1 3x3 only)
+  int pitch;                               // accumulator columns per image row of the tile: bw (+ 2 halo columns if fold)
   int Ck, ncc, kblocks, bw, bh, tiles_w, tiles_h, m_tiles, num_items, relu;
   const float* bias;
   const __half* residual;
@@ -542,14 +545,21 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (leader) {
           mbar_expect_tx(bar_full + 8 * stage, p.b_bytes);   // bytes delivered by the two boxes
           const uint32_t sa = stage0 + stage * p.stage_bytes;
-          tma_load_3d(&tmW, bar_full + 8 * stage, sa, cc * p.Ck, mt * 128, tap);
-          // stride 2: the tensor map steps 2 elements along W and H, coordinates stay in input pixels
-          tma_load_4d(&tmX, bar_full + 8 * stage, sa + p.a_bytes, cc * p.Ck, w0 * p.stride + kw - p.pad,
-                      h0 * p.stride + kh - p.pad, b);
+          if (p.fold) {
+            // the three horizontal taps of row kh share one pixel box (one-pixel halo left and right, zero filled)
+            tma_load_3d(&tmW, bar_full + 8 * stage, sa, cc * p.Ck, mt * 128, kh * 3);
+            tma_load_4d(&tmX, bar_full + 8 * stage, sa + p.a_bytes, cc * p.Ck, w0 - 1, h0 + kh - 1, b);
+          } else {
+            tma_load_3d(&tmW, bar_full + 8 * stage, sa, cc * p.Ck, mt * 128, tap);
+            // stride 2: the tensor map steps 2 elements along W and H, coordinates stay in input pixels
+            tma_load_4d(&tmX, bar_full + 8 * stage, sa + p.a_bytes, cc * p.Ck, w0 * p.stride + kw - p.pad,
+                        h0 * p.stride + kh - p.pad, b);
+          }
         }
         __syncwarp();
         if (++stage == p.nstages) { stage = 0; phase ^= 1; }
-        if (++cc == p.ncc) { cc = 0; ++tap; if (++kw == p.ksize) { kw = 0; ++kh; } }
+        if (p.fold) { if (++cc == p.ncc) { cc = 0; ++kh; } }
+        else if (++cc == p.ncc) { cc = 0; ++tap; if (++kw == p.ksize) { kw = 0; ++kh; } }
       }
     }
   } else if (warp == 1) {
@@ -566,11 +576,27 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (leader) {
           const uint32_t sa = stage0 + stage * p.stage_bytes;
           const uint32_t alo = desc_lo(sa), blo = desc_lo(sa + p.a_bytes);
-          tc_mma_f16(d_tmem, desc_from(dhi, alo), desc_from(dhi, blo), p.idesc, kb != 0);
-          tc_mma_f16(d_tmem, desc_from(dhi, alo + 2), desc_from(dhi, blo + 2), p.idesc, 1);
-          if (ksteps == 4) {
-            tc_mma_f16(d_tmem, desc_from(dhi, alo + 4), desc_from(dhi, blo + 4), p.idesc, 1);
-            tc_mma_f16(d_tmem, desc_from(dhi, alo + 6), desc_from(dhi, blo + 6), p.idesc, 1);
+          if (p.fold) {
+            // tap kw: weight tile kw of the 3-tap box (128 rows x Ck), pixel rows shifted by kw (absolute-address
+            // swizzle: the descriptor start moves by one pixel row, base_offset stays 0)
+            const uint32_t a_tap = (128u * (uint32_t)p.Ck * 2u) >> 4, b_row = ((uint32_t)p.Ck * 2u) >> 4;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              tc_mma_f16(d_tmem, desc_from(dhi, alo + kw * a_tap), desc_from(dhi, blo + kw * b_row), p.idesc,
+                         (kb | kw) != 0);
+              tc_mma_f16(d_tmem, desc_from(dhi, alo + kw * a_tap + 2), desc_from(dhi, blo + kw * b_row + 2), p.idesc, 1);
+              if (ksteps == 4) {
+                tc_mma_f16(d_tmem, desc_from(dhi, alo + kw * a_tap + 4), desc_from(dhi, blo + kw * b_row + 4), p.idesc, 1);
+                tc_mma_f16(d_tmem, desc_from(dhi, alo + kw * a_tap + 6), desc_from(dhi, blo + kw * b_row + 6), p.idesc, 1);
+              }
+            }
+          } else {
+            tc_mma_f16(d_tmem, desc_from(dhi, alo), desc_from(dhi, blo), p.idesc, kb != 0);
+            tc_mma_f16(d_tmem, desc_from(dhi, alo + 2), desc_from(dhi, blo + 2), p.idesc, 1);
+            if (ksteps == 4) {
+              tc_mma_f16(d_tmem, desc_from(dhi, alo + 4), desc_from(dhi, blo + 4), p.idesc, 1);
+              tc_mma_f16(d_tmem, desc_from(dhi, alo + 6), desc_from(dhi, blo + 6), p.idesc, 1);
+            }
           }
           tc_commit(bar_empty + 8 * stage);
         }
@@ -591,7 +617,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     __half* s_res = reinterpret_cast<__half*>(s_stage_ep + (half * 4 + q) * 4096 + 2048);   // [32 px][32 ch]
     const int prow = lane >> 2, ppart = lane & 3;          // cooperative 16-byte I/O: 8 pixels x 4 parts per pass
     uint32_t acc = 0, acc_phase = 0;
-    const int npix = p.bw * p.bh;
+    const int npix = p.pitch * p.bh;                       // accumulator columns in use (halo columns are skipped)
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       int b, h0, w0, mt;
       decode(item, b, h0, w0, mt);
@@ -605,8 +631,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int n = n0 + i * 8 + prow;
-          const int rr = n / p.bw, x = n - rr * p.bw;
-          const bool ok = ch_ok && n < npix && (h0 + rr) < p.H && (w0 + x) < p.W;
+          const int rr = n / p.pitch, x = n - rr * p.pitch;
+          const bool ok = ch_ok && n < npix && x < p.bw && (h0 + rr) < p.H && (w0 + x) < p.W;
           dst[i] = ok ? (((long long)b * p.H + h0 + rr) * p.W + w0 + x) : -1;
         }
       };
@@ -751,11 +777,30 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (warp >= 2) {                                         // all 512 columns start at zero
-    const uint32_t grp = (uint32_t)(warp - 2) >> 2;
-    const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * 256u;
+  // accumulator blocks start from the BIAS (written with tcgen05.st, re-written by the epilogue after it drained a
+  // block): the epilogue then needs no bias load / add (the smem bias loads + dependent FADDs were 45 % of its stall
+  // samples).  Ghost positions start from zero: they are added to a real block.
+  auto st_bias = [&](uint32_t ta, int hb) {                // 32 bias values of half hb from smem -> TMEM columns
+    uint32_t bb[32];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) tc_st32_zero(t0 + c * 32);
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const uint4 v = reinterpret_cast<const uint4*>(s_bias)[hb * 8 + j4];
+      bb[4 * j4] = v.x; bb[4 * j4 + 1] = v.y; bb[4 * j4 + 2] = v.z; bb[4 * j4 + 3] = v.w;
+    }
+    tc_st32_regs(ta, bb);
+  };
+  __syncthreads();                                         // s_bias visible
+  if (warp >= 2) {
+    const uint32_t grp = (uint32_t)(warp - 2) >> 2;
+    const uint32_t lanes0 = (uint32_t)((warp & 3) * 32) << 16;
+    for (uint32_t pos = grp; pos < 512u / C; pos += 2) {
+#pragma unroll
+      for (int hb = 0; hb < C / 32; ++hb) {
+        const uint32_t ta = tmem_base + lanes0 + pos * (uint32_t)C + hb * 32;
+        if (pos < NBL) st_bias(ta, hb);
+        else tc_st32_zero(ta);
+      }
+    }
     tc_wait_st();
   }
   tc_fence_before();
@@ -901,7 +946,7 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int hb = 0; hb < C / 32; ++hb) {              // 32 columns at a time (register budget)
           uint32_t acc[32];
           tc_ld32(taddr + hb * 32, acc);
-          tc_st32_zero(taddr + hb * 32);                   // hand the block back zeroed
+          st_bias(taddr + hb * 32, hb);                    // hand the block back holding the bias
           if (has_ghost) {
             uint32_t gacc[32];
             tc_ld32(gaddr + hb * 32, gacc);
@@ -919,12 +964,10 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
               const int j4 = hb * 4 + jj;
-              const float4 b0 = reinterpret_cast<const float4*>(s_bias)[2 * j4];
-              const float4 b1 = reinterpret_cast<const float4*>(s_bias)[2 * j4 + 1];
-              float v[8] = {__uint_as_float(acc[jj * 8 + 0]) + b0.x, __uint_as_float(acc[jj * 8 + 1]) + b0.y,
-                            __uint_as_float(acc[jj * 8 + 2]) + b0.z, __uint_as_float(acc[jj * 8 + 3]) + b0.w,
-                            __uint_as_float(acc[jj * 8 + 4]) + b1.x, __uint_as_float(acc[jj * 8 + 5]) + b1.y,
-                            __uint_as_float(acc[jj * 8 + 6]) + b1.z, __uint_as_float(acc[jj * 8 + 7]) + b1.w};
+              float v[8] = {__uint_as_float(acc[jj * 8 + 0]), __uint_as_float(acc[jj * 8 + 1]),
+                            __uint_as_float(acc[jj * 8 + 2]), __uint_as_float(acc[jj * 8 + 3]),
+                            __uint_as_float(acc[jj * 8 + 4]), __uint_as_float(acc[jj * 8 + 5]),
+                            __uint_as_float(acc[jj * 8 + 6]), __uint_as_float(acc[jj * 8 + 7])};
               if (p.residual) {
                 const __half2* h2 = reinterpret_cast<const __half2*>(&rpre[j4]);
 #pragma unroll
@@ -1027,11 +1070,26 @@ conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (warp >= 2 && warp < 18) {                             // both rings start at zero (every MMA accumulates)
-    const uint32_t grp = (uint32_t)(warp - 2) >> 2;         // 4 warpgroups x 128 columns
+  // ring blocks start from the bias of their conv (see conv_tc4_kernel), ghost positions from zero
+  auto st_bias = [&](uint32_t ta, const float* sb) {       // the 32 bias values of a conv from smem -> TMEM columns
+    uint32_t bb[32];
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const uint4 v = reinterpret_cast<const uint4*>(sb)[j4];
+      bb[4 * j4] = v.x; bb[4 * j4 + 1] = v.y; bb[4 * j4 + 2] = v.z; bb[4 * j4 + 3] = v.w;
+    }
+    tc_st32_regs(ta, bb);
+  };
+  __syncthreads();                                          // s_b1 / s_b2 visible
+  if (warp >= 2 && warp < 18) {
+    const uint32_t grp = (uint32_t)(warp - 2) >> 2;         // 4 warpgroups x 128 columns: 0,1 -> ring 1, 2,3 -> ring 2
     const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * 128u;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) tc_st32_zero(t0 + c * 32);
+    for (int c = 0; c < 4; ++c) {
+      const uint32_t pos = (grp & 1u) * 4u + (uint32_t)c;  // position inside the ring
+      if (pos < NBL) st_bias(t0 + c * 32, grp < 2 ? s_b1 : s_b2);
+      else tc_st32_zero(t0 + c * 32);
+    }
     tc_wait_st();
   }
   tc_fence_before();
@@ -1185,7 +1243,7 @@ conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + Ring::pos(blk) * 32u;
         uint32_t acc[32];
         tc_ld32(taddr, acc);
-        tc_st32_zero(taddr);
+        st_bias(taddr, s_b1);                               // hand the block back holding b1
         if (GHOST && blk >= NBL - 2u) {                     // warp-uniform: add the ghost block of this ring slot
           const uint32_t gaddr = tmem_base + ((uint32_t)(q * 32) << 16) + Ring::ghost_pos(blk) * 32u;
           uint32_t gacc[32];
@@ -1204,14 +1262,12 @@ conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 b0 = reinterpret_cast<const float4*>(s_b1)[2 * j4];
-          const float4 b1 = reinterpret_cast<const float4*>(s_b1)[2 * j4 + 1];
           uint4 v;
           __half2* o2 = reinterpret_cast<__half2*>(&v);
-          o2[0] = __hmax2(__floats2half2_rn(__uint_as_float(acc[j4 * 8 + 0]) + b0.x, __uint_as_float(acc[j4 * 8 + 1]) + b0.y), zero2);
-          o2[1] = __hmax2(__floats2half2_rn(__uint_as_float(acc[j4 * 8 + 2]) + b0.z, __uint_as_float(acc[j4 * 8 + 3]) + b0.w), zero2);
-          o2[2] = __hmax2(__floats2half2_rn(__uint_as_float(acc[j4 * 8 + 4]) + b1.x, __uint_as_float(acc[j4 * 8 + 5]) + b1.y), zero2);
-          o2[3] = __hmax2(__floats2half2_rn(__uint_as_float(acc[j4 * 8 + 6]) + b1.z, __uint_as_float(acc[j4 * 8 + 7]) + b1.w), zero2);
+          o2[0] = __hmax2(__floats2half2_rn(__uint_as_float(acc[j4 * 8 + 0]), __uint_as_float(acc[j4 * 8 + 1])), zero2);
+          o2[1] = __hmax2(__floats2half2_rn(__uint_as_float(acc[j4 * 8 + 2]), __uint_as_float(acc[j4 * 8 + 3])), zero2);
+          o2[2] = __hmax2(__floats2half2_rn(__uint_as_float(acc[j4 * 8 + 4]), __uint_as_float(acc[j4 * 8 + 5])), zero2);
+          o2[3] = __hmax2(__floats2half2_rn(__uint_as_float(acc[j4 * 8 + 6]), __uint_as_float(acc[j4 * 8 + 7])), zero2);
           if (!keep) v = make_uint4(0, 0, 0, 0);
           const uint32_t a = row_addr + (((uint32_t)j4 ^ sw) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
@@ -1235,26 +1291,24 @@ conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int R = h1 - h0;
       const int w = wt * 126 - 1 + m;
       const bool valid = m >= 1 && m <= 126 && w < p.W;
-      uint4 rpre[4], rnext[4];                               // residual = block input (L2: just streamed), one row ahead
+      uint4 rpre[4];                                         // residual = block input (L2: just streamed)
       auto res_row = [&](int r) { return (((size_t)b * p.H + (h0 + r)) * p.W + (valid ? w : 0)) * 32; };
-      auto load_res = [&](int r, uint4 (&dst)[4]) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.in + res_row(r));
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) dst[j4] = valid ? __ldg(rp + j4) : make_uint4(0, 0, 0, 0);
-      };
       const int r_first = (int)((grp - (grow2 & 1u)) & 1u);
-      if (r_first < R) load_res(r_first, rpre);
       for (int r = r_first; r < R; r += 2) {
         const uint32_t g = grow2 + (uint32_t)r;
         const uint32_t blk = Ring::idx(g);
         const size_t pix = res_row(r);
-        if (r + 2 < R) load_res(r + 2, rnext);
+        {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.in + pix);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) rpre[j4] = valid ? __ldg(rp + j4) : make_uint4(0, 0, 0, 0);
+        }
         mbar_wait(bar_t2full + 8 * blk, Ring::phase(g));
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + Ring::pos(blk) * 32u;
         uint32_t acc[32];
         tc_ld32(taddr, acc);
-        tc_st32_zero(taddr);
+        st_bias(taddr, s_b2);                               // hand the block back holding b2
         if (GHOST && blk >= NBL - 2u) {
           const uint32_t gaddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + Ring::ghost_pos(blk) * 32u;
           uint32_t gacc[32];
@@ -1272,12 +1326,10 @@ conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 b0 = reinterpret_cast<const float4*>(s_b2)[2 * j4];
-            const float4 b1 = reinterpret_cast<const float4*>(s_b2)[2 * j4 + 1];
-            float v[8] = {__uint_as_float(acc[j4 * 8 + 0]) + b0.x, __uint_as_float(acc[j4 * 8 + 1]) + b0.y,
-                          __uint_as_float(acc[j4 * 8 + 2]) + b0.z, __uint_as_float(acc[j4 * 8 + 3]) + b0.w,
-                          __uint_as_float(acc[j4 * 8 + 4]) + b1.x, __uint_as_float(acc[j4 * 8 + 5]) + b1.y,
-                          __uint_as_float(acc[j4 * 8 + 6]) + b1.z, __uint_as_float(acc[j4 * 8 + 7]) + b1.w};
+            float v[8] = {__uint_as_float(acc[j4 * 8 + 0]), __uint_as_float(acc[j4 * 8 + 1]),
+                          __uint_as_float(acc[j4 * 8 + 2]), __uint_as_float(acc[j4 * 8 + 3]),
+                          __uint_as_float(acc[j4 * 8 + 4]), __uint_as_float(acc[j4 * 8 + 5]),
+                          __uint_as_float(acc[j4 * 8 + 6]), __uint_as_float(acc[j4 * 8 + 7])};
             const __half2* h2 = reinterpret_cast<const __half2*>(&rpre[j4]);
             uint4 u;
             __half2* o2 = reinterpret_cast<__half2*>(&u);
@@ -1288,10 +1340,6 @@ conv_block32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             op[j4] = u;
           }
-        }
-        if (r + 2 < R) {
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) rpre[j4] = rnext[j4];
         }
       }
       grow2 += (uint32_t)R;
@@ -1577,7 +1625,7 @@ int conv_block32_forward(const ConvLayer& L1, const ConvLayer& L2, const __half*
 }
 
 static int conv3_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H_in,
-                         int W_in, int relu, int num_sms, cudaStream_t stream) {
+                         int W_in, int relu, int fold, int num_sms, cudaStream_t stream) {
   B200_CHECK(L.w3 != nullptr, B200_ERR_STATE, "conv v3: padded weights missing");
   B200_CHECK((L.ksize == 3 || L.ksize == 1) && (L.stride == 1 || L.stride == 2), B200_ERR_STATE,
              "conv v3: %dx%d stride %d unsupported", L.ksize, L.ksize, L.stride);
@@ -1586,24 +1634,40 @@ static int conv3_forward(const ConvLayer& L, const __half* in, const __half* res
   const int H = (H_in + 2 * p.pad - L.ksize) / L.stride + 1, W = (W_in + 2 * p.pad - L.ksize) / L.stride + 1;
   p.B = B; p.H = H; p.W = W; p.C_in = L.C_in; p.C_out = L.C_out; p.relu = relu;
   p.bias = L.bias; p.residual = residual; p.out = out;
-  p.Ck = (L.C_in >= 64) ? 64 : 32;
+  // fold (stride-1 3x3, the 16 layer3/4 convs): the per-tap version moved every activation element L2 -> smem nine
+  // times and ran at the L2 bandwidth (10.4 TB/s, profiles/r01_conv_tc3_layer3.ncu-rep) 1.8x above its MMA floor.
+  // One stage = (kh, 32 input channels): the 3 weight taps of that row + ONE pixel box with a one-pixel halo; the kw
+  // taps are descriptor shifts of one pixel row.  Pixel traffic 9x -> 3x, 6 MMAs per stage.
+  p.fold = (L.ksize == 3 && L.stride == 1 && fold) ? 1 : 0;
+  p.Ck = p.fold ? 32 : ((L.C_in >= 64) ? 64 : 32);
   p.ncc = L.C_in / p.Ck;
-  p.kblocks = L.ksize * L.ksize * p.ncc;
+  p.kblocks = p.fold ? 3 * p.ncc : L.ksize * L.ksize * p.ncc;
   p.swizzle = (p.Ck == 64) ? 128 : 64;
   // pixel tile: up to 256 output pixels of one image; several rows when the image is narrower.  A TMA box dimension
   // is at most 256 elements, and a strided box spans bw * stride input pixels: stride 2 -> at most 128 per row
-  const int max_bw = 256 / L.stride;
-  if (W >= max_bw) { p.bw = max_bw; p.bh = 256 / max_bw; }
-  else { p.bw = W; p.bh = 256 / W; }
-  if (p.bh > H) p.bh = H;
-  if (p.bh * L.stride > 256) p.bh = 256 / L.stride;
+  if (p.fold) {
+    // accumulator column of pixel (rr, x) = rr * (bw + 2) + x; the shifted reads need bh * (bw + 2) <= 258 rows
+    p.bw = W < 254 ? W : 254;
+    p.bh = 258 / (p.bw + 2);
+    if (p.bh > H) p.bh = H;
+    p.pitch = p.bw + 2;
+  } else {
+    const int max_bw = 256 / L.stride;
+    if (W >= max_bw) { p.bw = max_bw; p.bh = 256 / max_bw; }
+    else { p.bw = W; p.bh = 256 / W; }
+    if (p.bh > H) p.bh = H;
+    if (p.bh * L.stride > 256) p.bh = 256 / L.stride;
+    p.pitch = p.bw;
+  }
   p.tiles_w = ceil_div(W, p.bw);
   p.tiles_h = ceil_div(H, p.bh);
   p.m_tiles = ceil_div(L.C_out, 128);
   p.num_items = B * p.tiles_h * p.tiles_w * p.m_tiles;
-  p.a_bytes = 128u * p.Ck * 2;
-  const uint32_t b_full = 256u * p.Ck * 2;                 // the MMA reads N = 256 rows: keep the slot that large
-  const uint32_t delivered = p.a_bytes + (uint32_t)p.bw * p.bh * p.Ck * 2;   // bytes the two TMA boxes deliver
+  const int wtaps = p.fold ? 3 : 1;                        // weight taps per stage
+  p.a_bytes = (uint32_t)wtaps * 128u * p.Ck * 2;
+  // the MMA reads N = 256 rows (from a start shifted by up to 2 rows when folding): keep the slot that large
+  const uint32_t b_full = (uint32_t)align_up((size_t)(256 + (p.fold ? 2 : 0)) * p.Ck * 2, 1024);
+  const uint32_t delivered = p.a_bytes + (uint32_t)p.pitch * p.bh * p.Ck * 2;   // bytes the two TMA boxes deliver
   const uint32_t slot = p.a_bytes + b_full;
   p.stage_bytes = slot;                                     // the kernel addresses stage s at stage0 + s * stage_bytes
   p.b_bytes = delivered;                                    // bytes to expect per stage
@@ -1617,7 +1681,7 @@ static int conv3_forward(const ConvLayer& L, const __half* in, const __half* res
     cuuint64_t dims[4] = {(cuuint64_t)L.C_in, (cuuint64_t)W_in, (cuuint64_t)H_in, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)L.C_in * 2, (cuuint64_t)W_in * L.C_in * 2,
                              (cuuint64_t)H_in * W_in * L.C_in * 2};
-    cuuint32_t box[4] = {(cuuint32_t)p.Ck, (cuuint32_t)(p.bw * L.stride), (cuuint32_t)(p.bh * L.stride), 1};
+    cuuint32_t box[4] = {(cuuint32_t)p.Ck, (cuuint32_t)(p.pitch * L.stride), (cuuint32_t)(p.bh * L.stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)L.stride, (cuuint32_t)L.stride, 1};
     CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(in), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1629,7 +1693,7 @@ static int conv3_forward(const ConvLayer& L, const __half* in, const __half* res
     const int rows = p.m_tiles * 128;                       // padded output-channel rows
     cuuint64_t dims[3] = {(cuuint64_t)L.C_in, (cuuint64_t)rows, (cuuint64_t)(L.ksize * L.ksize)};
     cuuint64_t strides[2] = {(cuuint64_t)L.C_in * 2, (cuuint64_t)rows * L.C_in * 2};
-    cuuint32_t box[3] = {(cuuint32_t)p.Ck, 128, 1};
+    cuuint32_t box[3] = {(cuuint32_t)p.Ck, 128, (cuuint32_t)wtaps};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(L.w3), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1733,13 +1797,14 @@ static int conv2_forward(const ConvLayer& L, const __half* in, const __half* res
 }
 
 int conv_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H_in, int W_in,
-                 int relu, int impl, int num_sms, cudaStream_t stream, int ghost) {
+                 int relu, int impl, int num_sms, cudaStream_t stream, int flags) {
+  const int ghost = flags & kConvGhost, fold = (flags & kConvFold) ? 1 : 0;
   if (impl == 7 || impl == 8) {
     // channels-as-M tcgen05 conv for stride-1 3x3 with C_out >= 128 (N = 256 pixels balances the A-operand read);
     // impl 8 (default): narrower layers use the strip-streaming pixels-as-M kernel, impl 7: the per-tap kernel
     // (impl 8 also sends the stride-2 3x3 convs and the 1x1 stride-2 shortcuts there: TMA element strides)
     if ((L.ksize == 3 && L.stride == 1 && L.C_out >= 128) || (impl == 8 && L.stride == 2 && L.w3))
-      return conv3_forward(L, in, residual, out, B, H_in, W_in, relu, num_sms, stream);
+      return conv3_forward(L, in, residual, out, B, H_in, W_in, relu, fold, num_sms, stream);
     if (impl == 8 && L.ksize == 3 && L.stride == 1 && L.C_in == L.C_out && L.C_in <= 64 && L.w4)
       return conv4_forward(L, in, residual, out, B, H_in, W_in, relu, ghost, num_sms, stream);   // vertical taps folded into N
     impl = (impl == 8) ? 6 : 1;

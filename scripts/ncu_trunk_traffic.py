@@ -4,6 +4,7 @@ reads for `roofline.traffic`.   Usage: python scripts/ncu_trunk_traffic.py launc
 import collections
 import csv
 import json
+import re
 import sys
 
 TRUNK = ("conv1_kernel", "conv_block32_kernel", "conv_block64_kernel", "conv_tc_kernel", "conv_tc4_kernel",
@@ -17,7 +18,8 @@ def main(src, dst):
     ix = {h: i for i, h in enumerate(rows[hi])}
     per = collections.OrderedDict()
     for r in rows[hi + 1:]:
-        d = per.setdefault(int(r[ix["ID"]]), {"name": r[ix["Kernel Name"]].split("(")[0].replace("b200::", "")})
+        name = re.sub(r"<.*", "", r[ix["Kernel Name"]].split("(")[0].replace("void ", "").replace("b200::", ""))
+        d = per.setdefault(int(r[ix["ID"]]), {"name": name})
         d[r[ix["Metric Name"]]] = float(r[ix["Metric Value"]].replace(",", "")) * UNIT[r[ix["Metric Unit"]]]
     launches = [d for _, d in sorted(per.items()) if d["name"] in TRUNK]
     half = launches[len(launches) // 2:]                     # second (warm) pass

@@ -179,16 +179,23 @@ def test_embedding_parity(ctx, dev, oracle_models):
     # fused layer1 BasicBlocks are bit-identical to the two-kernel path when both use plain TMEM rings (same MMAs,
     # same rounding points); the default ghost-block rings (no seam-split MMAs) add two fp32 partial sums for two
     # ring slots, which moves results by fp32 rounding only
-    ctx.set_option("conv_ghost", 0)
-    plain = ctx.emb_trunk(ref_fb.to(dev)).cpu().numpy()
+    plain = out[8]                                        # default: plain rings, fused layer1, folded tc3 taps
     ctx.set_option("conv_fuse", 0)
     unfused = ctx.emb_trunk(ref_fb.to(dev)).cpu().numpy()
     ctx.set_option("conv_fuse", 1)
-    ctx.set_option("conv_ghost", 1)
     assert np.array_equal(unfused, plain)
-    assert np.abs(plain - out[8]).max() <= 2e-3 * np.abs(plain).max()
-    rel = np.abs(plain - ref_frames.numpy()).max() / np.abs(ref_frames.numpy()).max()
-    assert rel < 2e-2
+    ctx.set_option("conv_ghost", 1)
+    ghost = ctx.emb_trunk(ref_fb.to(dev)).cpu().numpy()
+    ctx.set_option("conv_ghost", 0)
+    assert np.abs(plain - ghost).max() <= 2e-3 * np.abs(plain).max()
+    # conv_tc3 with one pixel box per (kh, channel block) and descriptor-shifted horizontal taps (default) against
+    # the per-tap staging: the same products in a different accumulation order
+    ctx.set_option("conv_fold", 0)
+    per_tap = ctx.emb_trunk(ref_fb.to(dev)).cpu().numpy()
+    ctx.set_option("conv_fold", 1)
+    assert np.abs(plain - per_tap).max() <= 2e-3 * np.abs(plain).max()
+    for variant in (ghost, per_tap):
+        assert np.abs(variant - ref_frames.numpy()).max() / np.abs(ref_frames.numpy()).max() < 2e-2
     rng = np.random.default_rng(0)
     masks = (rng.uniform(size=(n, 3, 589)) < 0.5).astype(np.uint8)
     masks[0, 2] = 0                                        # all-zero weights (test_stats_pool.py:111-131 case)
