@@ -21,6 +21,7 @@ struct b200_ctx {
   int conv_fuse = 1;       // 1 = layer1 BasicBlocks as one fused kernel (conv_block32_kernel) when conv_impl == 8
   int conv_ghost = 0;      // 1 = TMEM rings with ghost blocks (no seam-split MMAs) in conv_tc4 / conv_block32
   int conv_fold = 1;       // 1 = conv_tc3 loads one pixel box per (kh, channel block), kw taps are descriptor shifts
+  int conv_scfold = 1;     // 1 = layer2.0: the 1x1 stride-2 shortcut rides in the padded weight rows of the stride-2 conv
   int conv_impl = 8;   // channels-as-M conv for C_out >= 128, strip-streaming conv for the narrow stride-1 3x3, per-tap conv otherwise
   int seg_max_batch = 4736;     // chunks per segmentation sub-batch (37 LSTM tiles of 128 sequences x 2 directions = 74 clusters)
   int emb_max_batch = 256;      // chunks per embedding sub-batch
@@ -259,6 +260,7 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value) {
   else if (k == "conv_fuse") ctx->conv_fuse = (int)value;
   else if (k == "conv_ghost") ctx->conv_ghost = (int)value;
   else if (k == "conv_fold") ctx->conv_fold = (int)value;
+  else if (k == "conv_scfold") ctx->conv_scfold = (int)value;
   else B200_CHECK(false, B200_ERR_INVALID, "unknown option '%s'", key);
   B200_CHECK(ctx->seg_max_batch >= 1 && ctx->emb_max_batch >= 1 && ctx->conv_impl >= 0 && ctx->conv_impl <= 8,
              B200_ERR_INVALID, "option '%s' value %lld out of range", key, (long long)value);
@@ -518,6 +520,26 @@ int b200_emb_load(b200_ctx* ctx, const b200_emb_weights* w) {
       B.has_shortcut = (s != 1 || in_planes != planes[l]);
       if (B.has_shortcut) {
         if ((rc = make_conv(ctx, w->block_shortcut[bi], in_planes, planes[l], 1, s, &B.shortcut))) return rc;
+        if (planes[l] == 64 && s == 2) {
+          // the 64 zero-padded rows of conv1's 128-row channels-as-M weight tiles carry the 1x1 shortcut (centre tap)
+          const int cin = in_planes, cout = 64;
+          const b200_conv_bn &c1 = w->block_conv1[bi], &sc = w->block_shortcut[bi];
+          std::vector<__half> w3s((size_t)9 * 128 * cin, __float2half(0.f));
+          std::vector<float> bias_s(128);
+          for (int co = 0; co < cout; ++co) {
+            const float s1 = c1.bn_weight[co] / std::sqrt(c1.bn_var[co] + 1e-5f);
+            const float s2 = sc.bn_weight[co] / std::sqrt(sc.bn_var[co] + 1e-5f);
+            bias_s[co] = c1.bn_bias[co] - c1.bn_mean[co] * s1;
+            bias_s[64 + co] = sc.bn_bias[co] - sc.bn_mean[co] * s2;
+            for (int ci = 0; ci < cin; ++ci) {
+              for (int t = 0; t < 9; ++t)
+                w3s[((size_t)t * 128 + co) * cin + ci] = __float2half(c1.conv_weight[((size_t)co * cin + ci) * 9 + t] * s1);
+              w3s[((size_t)4 * 128 + 64 + co) * cin + ci] = __float2half(sc.conv_weight[(size_t)co * cin + ci] * s2);
+            }
+          }
+          if ((rc = upload(ctx, w3s, &B.conv1.w3s))) return rc;
+          if ((rc = upload(ctx, bias_s, &B.conv1.bias_s))) return rc;
+        }
       }
       in_planes = planes[l];
       E.blocks.push_back(B);
@@ -651,6 +673,13 @@ static int block_run(b200_ctx* ctx, const BlockWeights& B, __half* A, __half* Bf
   const int impl_s1 = ctx->conv_impl == 2 ? 1 : ctx->conv_impl;
   const int Ho = (H + 2 - 3) / s + 1, Wo = (Wd + 2 - 3) / s + 1;
   int rc;
+  if (ctx->conv_impl == 8 && ctx->conv_scfold && B.has_shortcut && B.conv1.w3s) {
+    // layer2.0: stride-2 conv1 and the 1x1 shortcut in one launch (the shortcut rides in the padded weight rows)
+    if ((rc = conv_s2_shortcut_forward(B.conv1, A, Bf, Cf, nb, H, Wd, ctx->num_sms, st))) return rc;
+    if ((rc = conv_forward(B.conv2, Bf, Cf, A, nb, Ho, Wo, 1, impl_s1, ctx->num_sms, st, conv_flags(ctx)))) return rc;
+    ctx->launches += 2;
+    return B200_OK;
+  }
   if ((rc = conv_forward(B.conv1, A, nullptr, Bf, nb, H, Wd, 1, impl1, ctx->num_sms, st, conv_flags(ctx)))) return rc;
   const __half* res = A;
   if (B.has_shortcut) {

@@ -480,6 +480,8 @@ struct ConvV3Params {
   const float* bias;
   const __half* residual;
   __half* out;
+  __half* out2;                            // C_split > 0: channels >= C_split go here (no ReLU), see ConvLayer::w3s
+  int C_split;
   uint32_t a_bytes, b_bytes, stage_bytes, nstages, idesc, swizzle;
 };
 
@@ -624,6 +626,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int c0 = mt * 128 + q * 32;                    // first channel of this warp
       const bool ch_ok = c0 < p.C_out;                     // C_out = 64: the upper two quadrants are zero padding
       const float bias = ch_ok ? s_bias[c0 + lane] : 0.f;
+      // two outputs (conv | folded shortcut): channels >= C_split belong to the second tensor, which has no ReLU
+      const bool second = p.C_split > 0 && c0 >= p.C_split;
+      __half* const outp = second ? p.out2 : p.out;
+      const int cq = second ? c0 - p.C_split : c0;
+      const int cstride = p.C_split > 0 ? p.C_split : p.C_out;
+      const bool relu = p.relu && !second;
       // global pixel index of the 4 pixels this lane moves per chunk (16-byte pieces), -1 when outside the image
       long long gp[4], gpn[4];
       uint4 rpre[4];
@@ -639,7 +647,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       auto load_res = [&](const long long (&g)[4]) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          rpre[i] = g[i] >= 0 ? __ldg(reinterpret_cast<const uint4*>(p.residual + g[i] * p.C_out + c0 + ppart * 8))
+          rpre[i] = g[i] >= 0 ? __ldg(reinterpret_cast<const uint4*>(p.residual + g[i] * cstride + cq + ppart * 8))
                               : make_uint4(0, 0, 0, 0);
       };
       const int first = half * 32;
@@ -669,14 +677,14 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float a = v[j];
-          if (p.relu) a = fmaxf(a, 0.f);
+          if (relu) a = fmaxf(a, 0.f);
           s_out[j * 32 + lane] = __float2half_rn(a);
         }
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (gp[i] >= 0)
-            *reinterpret_cast<uint4*>(p.out + gp[i] * p.C_out + c0 + ppart * 8) =
+            *reinterpret_cast<uint4*>(outp + gp[i] * cstride + cq + ppart * 8) =
                 *reinterpret_cast<const uint4*>(s_out + (i * 8 + prow) * 32 + ppart * 8);
         }
         __syncwarp();
@@ -1625,8 +1633,10 @@ int conv_block32_forward(const ConvLayer& L1, const ConvLayer& L2, const __half*
 }
 
 static int conv3_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H_in,
-                         int W_in, int relu, int fold, int num_sms, cudaStream_t stream) {
+                         int W_in, int relu, int fold, int num_sms, cudaStream_t stream, __half* out_sc = nullptr) {
   B200_CHECK(L.w3 != nullptr, B200_ERR_STATE, "conv v3: padded weights missing");
+  B200_CHECK(out_sc == nullptr || (L.w3s && L.bias_s && L.C_out == 64 && L.stride == 2 && L.ksize == 3),
+             B200_ERR_STATE, "conv v3: folded shortcut needs a 64-channel stride-2 3x3 conv with w3s");
   B200_CHECK((L.ksize == 3 || L.ksize == 1) && (L.stride == 1 || L.stride == 2), B200_ERR_STATE,
              "conv v3: %dx%d stride %d unsupported", L.ksize, L.ksize, L.stride);
   ConvV3Params p{};
@@ -1634,12 +1644,15 @@ static int conv3_forward(const ConvLayer& L, const __half* in, const __half* res
   const int H = (H_in + 2 * p.pad - L.ksize) / L.stride + 1, W = (W_in + 2 * p.pad - L.ksize) / L.stride + 1;
   p.B = B; p.H = H; p.W = W; p.C_in = L.C_in; p.C_out = L.C_out; p.relu = relu;
   p.bias = L.bias; p.residual = residual; p.out = out;
+  if (out_sc) { p.C_out = 128; p.C_split = 64; p.out2 = out_sc; p.bias = L.bias_s; }
   // fold (stride-1 3x3, the 16 layer3/4 convs): the per-tap version moved every activation element L2 -> smem nine
   // times and ran at the L2 bandwidth (10.4 TB/s, profiles/r01_conv_tc3_layer3.ncu-rep) 1.8x above its MMA floor.
   // One stage = (kh, 32 input channels): the 3 weight taps of that row + ONE pixel box with a one-pixel halo; the kw
   // taps are descriptor shifts of one pixel row.  Pixel traffic 9x -> 3x, 6 MMAs per stage.
   p.fold = (L.ksize == 3 && L.stride == 1 && fold) ? 1 : 0;
-  p.Ck = p.fold ? 32 : ((L.C_in >= 64) ? 64 : 32);
+  int fold_ck = 32;                                        // 4 stages of 41 KB; 64 -> 2 stages of 82 KB (A/B knob)
+  if (const char* e = getenv("B200_TC3_CK")) fold_ck = atoi(e) == 64 ? 64 : 32;
+  p.Ck = p.fold ? fold_ck : ((L.C_in >= 64) ? 64 : 32);
   p.ncc = L.C_in / p.Ck;
   p.kblocks = p.fold ? 3 * p.ncc : L.ksize * L.ksize * p.ncc;
   p.swizzle = (p.Ck == 64) ? 128 : 64;
@@ -1661,7 +1674,7 @@ static int conv3_forward(const ConvLayer& L, const __half* in, const __half* res
   }
   p.tiles_w = ceil_div(W, p.bw);
   p.tiles_h = ceil_div(H, p.bh);
-  p.m_tiles = ceil_div(L.C_out, 128);
+  p.m_tiles = ceil_div(p.C_out, 128);
   p.num_items = B * p.tiles_h * p.tiles_w * p.m_tiles;
   const int wtaps = p.fold ? 3 : 1;                        // weight taps per stage
   p.a_bytes = (uint32_t)wtaps * 128u * p.Ck * 2;
@@ -1695,7 +1708,8 @@ static int conv3_forward(const ConvLayer& L, const __half* in, const __half* res
     cuuint64_t strides[2] = {(cuuint64_t)L.C_in * 2, (cuuint64_t)rows * L.C_in * 2};
     cuuint32_t box[3] = {(cuuint32_t)p.Ck, 128, (cuuint32_t)wtaps};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(L.w3), dims, strides, box, estr,
+    CUresult r = enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(out_sc ? L.w3s : L.w3), dims, strides,
+                     box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE,
                      p.swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1711,6 +1725,11 @@ static int conv3_forward(const ConvLayer& L, const __half* in, const __half* res
   conv_tc3_kernel<<<grid, kV3Threads, smem, stream>>>(tmX, tmW, p);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
+}
+
+int conv_s2_shortcut_forward(const ConvLayer& L, const __half* in, __half* out, __half* out_sc, int B, int H_in,
+                             int W_in, int num_sms, cudaStream_t stream) {
+  return conv3_forward(L, in, nullptr, out, B, H_in, W_in, 1, 0, num_sms, stream, out_sc);
 }
 
 static int conv2_forward(const ConvLayer& L, const __half* in, const __half* residual, __half* out, int B, int H, int W,

@@ -194,6 +194,12 @@ def test_embedding_parity(ctx, dev, oracle_models):
     per_tap = ctx.emb_trunk(ref_fb.to(dev)).cpu().numpy()
     ctx.set_option("conv_fold", 1)
     assert np.abs(plain - per_tap).max() <= 2e-3 * np.abs(plain).max()
+    # layer2.0: the 1x1 stride-2 shortcut folded into the stride-2 conv's launch (default) against separate launches:
+    # the very same MMAs on the same operands -> bit-identical
+    ctx.set_option("conv_scfold", 0)
+    separate = ctx.emb_trunk(ref_fb.to(dev)).cpu().numpy()
+    ctx.set_option("conv_scfold", 1)
+    assert np.array_equal(separate, plain)
     for variant in (ghost, per_tap):
         assert np.abs(variant - ref_frames.numpy()).max() / np.abs(ref_frames.numpy()).max() < 2e-2
     rng = np.random.default_rng(0)
