@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--cpu-sample-seconds", type=float, default=24.0)
     ap.add_argument("--parallelism", default="auto", choices=["auto", "pool", "files"],
                     help="N>1 data path: global chunk pool + one all-gather (default) or collective-free file sharding")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="pool mode: embeddings pushed to peers from the GEMM epilogue over symmetric memory (p2p, "
+                         "falls back to nccl when unavailable) or one ncclAllGather")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager CUDA fp32 leg")
     ap.add_argument("--min-warmup", type=int, default=3, help="lower only when profiling under ncu")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (profiling runs)")
@@ -263,7 +266,7 @@ def main():
     audio_hours = nfiles * args.minutes / 60.0
     h2d = sum(f["waveform"].numel() * 4 for f in files)
     use_pool = pool_mode(args, world)
-    pool = ChunkPool(pipe) if use_pool else None
+    pool = ChunkPool(pipe, collective=args.collective) if use_pool else None
 
     def sync():
         torch.cuda.synchronize(dev)
@@ -328,7 +331,11 @@ def main():
         per_step = [ev[0].elapsed_time(ev[1]) for ev in coll_ms if ev is not None]
         t = torch.tensor([float(np.mean(per_step)) if per_step else 0.0], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        collective = {"op": "ncclAllGather (in place, one packed buffer: embeddings f32 | powerset classes u8)",
+        collective = {"op": ("fused: embedding GEMM epilogue pushes its tiles to every peer (P2P stores over NVLink, "
+                             "symmetric memory) + P2P copy of the powerset classes + symmetric-memory barrier; "
+                             "timed part = class copy + barrier (the embedding pushes are inside the GEMM)")
+                      if pool.collective == "p2p" else
+                      "ncclAllGather (in place, one packed buffer: embeddings f32 | powerset classes u8)",
                       "bytes_sent_per_rank": pool.last_collective["bytes_sent"],
                       "bytes_received_per_rank": pool.last_collective["bytes_received"],
                       "ms_per_step_max_over_ranks": float(t.item()),

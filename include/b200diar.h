@@ -127,6 +127,17 @@ int b200_powerset_to_multilabel(b200_ctx* ctx, const uint8_t* classes, int64_t n
  * StatsPool weights; emb[num_chunks][3][256] fp32. */
 int b200_emb_forward(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, const int32_t* chunk_valid,
                      int32_t num_chunks, const uint8_t* masks, float* emb, void* stream);
+/* The same with a fused all-gather for the multi-GPU chunk pool: emb_peers[n_peers] (HOST array
+ * of DEVICE pointers, n_peers <= 7) are this rank's slot inside the OTHER GPUs' gather buffers (peer memory mapped
+ * over NVLink, e.g. CUDA IPC / torch symmetric memory); the epilogue of the final Linear GEMM stores every output
+ * tile to `emb` and to all peers (P2P stores), so the exchange overlaps the GEMM and no collective call follows.
+ * The caller synchronises the ranks afterwards (any barrier with system-scope release/acquire). */
+int b200_emb_forward_push(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, const int32_t* chunk_valid,
+                          int32_t num_chunks, const uint8_t* masks, float* emb, float* const* emb_peers,
+                          int32_t n_peers, void* stream);
+/* P2P push of a byte range (16-byte aligned) to the same offsets of n_dsts <= 7 peer buffers: the powerset classes
+ * of this rank's chunks, next to the embeddings pushed by b200_emb_forward_push. */
+int b200_push(b200_ctx* ctx, const void* src, int64_t bytes, void* const* dsts, int32_t n_dsts, void* stream);
 /* compute_fbank (wespeaker/__init__.py:113-139): fbank[num_chunks][998][80], global-mean centred. */
 int b200_emb_fbank(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, const int32_t* chunk_valid,
                    int32_t num_chunks, float* fbank, void* stream);

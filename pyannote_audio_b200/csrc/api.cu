@@ -722,8 +722,33 @@ static int trunk_run(b200_ctx* ctx, const EmbWs& w, int nb, cudaStream_t st, con
   return B200_OK;
 }
 
+static int emb_forward_impl(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, const int32_t* chunk_valid,
+                            int32_t num_chunks, const uint8_t* masks, float* emb, float* const* emb_peers,
+                            int32_t n_peers, void* stream);
+
 int b200_emb_forward(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, const int32_t* chunk_valid,
                      int32_t num_chunks, const uint8_t* masks, float* emb, void* stream) {
+  return emb_forward_impl(ctx, wav, chunk_off, chunk_valid, num_chunks, masks, emb, nullptr, 0, stream);
+}
+
+int b200_emb_forward_push(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, const int32_t* chunk_valid,
+                          int32_t num_chunks, const uint8_t* masks, float* emb, float* const* emb_peers,
+                          int32_t n_peers, void* stream) {
+  B200_CHECK(n_peers >= 0 && n_peers <= 7 && (n_peers == 0 || emb_peers), B200_ERR_INVALID, "bad peer list");
+  return emb_forward_impl(ctx, wav, chunk_off, chunk_valid, num_chunks, masks, emb, emb_peers, n_peers, stream);
+}
+
+int b200_push(b200_ctx* ctx, const void* src, int64_t bytes, void* const* dsts, int32_t n_dsts, void* stream) {
+  B200_CHECK(ctx && src && (n_dsts == 0 || dsts) && bytes >= 0 && n_dsts >= 0, B200_ERR_INVALID, "bad arguments");
+  if (bytes == 0 || n_dsts == 0) return B200_OK;
+  DeviceGuard g(ctx->device);
+  ctx->launches += 1;
+  return push_bytes(src, bytes, dsts, n_dsts, (cudaStream_t)stream);
+}
+
+static int emb_forward_impl(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, const int32_t* chunk_valid,
+                            int32_t num_chunks, const uint8_t* masks, float* emb, float* const* emb_peers,
+                            int32_t n_peers, void* stream) {
   B200_CHECK(ctx && ctx->emb.loaded, B200_ERR_STATE, "embedding weights not loaded");
   B200_CHECK(wav && chunk_off && chunk_valid && masks && emb && num_chunks >= 0, B200_ERR_INVALID, "bad arguments");
   if (num_chunks == 0) return B200_OK;
@@ -756,8 +781,11 @@ int b200_emb_forward(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, 
       return rc;
     ctx->launches += 1;
   }
+  // the Linear 5120 -> 256 of ALL chunks; with peers its epilogue also pushes every tile to the other GPUs (fused
+  // all-gather of the embeddings over NVLink)
   rc = gemm_tc_split(st_hi, st_lo, 2 * kStatsDim, ctx->emb.seg1_w_hi, ctx->emb.seg1_w_lo, 2 * kStatsDim, emb, kEmbDim,
-                     nullptr, nullptr, 0, ctx->emb.seg1_b, (int)rows, kEmbDim, 2 * kStatsDim, 0, ctx->num_sms, st);
+                     nullptr, nullptr, 0, ctx->emb.seg1_b, (int)rows, kEmbDim, 2 * kStatsDim, 0, ctx->num_sms, st,
+                     emb_peers, n_peers);
   ctx->launches += 1;
   return rc;
 }

@@ -541,9 +541,6 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       int b, h0, w0, mt;
       decode(item, b, h0, w0, mt);
-      int nb = 0, nh0 = 0, nw0 = 0, nmt = 0;
-      const bool has_next = p.fold && item + (int)gridDim.x < p.num_items;
-      if (has_next) decode(item + gridDim.x, nb, nh0, nw0, nmt);
       int tap = 0, cc = 0, kh = 0, kw = 0;
       for (int kb = 0; kb < p.kblocks; ++kb) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -554,7 +551,6 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             // the three horizontal taps of row kh share one pixel box (one-pixel halo left and right, zero filled)
             tma_load_3d(&tmW, bar_full + 8 * stage, sa, cc * p.Ck, mt * 128, kh * 3);
             tma_load_4d(&tmX, bar_full + 8 * stage, sa + p.a_bytes, cc * p.Ck, w0 - 1, h0 + kh - 1, b);
-            if (has_next) tma_prefetch_4d(&tmX, cc * p.Ck, nw0 - 1, nh0 + kh - 1, nb);   // same box of the next tile -> L2
           } else {
             tma_load_3d(&tmW, bar_full + 8 * stage, sa, cc * p.Ck, mt * 128, tap);
             // stride 2: the tensor map steps 2 elements along W and H, coordinates stay in input pixels
@@ -921,26 +917,30 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int R = h1 - h0;
       const int w = wt * kTileM + q * 32 + lane;
       const bool valid = w < p.W;
-      // The residual of a row is requested (registers) before the accumulator wait and pulled into L2 res_pf rows
-      // earlier; a row's TMEM traffic is issued back to back (all tcgen05.ld, one wait, all tcgen05.st of the bias
-      // row, one wait) and the block is handed back before the arithmetic and the global stores: serialised
-      // ld / wait / st / ld / wait / st cost the epilogue a third of its samples (profiles/r02_*)
-      uint4 rpre[NJ];
+      // residual rows are software-pipelined one row of this group ahead (registers): with the load issued right
+      // before the accumulator wait the epilogue stalled on it for 16 % of its samples and the MMA warp waited for
+      // TMEM blocks a third of the time (ncu, layer2 conv2)
+      uint4 rpre[NJ], rnext[NJ];
       auto res_row = [&](int r) { return (((size_t)b * p.H + (h0 + r)) * p.W + (valid ? w : 0)) * (size_t)C; };
+      auto load_res = [&](int r, uint4 (&dst)[NJ]) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + res_row(r));
+#pragma unroll
+        for (int j4 = 0; j4 < NJ; ++j4) dst[j4] = valid ? __ldg(rp + j4) : make_uint4(0, 0, 0, 0);
+      };
       const int r_first = (int)((grp - (grow & 1u)) & 1u);   // first row of this item handled by this warpgroup
+      if (p.residual && r_first < R) load_res(r_first, rpre);
       for (int r = r_first; r < R; r += 2) {
         const uint32_t g = grow + (uint32_t)r;
         const uint32_t blk = Ring::idx(g);
         const size_t pix = res_row(r);
         if (p.residual) {
+          // rows further ahead: pull them into L2 (one 64/128-byte pixel per thread)
           if (p.res_pf && valid && r + p.res_pf < R) {
             const __half* nxt = p.residual + pix + (size_t)p.res_pf * p.W * C;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
             if (C == 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 32));
           }
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix);
-#pragma unroll
-          for (int j4 = 0; j4 < NJ; ++j4) rpre[j4] = valid ? __ldg(rp + j4) : make_uint4(0, 0, 0, 0);
+          if (r + 2 < R) load_res(r + 2, rnext);
         }
         mbar_wait(bar_tfull + 8 * blk, Ring::phase(g));
         tc_fence_after();
@@ -948,54 +948,57 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t taddr = tmem_base + lanes + Ring::pos(blk) * (uint32_t)C;
         const bool has_ghost = GHOST && blk >= NBL - 2u;   // warp-uniform
         const uint32_t gaddr = tmem_base + lanes + Ring::ghost_pos(blk) * (uint32_t)C;
-        uint32_t acc[C];
+        uint4* op = reinterpret_cast<uint4*>(p.out + pix);
+        const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
-        for (int hb = 0; hb < C / 32; ++hb) tc_ld32_issue(taddr + hb * 32, acc + hb * 32);
-        tc_wait_ld();
-#pragma unroll
-        for (int hb = 0; hb < C / 32; ++hb) st_bias(taddr + hb * 32, hb);   // hand the block back holding the bias
-        if (has_ghost) {
-#pragma unroll
-          for (int hb = 0; hb < C / 32; ++hb) {
+        for (int hb = 0; hb < C / 32; ++hb) {              // 32 columns at a time (register budget)
+          uint32_t acc[32];
+          tc_ld32(taddr + hb * 32, acc);
+          st_bias(taddr + hb * 32, hb);                    // hand the block back holding the bias
+          if (has_ghost) {
             uint32_t gacc[32];
             tc_ld32(gaddr + hb * 32, gacc);
             tc_st32_zero(gaddr + hb * 32);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              acc[hb * 32 + j] = __float_as_uint(__uint_as_float(acc[hb * 32 + j]) + __uint_as_float(gacc[j]));
+            for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(gacc[j]));
           }
-        }
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * blk);
-        if (valid) {
-          uint4* op = reinterpret_cast<uint4*>(p.out + pix);
-          const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+          if (hb == C / 32 - 1) {
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * blk);
+          }
+          if (valid) {
 #pragma unroll
-          for (int j4 = 0; j4 < NJ; ++j4) {
-            float v[8] = {__uint_as_float(acc[j4 * 8 + 0]), __uint_as_float(acc[j4 * 8 + 1]),
-                          __uint_as_float(acc[j4 * 8 + 2]), __uint_as_float(acc[j4 * 8 + 3]),
-                          __uint_as_float(acc[j4 * 8 + 4]), __uint_as_float(acc[j4 * 8 + 5]),
-                          __uint_as_float(acc[j4 * 8 + 6]), __uint_as_float(acc[j4 * 8 + 7])};
-            if (p.residual) {
-              const __half2* h2 = reinterpret_cast<const __half2*>(&rpre[j4]);
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j4 = hb * 4 + jj;
+              float v[8] = {__uint_as_float(acc[jj * 8 + 0]), __uint_as_float(acc[jj * 8 + 1]),
+                            __uint_as_float(acc[jj * 8 + 2]), __uint_as_float(acc[jj * 8 + 3]),
+                            __uint_as_float(acc[jj * 8 + 4]), __uint_as_float(acc[jj * 8 + 5]),
+                            __uint_as_float(acc[jj * 8 + 6]), __uint_as_float(acc[jj * 8 + 7])};
+              if (p.residual) {
+                const __half2* h2 = reinterpret_cast<const __half2*>(&rpre[j4]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __half22float2(h2[e]);
+                  v[2 * e] += f.x;
+                  v[2 * e + 1] += f.y;
+                }
+              }
+              uint4 u;
+              __half2* o2 = reinterpret_cast<__half2*>(&u);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(h2[e]);
-                v[2 * e] += f.x;
-                v[2 * e + 1] += f.y;
+                const __half2 hv = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                o2[e] = p.relu ? __hmax2(hv, zero2) : hv;   // relu after rounding == rounding after relu
               }
+              op[j4] = u;
             }
-            uint4 u;
-            __half2* o2 = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const __half2 hv = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-              o2[e] = p.relu ? __hmax2(hv, zero2) : hv;   // relu after rounding == rounding after relu
-            }
-            op[j4] = u;
           }
+        }
+        if (p.residual && r + 2 < R) {
+#pragma unroll
+          for (int j4 = 0; j4 < NJ; ++j4) rpre[j4] = rnext[j4];
         }
       }
       grow += (uint32_t)R;
@@ -1519,7 +1522,7 @@ static int conv4_forward(const ConvLayer& L, const __half* in, const __half* res
              "conv v4: folded weights missing");
   ConvV4Params p{};
   p.B = B; p.H = H; p.W = W; p.C = C; p.relu = relu; p.bias = L.bias; p.residual = residual; p.out = out;
-  { const char* e = getenv("B200_RES_PF"); p.res_pf = e ? atoi(e) : 8; }
+  { const char* e = getenv("B200_RES_PF"); p.res_pf = e ? atoi(e) : 4; }
   p.swizzle = (C == 64) ? 128 : 64;
   p.tiles_w = ceil_div(W, kTileM);
   const int strips = B * p.tiles_w;

@@ -30,6 +30,11 @@ struct GemmTcParams {
   int ldc, ldc_h;
   uint32_t a_bytes, b_bytes, stage_bytes, nstages, idesc;
   int gx_T;            // > 0: "gx mode" (see gemm_tc_split_gx): M tiles are (t, 128 consecutive sequences)
+  // fused all-gather: the epilogue also stores every fp32 output tile to the same offsets of up to 7 PEER buffers
+  // (other GPUs' memory mapped over NVLink: P2P stores, 128 contiguous bytes per thread), so the exchange of the
+  // result overlaps the GEMM tile by tile and no separate collective runs
+  float* C_peer[7];
+  int n_peer;
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -161,6 +166,11 @@ gemm_tc_split_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_cons
             float4* op = reinterpret_cast<float4*>(p.C + (size_t)m * p.ldc + col);
 #pragma unroll
             for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int pr = 0; pr < p.n_peer; ++pr) {        // push the same 128 bytes to every peer GPU
+              float4* pp = reinterpret_cast<float4*>(p.C_peer[pr] + (size_t)m * p.ldc + col);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) pp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
           }
           if (p.C_hi) {
             uint4* oh = reinterpret_cast<uint4*>(p.C_hi + (size_t)m * p.ldc_h + col);
@@ -276,12 +286,16 @@ static int launch_gemm(GemmTcParams& p, const CUtensorMap& tmAh, const CUtensorM
 
 int gemm_tc_split(const __half* A_hi, const __half* A_lo, int lda, const __half* B_hi, const __half* B_lo, int ldb,
                   float* C, int ldc, __half* C_hi, __half* C_lo, int ldc_h, const float* bias, int M, int N, int K,
-                  int act, int num_sms, cudaStream_t stream) {
+                  int act, int num_sms, cudaStream_t stream, float* const* C_peers, int n_peers) {
   B200_CHECK(K % kGemmK == 0 && N % 128 == 0 && N <= 1024 && lda % 8 == 0 && ldb % 8 == 0, B200_ERR_INVALID,
              "gemm_tc_split: unsupported shape M=%d N=%d K=%d", M, N, K);
   GemmTcParams p{};
   p.M = M; p.N = N; p.K = K; p.act = act; p.bias = bias; p.C = C; p.C_hi = C_hi; p.C_lo = C_lo; p.ldc = ldc;
   p.ldc_h = ldc_h;
+  B200_CHECK(n_peers >= 0 && n_peers <= 7 && (n_peers == 0 || (C_peers && C)), B200_ERR_INVALID,
+             "gemm_tc_split: at most 7 peer outputs");
+  p.n_peer = n_peers;
+  for (int i = 0; i < n_peers; ++i) p.C_peer[i] = C_peers[i];
   p.tiles_m = ceil_div(M, kGemmM);
   CUtensorMap tmAh, tmAl;
   int rc;

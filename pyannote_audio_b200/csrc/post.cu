@@ -116,6 +116,38 @@ int powerset_speech(const unsigned char* cls, long long n, float* out, cudaStrea
   return B200_OK;
 }
 
+// push a byte range to the same offsets of up to 7 peer buffers (P2P stores over NVLink, 16 bytes per thread): the
+// powerset classes of a rank's chunks next to the embeddings that gemm_tc_split_kernel pushes from its epilogue
+struct PushDsts { unsigned char* d[7]; };
+__global__ void push_bytes_kernel(const uint4* __restrict__ src, PushDsts dsts, int n, long long n16,
+                                  const unsigned char* __restrict__ src_tail, long long tail0, long long bytes) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n16) {
+    const uint4 v = src[i];
+    for (int p = 0; p < n; ++p) reinterpret_cast<uint4*>(dsts.d[p])[i] = v;
+  } else if (i - n16 < bytes - tail0) {
+    const long long o = tail0 + (i - n16);
+    for (int p = 0; p < n; ++p) dsts.d[p][o] = src_tail[o];
+  }
+}
+
+int push_bytes(const void* src, long long bytes, void* const* dsts, int n, cudaStream_t stream) {
+  if (bytes <= 0 || n <= 0) return B200_OK;
+  B200_CHECK(n <= 7, B200_ERR_INVALID, "push: at most 7 peers");
+  B200_CHECK((reinterpret_cast<uintptr_t>(src) & 15) == 0, B200_ERR_INVALID, "push: source must be 16-byte aligned");
+  PushDsts d{};
+  for (int i = 0; i < n; ++i) {
+    B200_CHECK((reinterpret_cast<uintptr_t>(dsts[i]) & 15) == 0, B200_ERR_INVALID, "push: destinations must be 16-byte aligned");
+    d.d[i] = reinterpret_cast<unsigned char*>(dsts[i]);
+  }
+  const long long n16 = bytes / 16, tail0 = n16 * 16, total = n16 + (bytes - tail0);
+  push_bytes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(src), d, n, n16,
+                                                                          reinterpret_cast<const unsigned char*>(src),
+                                                                          tail0, bytes);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
 constexpr int kMaxK = 32;
 
 // KMAX is a compile-time bound so that the per-frame activation counters stay in registers (static indexing).

@@ -9,5 +9,6 @@ int frame_transitions(const unsigned char* discrete, int F, int K, int cap, int*
 int aggregate_scores(const float* scores, const int* sf, int C, int F, int K, const double* hamming, const double* warm,
                      int skip_average, float missing, float epsilon, float* out, cudaStream_t stream);
 int powerset_speech(const unsigned char* cls, long long n, float* out, cudaStream_t stream);
+int push_bytes(const void* src, long long bytes, void* const* dsts, int n, cudaStream_t stream);
 int clean_frames(const unsigned char* seg, int C, int* clean, unsigned char* active, cudaStream_t stream);
 }

@@ -41,7 +41,7 @@ int sgemm_nt(const float* A, int lda, const float* Bw, int ldb, float* C, int ld
 // split-precision tensor-core GEMM (gemm_tc.cu): C = act(A B^T + bias), A/B as fp16 (hi, lo) pairs
 int gemm_tc_split(const __half* A_hi, const __half* A_lo, int lda, const __half* B_hi, const __half* B_lo, int ldb,
                   float* C, int ldc, __half* C_hi, __half* C_lo, int ldc_h, const float* bias, int M, int N, int K,
-                  int act, int num_sms, cudaStream_t stream);
+                  int act, int num_sms, cudaStream_t stream, float* const* C_peers = nullptr, int n_peers = 0);
 int split_f16(const float* x, __half* hi, __half* lo, size_t n, cudaStream_t st);
 int gemm_tc_split_gx(const __half* A_hi, const __half* A_lo, int lda, const __half* B_hi, const __half* B_lo, int ldb,
                      float* G, const float* bias, int NB, int T, int N, int K, int num_sms, cudaStream_t stream);

@@ -369,9 +369,10 @@ class WeSpeakerResNet34(Model):
             n = _conv1d_num_frames(n, 3, s, p=1)
         return n
 
-    def forward_chunks(self, wav: torch.Tensor, chunk_off, chunk_valid, masks: torch.Tensor, out=None) -> torch.Tensor:
+    def forward_chunks(self, wav: torch.Tensor, chunk_off, chunk_valid, masks: torch.Tensor, out=None,
+                       peers=None) -> torch.Tensor:
         """Hot-path entry: (num_chunks, 3, 589) uint8 masks -> (num_chunks, 3, 256) embeddings, one trunk pass."""
-        return self._ctx().emb_forward(wav, chunk_off, chunk_valid, masks, out=out)
+        return self._ctx().emb_forward(wav, chunk_off, chunk_valid, masks, out=out, peers=peers)
 
     def _flat(self, waveforms):
         b, c, s = waveforms.shape

@@ -226,16 +226,34 @@ class Context:
         return out
 
     # ---- embeddings ------------------------------------------------------------------------------
-    def emb_forward(self, wav, chunk_off, chunk_valid, masks: torch.Tensor, out: Optional[torch.Tensor] = None):
+    def emb_forward(self, wav, chunk_off, chunk_valid, masks: torch.Tensor, out: Optional[torch.Tensor] = None,
+                    peers: Optional[Sequence[int]] = None):
+        """``peers``: raw device addresses of this rank's (n,3,256) float32 slot inside other GPUs' gather buffers
+        (peer-mapped memory); the final GEMM's epilogue then pushes the embeddings there (fused all-gather)."""
         off, valid = self._chunks(wav, chunk_off, chunk_valid)
         n = len(off)
         if tuple(masks.shape) != (n, SPEAKERS, FRAMES) or masks.dtype != torch.uint8 or not masks.is_contiguous():
             raise ValueError(f"masks must be a contiguous uint8 tensor of shape ({n}, 3, 589)")
         emb = self._out(out, (n, SPEAKERS, EMB_DIM), torch.float32)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.b200_emb_forward(self._h, _ptr(wav), off.ctypes.data, valid.ctypes.data, n, _ptr(masks),
-                                                 _ptr(emb), _stream(self.device)))
+            if peers:
+                arr = (C.c_void_p * len(peers))(*[C.c_void_p(int(a)) for a in peers])
+                _lib.check(self.lib.b200_emb_forward_push(self._h, _ptr(wav), off.ctypes.data, valid.ctypes.data, n,
+                                                          _ptr(masks), _ptr(emb), arr, len(peers),
+                                                          _stream(self.device)))
+            else:
+                _lib.check(self.lib.b200_emb_forward(self._h, _ptr(wav), off.ctypes.data, valid.ctypes.data, n,
+                                                     _ptr(masks), _ptr(emb), _stream(self.device)))
         return emb
+
+    def push(self, src: torch.Tensor, peers: Sequence[int]):
+        """P2P copy of a contiguous device tensor to raw peer addresses (same layout), on the current stream."""
+        if not peers or src.numel() == 0:
+            return
+        arr = (C.c_void_p * len(peers))(*[C.c_void_p(int(a)) for a in peers])
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.b200_push(self._h, _ptr(src), src.numel() * src.element_size(), arr, len(peers),
+                                          _stream(self.device)))
 
     def emb_fbank(self, wav, chunk_off, chunk_valid):
         off, valid = self._chunks(wav, chunk_off, chunk_valid)

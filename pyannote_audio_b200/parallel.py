@@ -68,11 +68,18 @@ class ChunkPool:
     EMB_BYTES = 3 * 256 * 4
     CLS_BYTES = 589
 
-    def __init__(self, pipeline, group=None):
+    def __init__(self, pipeline, group=None, collective: str = "nccl"):
+        """``collective``: "nccl" = one in-place ncclAllGather of the packed buffer; "p2p" = no collective call at
+        all: the pool buffer lives in symmetric memory (every GPU maps every peer's buffer over NVLink), the final
+        Linear GEMM of the embedding network pushes its output tiles to all peers from its epilogue
+        (b200_emb_forward_push), the powerset classes follow with a P2P copy kernel, and a symmetric-memory barrier
+        publishes the stores.  Falls back to "nccl" when symmetric memory cannot be set up."""
         self.pipeline, self.group = pipeline, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.collective = collective if self.world > 1 else "nccl"
         self.last_collective = dict(bytes_sent=0, bytes_received=0, ms=None)
         self._events = None
+        self._symm = None          # (buffer, handle) of the symmetric pool
 
     # ---- planning: per-file chunk counts of every rank (tiny object all-gather, once per batch of files) ----------
     def plan(self, layouts, uris):
@@ -115,16 +122,32 @@ class ChunkPool:
         ctx = get_context(pipe.device)
         num_speakers, min_speakers, max_speakers = set_num_speakers(num_speakers, min_speakers, max_speakers)
         pipe.d2h_bytes = 0
-        buf = resident.get("pool")
-        if buf is None or buf.numel() != self.world * plan["blk"]:
-            buf = resident["pool"] = torch.zeros(self.world * plan["blk"], dtype=torch.uint8, device=ctx.device)
+        buf, hdl = self._pool_buffer(resident, plan, ctx)
         emb_mine, cls_mine = self.views(buf, plan, self.rank)
         # ---- this rank's share of the pool: outputs land in its slice of the collective's buffer ----------------
         pipe._segmentation.model.forward_chunks(resident["wav"], resident["off"], resident["valid"], out=cls_mine)
         seg_mine = ctx.powerset_to_multilabel(cls_mine)
-        pipe.embedding.forward_chunks(resident["wav"], resident["off"], resident["valid"], pipe._masks(seg_mine),
-                                      out=emb_mine)
-        self.exchange(buf, plan)
+        if hdl is None:
+            pipe.embedding.forward_chunks(resident["wav"], resident["off"], resident["valid"], pipe._masks(seg_mine),
+                                          out=emb_mine)
+            self.exchange(buf, plan)
+        else:
+            # fused: the embedding GEMM's epilogue stores every tile into all peers' copies of this rank's slot
+            peers = [r for r in range(self.world) if r != self.rank]
+            emb_off = emb_mine.data_ptr() - buf.data_ptr()
+            cls_off = cls_mine.data_ptr() - buf.data_ptr()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            pipe.embedding.forward_chunks(resident["wav"], resident["off"], resident["valid"], pipe._masks(seg_mine),
+                                          out=emb_mine, peers=[int(hdl.buffer_ptrs[r]) + emb_off for r in peers])
+            e0.record()
+            ctx.push(cls_mine, [int(hdl.buffer_ptrs[r]) + cls_off for r in peers])
+            hdl.barrier(channel=0)                         # all ranks' pushes have landed and are visible
+            e1.record()
+            self._events = (e0, e1)
+            self.last_collective = dict(bytes_sent=int(plan["counts"][self.rank] * (self.EMB_BYTES + self.CLS_BYTES)
+                                                       * (self.world - 1)),
+                                        bytes_received=int(sum(plan["counts"][r] for r in peers)
+                                                           * (self.EMB_BYTES + self.CLS_BYTES)))
         got = self.owned_inputs(buf, plan)
         if got is None:
             return
@@ -140,6 +163,33 @@ class ChunkPool:
                                   return_artifacts, classes=cls)
         for meta, out in zip(metas, outs):
             yield meta, out
+
+    def _pool_buffer(self, resident, plan, ctx):
+        """The packed pool buffer: a plain device tensor (nccl) or a symmetric-memory allocation + handle (p2p)."""
+        nbytes = self.world * plan["blk"]
+        if self.collective == "p2p":
+            if self._symm is None or self._symm[0].numel() != nbytes:
+                try:
+                    import torch.distributed._symmetric_memory as symm_mem
+
+                    grp = self.group if self.group is not None else dist.group.WORLD
+                    t = symm_mem.empty(nbytes, dtype=torch.uint8, device=ctx.device)
+                    hdl = symm_mem.rendezvous(t, group=grp)
+                    t.zero_()
+                    torch.cuda.synchronize(ctx.device)
+                    dist.barrier(group=self.group)
+                    self._symm = (t, hdl)
+                except Exception as exc:           # symmetric memory unavailable: same data path through NCCL
+                    import warnings
+
+                    warnings.warn(f"symmetric memory unavailable ({exc}); ChunkPool falls back to ncclAllGather")
+                    self.collective = "nccl"
+            if self.collective == "p2p":
+                return self._symm
+        buf = resident.get("pool")
+        if buf is None or buf.numel() != nbytes:
+            buf = resident["pool"] = torch.zeros(nbytes, dtype=torch.uint8, device=ctx.device)
+        return buf, None
 
     def exchange(self, buf, plan):
         """The one exchange step of the path: in-place all-gather of the packed per-rank blocks."""
