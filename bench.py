@@ -115,7 +115,9 @@ def workload_config(args, world):
     """The `config` object of the JSON line: identical for the GPU arm and the CPU reference arm."""
     step_chunks = int(round(args.minutes * 60.0)) - 10 + 1
     par = "single GPU" if world == 1 else (
-        f"global chunk pool x{world} + one NCCL all-gather, per-file stage on rank g mod {world}"
+        f"global chunk pool x{world}, embeddings + classes exchanged once ({args.collective}: "
+        + ("pushed to the peers from the embedding GEMM's epilogue over NVLink" if args.collective == "p2p"
+           else "one ncclAllGather") + f"), per-file stage on rank g mod {world}"
         if pool_mode(args, world) else f"file-sharded x{world}, no data-path collective")
     return {"workload": f"community-1 diarization pipeline end-to-end, {args.files_per_gpu} x {args.minutes:g} min "
                         f"synthetic 16 kHz mono files per GPU (BASELINE.json configs[4] scaled per GPU)",

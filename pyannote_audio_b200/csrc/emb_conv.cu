@@ -473,6 +473,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 struct ConvV3Params {
   int B, H, W, C_in, C_out;                // H, W: OUTPUT size (the input size only lives in the tensor map)
   int stride, pad, ksize;                  // 3x3 pad 1 (stride 1 or 2) or 1x1 pad 0 (stride 2: the block shortcuts)
+  int dbg;                                 // timing experiments only (B200_TC3_DBG): 1 = weight loads only for the
+                                           //    first stages, 2 = pixel loads only for the first stages (wrong results)
   int fold;                                // 1: a stage holds one (kh, channel block): 3 weight taps + ONE pixel box with
                                            //    a one-pixel halo, the kw taps are descriptor shifts (stride-1 3x3 only)
   int pitch;                               // accumulator columns per image row of the tile: bw (+ 2 halo columns if fold)
@@ -545,9 +547,17 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       for (int kb = 0; kb < p.kblocks; ++kb) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
         if (leader) {
-          mbar_expect_tx(bar_full + 8 * stage, p.b_bytes);   // bytes delivered by the two boxes
+          if (!(p.fold && p.dbg)) mbar_expect_tx(bar_full + 8 * stage, p.b_bytes);   // bytes delivered by the two boxes
           const uint32_t sa = stage0 + stage * p.stage_bytes;
-          if (p.fold) {
+          if (p.fold && p.dbg) {
+            // experiment: after the first pass over the stages one of the two streams is no longer loaded
+            const bool warm = item != (int)blockIdx.x || kb >= (int)p.nstages;
+            const bool do_w = !(warm && p.dbg == 1), do_x = !(warm && p.dbg == 2);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_full + 8 * stage),
+                         "r"((do_w ? p.a_bytes : 0u) + (do_x ? p.b_bytes - p.a_bytes : 0u)) : "memory");
+            if (do_w) tma_load_3d(&tmW, bar_full + 8 * stage, sa, cc * p.Ck, mt * 128, kh * 3);
+            if (do_x) tma_load_4d(&tmX, bar_full + 8 * stage, sa + p.a_bytes, cc * p.Ck, w0 - 1, h0 + kh - 1, b);
+          } else if (p.fold) {
             // the three horizontal taps of row kh share one pixel box (one-pixel halo left and right, zero filled)
             tma_load_3d(&tmW, bar_full + 8 * stage, sa, cc * p.Ck, mt * 128, kh * 3);
             tma_load_4d(&tmX, bar_full + 8 * stage, sa + p.a_bytes, cc * p.Ck, w0 - 1, h0 + kh - 1, b);
@@ -734,7 +744,7 @@ struct ConvV4Params {
   uint32_t a_bytes, a_slot_bytes, wkw_bytes, swizzle, w_off, a_off;
 };
 
-constexpr int kV4Threads = 320;   // TMA warp, MMA warp, 2 x 4 epilogue warps (alternate rows)
+// threads = TMA warp + MMA warp + G epilogue warpgroups of 4 warps; warpgroup k drains the rows r = k (mod G)
 
 // Ring geometry.  The 512 TMEM columns hold P = 512 / C blocks of C columns.  GHOST = false: all P blocks form the
 // ring and a run of rows that crosses the ring seam is issued as two narrower MMAs (25 % more MMAs for C = 64, and
@@ -751,8 +761,8 @@ struct TmemRing {
   __device__ static __forceinline__ uint32_t ghost_pos(uint32_t i) { return 2u * NBL - 1u - i; }   // i >= NBL - 2
 };
 
-template <int C, bool GHOST>
-__global__ void __launch_bounds__(kV4Threads, 1)
+template <int C, bool GHOST, int G>
+__global__ void __launch_bounds__(64 + 128 * G, 1)
 conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvV4Params p) {
   using Ring = TmemRing<512 / C, GHOST>;
   constexpr uint32_t NBL = Ring::NBL;
@@ -801,7 +811,7 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp >= 2) {
     const uint32_t grp = (uint32_t)(warp - 2) >> 2;
     const uint32_t lanes0 = (uint32_t)((warp & 3) * 32) << 16;
-    for (uint32_t pos = grp; pos < 512u / C; pos += 2) {
+    for (uint32_t pos = grp; pos < 512u / C; pos += G) {
 #pragma unroll
       for (int hb = 0; hb < C / 32; ++hb) {
         const uint32_t ta = tmem_base + lanes0 + pos * (uint32_t)C + hb * 32;
@@ -906,7 +916,8 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       grow += (uint32_t)R;
     }
   } else {
-    // two epilogue warpgroups (warps 2-5 and 6-9) take alternate rows so that a scheduler always has a second warp
+    // G epilogue warpgroups take the rows round robin: the epilogue is a chain of TMEM / memory round trips, more
+    // warps in flight hide them
     const int q = warp & 3;
     const uint32_t grp = (uint32_t)(warp - 2) >> 2;
     constexpr int NJ = C / 8;                              // 16-byte pieces per pixel
@@ -927,9 +938,10 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
         for (int j4 = 0; j4 < NJ; ++j4) dst[j4] = valid ? __ldg(rp + j4) : make_uint4(0, 0, 0, 0);
       };
-      const int r_first = (int)((grp - (grow & 1u)) & 1u);   // first row of this item handled by this warpgroup
-      if (p.residual && r_first < R) load_res(r_first, rpre);
-      for (int r = r_first; r < R; r += 2) {
+      const int r_first = (int)((grp + G - (grow % G)) % G); // first row of this item handled by this warpgroup
+      constexpr bool kPipe = (G == 2);                       // register-prefetch the next row only when registers allow
+      if (kPipe && p.residual && r_first < R) load_res(r_first, rpre);
+      for (int r = r_first; r < R; r += G) {
         const uint32_t g = grow + (uint32_t)r;
         const uint32_t blk = Ring::idx(g);
         const size_t pix = res_row(r);
@@ -940,7 +952,8 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
             if (C == 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 32));
           }
-          if (r + 2 < R) load_res(r + 2, rnext);
+          if (kPipe) { if (r + G < R) load_res(r + G, rnext); }
+          else load_res(r, rpre);
         }
         mbar_wait(bar_tfull + 8 * blk, Ring::phase(g));
         tc_fence_after();
@@ -996,7 +1009,7 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
         }
-        if (p.residual && r + 2 < R) {
+        if (kPipe && p.residual && r + G < R) {
 #pragma unroll
           for (int j4 = 0; j4 < NJ; ++j4) rpre[j4] = rnext[j4];
         }
@@ -1566,14 +1579,23 @@ static int conv4_forward(const ConvLayer& L, const __half* in, const __half* res
   }
   const size_t smem = 1024 + p.a_off + (size_t)p.n_aslots * p.a_slot_bytes;
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
-  auto launch = [&](auto kernel) -> int {
+  int groups = (C == 64) ? 3 : 2;                          // epilogue warpgroups (A/B knob: B200_TC4_G = 2 | 3 | 4)
+  if (const char* e = getenv("B200_TC4_G")) { const int v = atoi(e); if (v >= 2 && v <= 4) groups = v; }
+  auto launch = [&](auto kernel, int g) -> int {
     B200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    kernel<<<grid, kV4Threads, smem, stream>>>(tmA, tmB, p);
+    kernel<<<grid, 64 + 128 * g, smem, stream>>>(tmA, tmB, p);
     B200_CUDA_OK(cudaGetLastError());
     return B200_OK;
   };
-  if (C == 32) return ghost ? launch(conv_tc4_kernel<32, true>) : launch(conv_tc4_kernel<32, false>);
-  return ghost ? launch(conv_tc4_kernel<64, true>) : launch(conv_tc4_kernel<64, false>);
+  if (ghost) return C == 32 ? launch(conv_tc4_kernel<32, true, 2>, 2) : launch(conv_tc4_kernel<64, true, 2>, 2);
+  if (C == 32) {
+    if (groups == 2) return launch(conv_tc4_kernel<32, false, 2>, 2);
+    if (groups == 3) return launch(conv_tc4_kernel<32, false, 3>, 3);
+    return launch(conv_tc4_kernel<32, false, 4>, 4);
+  }
+  if (groups == 2) return launch(conv_tc4_kernel<64, false, 2>, 2);
+  if (groups == 3) return launch(conv_tc4_kernel<64, false, 3>, 3);
+  return launch(conv_tc4_kernel<64, false, 4>, 4);
 }
 
 // fused BasicBlock (conv_block32_kernel): in -> out, out must not alias in (tiles read their neighbours' halo)
@@ -1650,6 +1672,7 @@ static int conv3_forward(const ConvLayer& L, const __half* in, const __half* res
   // One stage = (kh, 32 input channels): the 3 weight taps of that row + ONE pixel box with a one-pixel halo; the kw
   // taps are descriptor shifts of one pixel row.  Pixel traffic 9x -> 3x, 6 MMAs per stage.
   p.fold = (L.ksize == 3 && L.stride == 1 && fold) ? 1 : 0;
+  if (const char* e = getenv("B200_TC3_DBG")) p.dbg = atoi(e);
   int fold_ck = 32;                                        // 4 stages of 41 KB; 64 -> 2 stages of 82 KB (A/B knob)
   if (const char* e = getenv("B200_TC3_CK")) fold_ck = atoi(e) == 64 ? 64 : 32;
   p.Ck = p.fold ? fold_ck : ((L.C_in >= 64) ? 64 : 32);
