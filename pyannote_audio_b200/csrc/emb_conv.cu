@@ -488,7 +488,7 @@ struct ConvV3Params {
 };
 
 constexpr int kV3Threads = 320;          // TMA warp, MMA warp, 2 x 4 epilogue warps (alternate 32-pixel chunks)
-constexpr uint32_t kV3Staging = 32768;   // 8 epilogue warps x (2 KB out + 2 KB residual) transpose buffers
+constexpr uint32_t kV3Staging = 16384;   // 8 epilogue warps x 2 KB transpose buffer (residual in, then result out)
 
 __global__ void __launch_bounds__(kV3Threads, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvV3Params p) {
@@ -497,7 +497,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
   // [0,64) full  [64,128) empty  [128,144) tfull  [144,160) tempty  [192] tmem slot  [1024,2048) bias
-  // [2048, 2048+32K) epilogue transpose staging (8 warps x (2 KB out + 2 KB residual))  then the stages
+  // [2048, 2048+16K) epilogue transpose staging (8 warps x 2 KB)  then the stages
   const uint32_t bar_full = base, bar_empty = base + 64, bar_tfull = base + 128, bar_tempty = base + 144;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + 192);
   float* s_bias = reinterpret_cast<float*>(gbase + 1024);
@@ -625,8 +625,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     // with four warps the transposing epilogue of a residual conv took as long as the tile's MMAs
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    __half* s_out = reinterpret_cast<__half*>(s_stage_ep + (half * 4 + q) * 4096);          // [32 px][32 ch]
-    __half* s_res = reinterpret_cast<__half*>(s_stage_ep + (half * 4 + q) * 4096 + 2048);   // [32 px][32 ch]
+    // one [32 px][32 ch] fp16 buffer per warp: the residual chunk passes through it first (coalesced 16-byte loads
+    // in, own-channel reads out), then the result goes the other way; halving the staging bought a fifth stage
+    __half* s_out = reinterpret_cast<__half*>(s_stage_ep + (half * 4 + q) * 2048);
     const int prow = lane >> 2, ppart = lane & 3;          // cooperative 16-byte I/O: 8 pixels x 4 parts per pass
     uint32_t acc = 0, acc_phase = 0;
     const int npix = p.pitch * p.bh;                       // accumulator columns in use (halo columns are skipped)
@@ -678,11 +679,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (more) pixels(n0 + 64, gpn);
         if (p.residual) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(s_res + (i * 8 + prow) * 32 + ppart * 8) = rpre[i];
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(s_out + (i * 8 + prow) * 32 + ppart * 8) = rpre[i];
           __syncwarp();
           if (more) load_res(gpn);                         // prefetch the next chunk's residual
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __half2float(s_res[j * 32 + lane]);
+          for (int j = 0; j < 32; ++j) v[j] += __half2float(s_out[j * 32 + lane]);
+          __syncwarp();                                    // everyone has read before the buffer is overwritten
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -1707,7 +1709,7 @@ static int conv3_forward(const ConvLayer& L, const __half* in, const __half* res
   const uint32_t slot = p.a_bytes + b_full;
   p.stage_bytes = slot;                                     // the kernel addresses stage s at stage0 + s * stage_bytes
   p.b_bytes = delivered;                                    // bytes to expect per stage
-  p.nstages = (200u * 1024 - kV3Staging) / slot;
+  p.nstages = (227u * 1024 - 1024 - 3072 - kV3Staging) / slot;   // 5 stages of 41 KB when folding
   if (p.nstages > 8) p.nstages = 8;
   p.idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   PFN_encodeTiled enc = get_encode();
