@@ -446,7 +446,7 @@ int b200_seg_load(b200_ctx* ctx, const b200_seg_weights* w) {
     if ((rc = upload(ctx, wih, &S.w_ih[l]))) return rc;
     if ((rc = upload(ctx, bg, &S.b_g[l]))) return rc;
     if ((rc = upload(ctx, whh, &S.w_hh[l]))) return rc;
-    {   // tensor-core recurrence: rows (dir, rank, unit_local, gate), k contiguous, as fp16 (hi, lo)
+    {   // tensor-core recurrence: rows (dir, rank, unit_local, gate), k contiguous (permuted, below), as fp16 (hi, lo)
       std::vector<__half> hi((size_t)1024 * 128), lo((size_t)1024 * 128);
       for (int d = 0; d < 2; ++d) {
         const float* Wh = w->lstm_w_hh[l * 2 + d];
@@ -455,7 +455,10 @@ int b200_seg_load(b200_ctx* ctx, const b200_seg_weights* w) {
             for (int gt = 0; gt < 4; ++gt)
               for (int k = 0; k < 128; ++k) {
                 const float v = Wh[(size_t)(gt * 128 + 64 * r + ul) * 128 + k];
-                const size_t o = ((size_t)((d * 2 + r) * 256 + ul * 4 + gt)) * 128 + k;
+                // K order inside a k-block of 64 units: (chunk, half, unit-in-chunk) for unit = half*32 + chunk*8 + u,
+                // so that the units the epilogue warps finish together form one 16-wide k-step (seg_lstm_tc.cu)
+                const int kl = k & 63, kp = (k & 64) | (((kl & 31) >> 3) << 4) | ((kl >> 5) << 3) | (kl & 7);
+                const size_t o = ((size_t)((d * 2 + r) * 256 + ul * 4 + gt)) * 128 + kp;
                 hi[o] = __float2half(v);
                 lo[o] = __float2half(v - __half2float(hi[o]));
               }

@@ -478,6 +478,7 @@ struct ConvV3Params {
   int fold;                                // 1: a stage holds one (kh, channel block): 3 weight taps + ONE pixel box with
                                            //    a one-pixel halo, the kw taps are descriptor shifts (stride-1 3x3 only)
   int pitch;                               // accumulator columns per image row of the tile: bw (+ 2 halo columns if fold)
+  int mc;                                  // fold only: CTAs per cluster that share the weight stream (TMA multicast), 1 = off
   int Ck, ncc, kblocks, bw, bh, tiles_w, tiles_h, m_tiles, num_items, relu;
   const float* bias;
   const __half* residual;
@@ -491,7 +492,8 @@ constexpr int kV3Threads = 320;          // TMA warp, MMA warp, 2 x 4 epilogue w
 constexpr uint32_t kV3Staging = 16384;   // 8 epilogue warps x 2 KB transpose buffer (residual in, then result out)
 
 __global__ void __launch_bounds__(kV3Threads, 1)
-conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ConvV3Params p) {
+conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                const __grid_constant__ CUtensorMap tmWs, ConvV3Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -505,9 +507,19 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const uint32_t stage0 = base + 2048 + kV3Staging;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  // Weight multicast (p.mc > 1, folded stride-1 convs): the mc CTAs of a cluster work on mc different pixel tiles of
+  // the same output-channel tile in lockstep; each loads 1/mc of every weight stage and multicasts it to all, so the
+  // L2 -> SM weight traffic (59 % of the kernel's bytes, which ran at the L2 throughput cap) drops by (mc - 1) / mc.
+  // A stage is refilled only when the MMAs of ALL CTAs have released it (multicast tcgen05.commit, count mc).
+  uint32_t crank = 0;
+  if (p.mc > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const uint32_t mc = (uint32_t)p.mc;
+  const uint16_t cmask = (uint16_t)((1u << mc) - 1u);
+  const int cluster_id = (int)(blockIdx.x / mc), num_clusters = (int)(gridDim.x / mc);
+
   for (int i = threadIdx.x; i < p.C_out && i < 256; i += blockDim.x) s_bias[i] = p.bias[i];
   if (threadIdx.x == 0) {
-    for (uint32_t s = 0; s < p.nstages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (uint32_t s = 0; s < p.nstages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, mc); }
     for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -518,14 +530,17 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (mc > 1)                                              // peers' barriers exist before anything is multicast to them
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int ksteps = p.Ck / 16;
 
-  // item -> (b, th, tw, mt); mt fastest
+  // item -> (b, th, tw, mt); mt fastest; the CTAs of a cluster take consecutive pixel tiles of the same mt (tiles past
+  // the end are ghosts: zero-filled loads, no stores)
   auto decode = [&](int item, int& b, int& h0, int& w0, int& mt) {
     mt = item % p.m_tiles;
-    int t = item / p.m_tiles;
+    int t = (item / p.m_tiles) * (int)mc + (int)crank;
     const int tw = t % p.tiles_w; t /= p.tiles_w;
     const int th = t % p.tiles_h;
     b = t / p.tiles_h;
@@ -540,7 +555,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
     }
     uint32_t stage = 0, phase = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+    for (int item = cluster_id; item < p.num_items; item += num_clusters) {
       int b, h0, w0, mt;
       decode(item, b, h0, w0, mt);
       int tap = 0, cc = 0, kh = 0, kw = 0;
@@ -559,7 +574,16 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             if (do_x) tma_load_4d(&tmX, bar_full + 8 * stage, sa + p.a_bytes, cc * p.Ck, w0 - 1, h0 + kh - 1, b);
           } else if (p.fold) {
             // the three horizontal taps of row kh share one pixel box (one-pixel halo left and right, zero filled)
-            tma_load_3d(&tmW, bar_full + 8 * stage, sa, cc * p.Ck, mt * 128, kh * 3);
+            if (mc > 1) {
+              const uint32_t rows = 128u / mc, tap_bytes = 128u * (uint32_t)p.Ck * 2u;
+              const uint32_t dst = sa + crank * rows * (uint32_t)p.Ck * 2u;
+#pragma unroll
+              for (int k3 = 0; k3 < 3; ++k3)
+                tma_load_3d_mc(&tmWs, bar_full + 8 * stage, dst + k3 * tap_bytes, cc * p.Ck, mt * 128 + (int)(crank * rows),
+                               kh * 3 + k3, cmask);
+            } else {
+              tma_load_3d(&tmW, bar_full + 8 * stage, sa, cc * p.Ck, mt * 128, kh * 3);
+            }
             tma_load_4d(&tmX, bar_full + 8 * stage, sa + p.a_bytes, cc * p.Ck, w0 - 1, h0 + kh - 1, b);
           } else {
             tma_load_3d(&tmW, bar_full + 8 * stage, sa, cc * p.Ck, mt * 128, tap);
@@ -578,7 +602,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const bool leader = elect_one_sync();
     const uint32_t dhi = desc_hi((p.swizzle == 128) ? 1024u : 512u, (p.swizzle == 128) ? 2u : 4u);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+    for (int item = cluster_id; item < p.num_items; item += num_clusters) {
       mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * 256u;
@@ -610,7 +634,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               tc_mma_f16(d_tmem, desc_from(dhi, alo + 6), desc_from(dhi, blo + 6), p.idesc, 1);
             }
           }
-          tc_commit(bar_empty + 8 * stage);
+          if (mc > 1) tc_commit_mc(bar_empty + 8 * stage, cmask);     // the stage is free in every CTA of the cluster
+          else tc_commit(bar_empty + 8 * stage);
         }
         __syncwarp();
         if (++stage == p.nstages) { stage = 0; phase ^= 1; }
@@ -631,7 +656,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int prow = lane >> 2, ppart = lane & 3;          // cooperative 16-byte I/O: 8 pixels x 4 parts per pass
     uint32_t acc = 0, acc_phase = 0;
     const int npix = p.pitch * p.bh;                       // accumulator columns in use (halo columns are skipped)
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+    for (int item = cluster_id; item < p.num_items; item += num_clusters) {
       int b, h0, w0, mt;
       decode(item, b, h0, w0, mt);
       const int c0 = mt * 128 + q * 32;                    // first channel of this warp
@@ -651,7 +676,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         for (int i = 0; i < 4; ++i) {
           const int n = n0 + i * 8 + prow;
           const int rr = n / p.pitch, x = n - rr * p.pitch;
-          const bool ok = ch_ok && n < npix && x < p.bw && (h0 + rr) < p.H && (w0 + x) < p.W;
+          const bool ok = ch_ok && b < p.B && n < npix && x < p.bw && (h0 + rr) < p.H && (w0 + x) < p.W;
           dst[i] = ok ? (((long long)b * p.H + h0 + rr) * p.W + w0 + x) : -1;
         }
       };
@@ -715,6 +740,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  if (mc > 1)                                              // no CTA exits while a peer may still signal its barriers
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
@@ -744,9 +771,14 @@ struct ConvV4Params {
   const __half* residual;
   __half* out;
   uint32_t a_bytes, a_slot_bytes, wkw_bytes, swizzle, w_off, a_off;
+  uint32_t ones_off, btile_off;      // C = 64: constant A tile (ones) and B tile (bias) of the bias MMA
+  uint32_t r_off;                    // C = 64 with a residual: n_rslots slots of 16 KB (one residual pixel row each)
+  int n_rslots;
+  int wrap;                          // experiment (B200_TC4_WRAP): never split a run at the ring seam
 };
 
-// threads = TMA warp + MMA warp + G epilogue warpgroups of 4 warps; warpgroup k drains the rows r = k (mod G)
+// threads = TMA warp + MMA warp + G epilogue warpgroups of 4 warps (warpgroup k drains the rows r = k (mod G)) + one
+// more TMA warp that streams the residual rows into shared memory (C = 64)
 
 // Ring geometry.  The 512 TMEM columns hold P = 512 / C blocks of C columns.  GHOST = false: all P blocks form the
 // ring and a run of rows that crosses the ring seam is issued as two narrower MMAs (25 % more MMAs for C = 64, and
@@ -764,8 +796,9 @@ struct TmemRing {
 };
 
 template <int C, bool GHOST, int G>
-__global__ void __launch_bounds__(64 + 128 * G, 1)
-conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvV4Params p) {
+__global__ void __launch_bounds__(96 + 128 * G, 1)
+conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmR, ConvV4Params p) {
   using Ring = TmemRing<512 / C, GHOST>;
   constexpr uint32_t NBL = Ring::NBL;
   extern __shared__ uint8_t smem_raw[];
@@ -773,18 +806,39 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
   // header: [0,64) a_full  [64,128) a_empty  [128,256) tfull[16]  [256,384) tempty[16]  [384,392) wbar
-  //         [512,516) tmem slot  [1024,1280) bias
+  //         [392,424) r_full[4]  [424,456) r_empty[4]  [512,516) tmem slot  [1024,1280) bias
   const uint32_t bar_afull = base, bar_aempty = base + 64, bar_tfull = base + 128, bar_tempty = base + 256;
-  const uint32_t bar_w = base + 384;
+  const uint32_t bar_w = base + 384, bar_rfull = base + 392, bar_rempty = base + 424;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + 512);
   float* s_bias = reinterpret_cast<float*>(gbase + 1024);
   const uint32_t w_smem = base + p.w_off, a_smem = base + p.a_off;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // C = 64 (round 2): the bias enters through the tensor core.  The first MMA into a drained accumulator block is
+  //   D[128 px][64 co] = ONES[128][16] * BT[64][16]^T  with accumulate = 0,
+  //   ONES[.][k] = 1 for k in {0, 1, 8, 9},  BT[co][{0, 8}] = fp16(bias) / 2,  BT[co][{1, 9}] = fp16(bias - fp16(bias)) / 2
+  // (22 significant bits of the fp32 bias; both 16-byte halves of a 32-byte row hold the same values, so the tiles do
+  // not depend on the SWIZZLE_32B piece order), and the epilogue neither writes the bias back with tcgen05.st (15 %
+  // of its stall samples, and TMEM port time taken from its own tcgen05.ld) nor loads it (another 15 %: 16 LDS.128
+  // per row): one more MMA per 12.
+  constexpr bool kBiasMma = (C == 64) && !GHOST;
   if ((int)threadIdx.x < C) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+  if (kBiasMma) {
+    uint4* ones = reinterpret_cast<uint4*>(gbase + p.ones_off);      // 128 rows x 32 B
+    uint4* bt = reinterpret_cast<uint4*>(gbase + p.btile_off);       // 64 rows x 32 B
+    for (int i = threadIdx.x; i < 128 * 2; i += blockDim.x) ones[i] = make_uint4(0x3C003C00u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < 64 * 2; i += blockDim.x) {
+      const float b = p.bias[i >> 1];
+      const __half bh = __float2half_rn(b), bl = __float2half_rn(b - __half2float(bh));
+      const __half bh2 = __float2half_rn(0.5f * __half2float(bh)), bl2 = __float2half_rn(0.5f * __half2float(bl));
+      bt[i] = make_uint4((uint32_t)__half_as_ushort(bh2) | ((uint32_t)__half_as_ushort(bl2) << 16), 0u, 0u, 0u);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.n_aslots; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
     for (uint32_t a = 0; a < NBL; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+    for (int r = 0; r < p.n_rslots; ++r) { mbar_init(bar_rfull + 8 * r, 1); mbar_init(bar_rempty + 8 * r, 4); }
     mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -810,7 +864,7 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_st32_regs(ta, bb);
   };
   __syncthreads();                                         // s_bias visible
-  if (warp >= 2) {
+  if (!kBiasMma && warp >= 2) {
     const uint32_t grp = (uint32_t)(warp - 2) >> 2;
     const uint32_t lanes0 = (uint32_t)((warp & 3) * 32) << 16;
     for (uint32_t pos = grp; pos < 512u / C; pos += G) {
@@ -880,13 +934,18 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t g = grow + (uint32_t)t;
           mbar_wait(bar_tempty + 8 * Ring::idx(g), Ring::phase(g) ^ 1u);
           tc_fence_after();
+          if (kBiasMma && leader) {                        // the block starts from the bias (overwrites the old row)
+            const uint32_t d32 = desc_hi(256u, 6u);        // 32-byte rows, SWIZZLE_32B, 8-row groups of 256 B
+            tc_mma_f16(tmem_base + Ring::pos(Ring::idx(g)) * (uint32_t)C, desc_from(d32, desc_lo(base + p.ones_off)),
+                       desc_from(d32, desc_lo(base + p.btile_off)), idesc0 | (((uint32_t)C >> 3) << 17), 0);
+          }
         }
         const uint32_t alo0 = desc_lo(a_smem + as * p.a_slot_bytes);
         const int r_lo = max(t - 2, 0);
         int ra = min(t, R - 1);
         while (ra >= r_lo) {                               // runs of rows whose blocks are contiguous in TMEM
           int rb = r_lo;
-          if (!GHOST) {                                    // the ring seam splits the run
+          if (!GHOST && !p.wrap) {                         // the ring seam splits the run
             rb = ra;
             while (rb > r_lo && Ring::idx(grow + (uint32_t)rb) != 0u) --rb;
           }
@@ -917,6 +976,28 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       grow += (uint32_t)R;
     }
+  } else if (warp == 2 + 4 * G) {
+    // residual rows -> shared memory (C = 64): loaded from global memory in the epilogue they were its critical path
+    // (65 % of the stall samples of a residual conv sat on the first use of the residual registers, tensor pipe 36 %
+    // active); a dedicated TMA warp runs n_rslots rows ahead of the epilogue instead
+    if (kBiasMma && p.residual != nullptr && p.n_rslots > 0) {
+      const bool leader = elect_one_sync();
+      uint32_t g = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        int b, wt, h0, h1;
+        decode(item, b, wt, h0, h1);
+        const int R = h1 - h0;
+        for (int r = 0; r < R; ++r, ++g) {
+          const uint32_t rs = g % (uint32_t)p.n_rslots, rph = (g / (uint32_t)p.n_rslots) & 1u;
+          mbar_wait(bar_rempty + 8 * rs, rph ^ 1u);
+          if (leader) {
+            mbar_expect_tx(bar_rfull + 8 * rs, 16384u);
+            tma_load_4d(&tmR, bar_rfull + 8 * rs, base + p.r_off + rs * 16384u, 0, wt * kTileM, h0 + r, b);
+          }
+          __syncwarp();
+        }
+      }
+    }
   } else {
     // G epilogue warpgroups take the rows round robin: the epilogue is a chain of TMEM / memory round trips, more
     // warps in flight hide them
@@ -942,12 +1023,13 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       };
       const int r_first = (int)((grp + G - (grow % G)) % G); // first row of this item handled by this warpgroup
       constexpr bool kPipe = (G == 2);                       // register-prefetch the next row only when registers allow
-      if (kPipe && p.residual && r_first < R) load_res(r_first, rpre);
+      const bool res_regs = p.residual && (!kBiasMma || p.n_rslots == 0);   // residual from global memory (registers)
+      if (res_regs && kPipe && r_first < R) load_res(r_first, rpre);
       for (int r = r_first; r < R; r += G) {
         const uint32_t g = grow + (uint32_t)r;
         const uint32_t blk = Ring::idx(g);
         const size_t pix = res_row(r);
-        if (p.residual) {
+        if (res_regs) {
           // rows further ahead: pull them into L2 (one 64/128-byte pixel per thread)
           if (p.res_pf && valid && r + p.res_pf < R) {
             const __half* nxt = p.residual + pix + (size_t)p.res_pf * p.W * C;
@@ -965,11 +1047,57 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t gaddr = tmem_base + lanes + Ring::ghost_pos(blk) * (uint32_t)C;
         uint4* op = reinterpret_cast<uint4*>(p.out + pix);
         const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
+        if constexpr (kBiasMma) {
+          // the block needs nothing written back: both halves of the row are read with one wait and the block is
+          // released before the conversion / stores
+          uint32_t acc[C];
+          static_assert(C == 64 || !kBiasMma, "the bias-MMA epilogue reads 64 columns");
+          tc_ld64(taddr, acc);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * blk);
+          if (p.residual && p.n_rslots > 0) {
+            // this thread's pixel row of the residual slot (TMA SWIZZLE_128B: 16-byte piece j sits at j ^ (row & 7))
+            const uint32_t rs = g % (uint32_t)p.n_rslots, rph = (g / (uint32_t)p.n_rslots) & 1u;
+            mbar_wait(bar_rfull + 8 * rs, rph);
+            const int m = q * 32 + lane;
+            const uint8_t* rrow = gbase + p.r_off + rs * 16384u + (uint32_t)m * 128u;
+#pragma unroll
+            for (int j4 = 0; j4 < NJ; ++j4) rpre[j4] = *reinterpret_cast<const uint4*>(rrow + ((j4 ^ (m & 7)) << 4));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_rempty + 8 * rs);
+          }
+          if (valid) {
+#pragma unroll
+            for (int j4 = 0; j4 < NJ; ++j4) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[j4 * 8 + e]);
+              if (p.residual) {
+                const __half2* h2 = reinterpret_cast<const __half2*>(&rpre[j4]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __half22float2(h2[e]);
+                  v[2 * e] += f.x;
+                  v[2 * e + 1] += f.y;
+                }
+              }
+              uint4 u;
+              __half2* o2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __half2 hv = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                o2[e] = p.relu ? __hmax2(hv, zero2) : hv;
+              }
+              op[j4] = u;
+            }
+          }
+        } else
 #pragma unroll
         for (int hb = 0; hb < C / 32; ++hb) {              // 32 columns at a time (register budget)
           uint32_t acc[32];
           tc_ld32(taddr + hb * 32, acc);
-          st_bias(taddr + hb * 32, hb);                    // hand the block back holding the bias
+          if (!kBiasMma) st_bias(taddr + hb * 32, hb);     // hand the block back holding the bias
           if (has_ghost) {
             uint32_t gacc[32];
             tc_ld32(gaddr + hb * 32, gacc);
@@ -978,7 +1106,7 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(gacc[j]));
           }
           if (hb == C / 32 - 1) {
-            tc_wait_st();
+            if (!kBiasMma) tc_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * blk);
@@ -1552,9 +1680,16 @@ static int conv4_forward(const ConvLayer& L, const __half* in, const __half* res
   p.a_bytes = 130u * C * 2;
   p.a_slot_bytes = (uint32_t)align_up(p.a_bytes, 1024);
   p.wkw_bytes = 3u * C * C * 2;                              // one horizontal tap: [(kh, co) = 3C][ci = C]
-  p.n_aslots = 7;
+  bool res_smem = (C == 64) && residual != nullptr && !ghost;         // residual rows through shared memory
+  if (const char* e = getenv("B200_TC4_RES_SMEM")) res_smem = res_smem && atoi(e) != 0;   // A/B knob
+  p.n_aslots = res_smem ? 4 : 7;
+  p.n_rslots = res_smem ? 4 : 0;
+  { const char* e = getenv("B200_TC4_WRAP"); p.wrap = (e && atoi(e)) ? 1 : 0; }
   p.w_off = 2048;
-  p.a_off = 2048 + (uint32_t)align_up(3u * p.wkw_bytes, 1024);
+  p.ones_off = 2048 + (uint32_t)align_up(3u * p.wkw_bytes, 1024);
+  p.btile_off = p.ones_off + (C == 64 ? 4096u : 0u);
+  p.a_off = p.btile_off + (C == 64 ? 2048u : 0u);         // C = 64: + the constant tiles of the bias MMA (6 KB)
+  p.r_off = p.a_off + (uint32_t)p.n_aslots * (uint32_t)align_up(130u * C * 2, 1024);
   PFN_encodeTiled enc = get_encode();
   B200_CHECK(enc != nullptr, B200_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   const CUtensorMapSwizzle sw = (C == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -1579,13 +1714,24 @@ static int conv4_forward(const ConvLayer& L, const __half* in, const __half* res
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(B, v4) failed: %d", (int)r);
   }
-  const size_t smem = 1024 + p.a_off + (size_t)p.n_aslots * p.a_slot_bytes;
+  CUtensorMap tmR = tmA;                                    // residual rows: [B][H][W][C], one 128-pixel row per box
+  if (res_smem) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)C, 128, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(residual), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(R, v4) failed: %d", (int)r);
+  }
+  const size_t smem = 1024 + p.r_off + (size_t)p.n_rslots * 16384;
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
   int groups = (C == 64) ? 3 : 2;                          // epilogue warpgroups (A/B knob: B200_TC4_G = 2 | 3 | 4)
   if (const char* e = getenv("B200_TC4_G")) { const int v = atoi(e); if (v >= 2 && v <= 4) groups = v; }
   auto launch = [&](auto kernel, int g) -> int {
     B200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    kernel<<<grid, 64 + 128 * g, smem, stream>>>(tmA, tmB, p);
+    kernel<<<grid, 96 + 128 * g, smem, stream>>>(tmA, tmB, tmR, p);
     B200_CUDA_OK(cudaGetLastError());
     return B200_OK;
   };
@@ -1700,7 +1846,16 @@ static int conv3_forward(const ConvLayer& L, const __half* in, const __half* res
   p.tiles_w = ceil_div(W, p.bw);
   p.tiles_h = ceil_div(H, p.bh);
   p.m_tiles = ceil_div(p.C_out, 128);
-  p.num_items = B * p.tiles_h * p.tiles_w * p.m_tiles;
+  // weight multicast across a cluster (folded convs): mc CTAs share one weight stream (A/B knob: B200_TC3_MC = 1 | 2 | 4)
+  // Measured (round 2): emb_forward of 256 segments 12.90 ms (mc = 1) / 13.23 (2) / 14.22 (4) -- the bytes INTO each SM
+  // are unchanged by multicast (xbar -> L1 625 MB per launch either way), only the L2 reads drop, and the lockstep
+  // costs more than that saves: the limit is the SM ingress port, not the L2 slices.  Off by default.
+  p.mc = 1;
+  if (p.fold && !p.dbg) {
+    if (const char* e = getenv("B200_TC3_MC")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) p.mc = v; }
+  }
+  const int pixel_tiles = B * p.tiles_h * p.tiles_w;
+  p.num_items = ceil_div(pixel_tiles, p.mc) * p.m_tiles;   // per cluster
   const int wtaps = p.fold ? 3 : 1;                        // weight taps per stage
   p.a_bytes = (uint32_t)wtaps * 128u * p.Ck * 2;
   // the MMA reads N = 256 rows (from a start shifted by up to 2 rows when folding): keep the slot that large
@@ -1740,15 +1895,48 @@ static int conv3_forward(const ConvLayer& L, const __half* in, const __half* res
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(W, v3) failed: %d", (int)r);
   }
+  CUtensorMap tmWs = tmW;                                   // 1/mc of one weight tap: the slice a CTA multicasts
+  if (p.mc > 1) {
+    const int rows = p.m_tiles * 128;
+    cuuint64_t dims[3] = {(cuuint64_t)L.C_in, (cuuint64_t)rows, (cuuint64_t)(L.ksize * L.ksize)};
+    cuuint64_t strides[2] = {(cuuint64_t)L.C_in * 2, (cuuint64_t)rows * L.C_in * 2};
+    cuuint32_t box[3] = {(cuuint32_t)p.Ck, (cuuint32_t)(128 / p.mc), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tmWs, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(L.w3), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     p.swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_CHECK(r == CUDA_SUCCESS, B200_ERR_CUDA, "cuTensorMapEncodeTiled(W slice, v3) failed: %d", (int)r);
+  }
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA_OK(cudaFuncSetAttribute(conv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const size_t smem = 1024 + 2048 + kV3Staging + (size_t)p.nstages * slot;
-  const int grid = p.num_items < num_sms ? p.num_items : num_sms;
-  conv_tc3_kernel<<<grid, kV3Threads, smem, stream>>>(tmX, tmW, p);
-  B200_CUDA_OK(cudaGetLastError());
+  int max_clusters = num_sms / p.mc;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kV3Threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)p.mc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (p.mc > 1) {
+    static int cached[5] = {0, 0, 0, 0, 0};                 // co-resident clusters of this size (GPC boundaries)
+    if (cached[p.mc] == 0) {
+      cfg.gridDim = dim3((unsigned)(max_clusters * p.mc));
+      int n = 0;
+      B200_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, conv_tc3_kernel, &cfg));
+      cached[p.mc] = n > 0 ? n : 1;
+    }
+    if (cached[p.mc] < max_clusters) max_clusters = cached[p.mc];
+  }
+  const int nclusters = p.num_items < max_clusters ? p.num_items : max_clusters;
+  cfg.gridDim = dim3((unsigned)(nclusters * p.mc));
+  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc3_kernel, tmX, tmW, tmWs, p));
   return B200_OK;
 }
 
