@@ -646,6 +646,7 @@ class OracleOutput:
     count: SWF = None
     embeddings: np.ndarray = None
     hard_clusters: np.ndarray = None
+    soft_clusters: np.ndarray = None                        # (chunks, speakers, clusters) scores behind hard_clusters
     centroids: np.ndarray = None
     discrete: SWF = None
     exclusive: SWF = None
@@ -678,8 +679,9 @@ def apply(seg_model, emb_model, plda: PLDA, waveform: torch.Tensor, threshold=0.
     emb = embeddings if embeddings is not None else get_embeddings(
         emb_model, waveform, seg, exclude_overlap=exclude_overlap, batch_size=emb_batch, share_trunk=share_trunk)
     out.embeddings = emb
-    hard, _, centroids = vbx_clustering(emb, seg.data, plda, threshold, Fa, Fb, num_clusters=num_speakers,
-                                        min_clusters=min_speakers, max_clusters=max_speakers)
+    hard, soft, centroids = vbx_clustering(emb, seg.data, plda, threshold, Fa, Fb, num_clusters=num_speakers,
+                                           min_clusters=min_speakers, max_clusters=max_speakers)
+    out.soft_clusters = soft
     count.data = np.minimum(count.data, max_speakers).astype(np.int8)
     inactive = np.sum(seg.data, axis=1) == 0
     hard = hard.copy()

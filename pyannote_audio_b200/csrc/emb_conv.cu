@@ -774,7 +774,6 @@ struct ConvV4Params {
   uint32_t ones_off, btile_off;      // C = 64: constant A tile (ones) and B tile (bias) of the bias MMA
   uint32_t r_off;                    // C = 64 with a residual: n_rslots slots of 16 KB (one residual pixel row each)
   int n_rslots;
-  int wrap;                          // experiment (B200_TC4_WRAP): never split a run at the ring seam
 };
 
 // threads = TMA warp + MMA warp + G epilogue warpgroups of 4 warps (warpgroup k drains the rows r = k (mod G)) + one
@@ -795,6 +794,9 @@ struct TmemRing {
   __device__ static __forceinline__ uint32_t ghost_pos(uint32_t i) { return 2u * NBL - 1u - i; }   // i >= NBL - 2
 };
 
+#ifdef B200_TC4_DEBUG
+__device__ unsigned int g_tc4_dbg = 0;
+#endif
 template <int C, bool GHOST, int G>
 __global__ void __launch_bounds__(96 + 128 * G, 1)
 conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -945,7 +947,8 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int ra = min(t, R - 1);
         while (ra >= r_lo) {                               // runs of rows whose blocks are contiguous in TMEM
           int rb = r_lo;
-          if (!GHOST && !p.wrap) {                         // the ring seam splits the run
+          if (!GHOST) {                                    // the ring seam splits the run (TMEM columns do not wrap:
+                                                           // a run past column 511 faults, measured)
             rb = ra;
             while (rb > r_lo && Ring::idx(grow + (uint32_t)rb) != 0u) --rb;
           }
@@ -1064,6 +1067,23 @@ conv_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint8_t* rrow = gbase + p.r_off + rs * 16384u + (uint32_t)m * 128u;
 #pragma unroll
             for (int j4 = 0; j4 < NJ; ++j4) rpre[j4] = *reinterpret_cast<const uint4*>(rrow + ((j4 ^ (m & 7)) << 4));
+            // generic-proxy reads, then the async proxy (TMA) overwrites the slot: without this fence the arrive
+            // overtook the loads (wrong residuals now and then; found with the B200_TC4_DEBUG compare below)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#ifdef B200_TC4_DEBUG
+            if (valid) {                                   // compare with the residual in global memory (not yet overwritten)
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + res_row(r));
+              for (int j4 = 0; j4 < NJ; ++j4) {
+                const uint4 gv = rp[j4];
+                if (gv.x != rpre[j4].x || gv.y != rpre[j4].y || gv.z != rpre[j4].z || gv.w != rpre[j4].w) {
+                  if (atomicAdd(&g_tc4_dbg, 1u) < 12u)
+                    printf("tc4 residual mismatch: blk %d item %d r %d g %u rs %u m %d j4 %d smem %08x global %08x\n",
+                           (int)blockIdx.x, item, r, g, rs, m, j4, rpre[j4].x, gv.x);
+                  break;
+                }
+              }
+            }
+#endif
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_rempty + 8 * rs);
           }
@@ -1682,9 +1702,16 @@ static int conv4_forward(const ConvLayer& L, const __half* in, const __half* res
   p.wkw_bytes = 3u * C * C * 2;                              // one horizontal tap: [(kh, co) = 3C][ci = C]
   bool res_smem = (C == 64) && residual != nullptr && !ghost;         // residual rows through shared memory
   if (const char* e = getenv("B200_TC4_RES_SMEM")) res_smem = res_smem && atoi(e) != 0;   // A/B knob
-  p.n_aslots = res_smem ? 4 : 7;
-  p.n_rslots = res_smem ? 4 : 0;
-  { const char* e = getenv("B200_TC4_WRAP"); p.wrap = (e && atoi(e)) ? 1 : 0; }
+  int groups = (C == 64) ? 3 : 2;                          // epilogue warpgroups (A/B knob: B200_TC4_G = 2 | 3 | 4)
+  if (const char* e = getenv("B200_TC4_G")) { const int v = atoi(e); if (v >= 2 && v <= 4) groups = v; }
+  if (ghost) groups = 2;
+  // ONE residual slot per epilogue warpgroup (row g -> slot g mod G = the group that drains row g): a slot shared by
+  // several groups lets a fast group wait on a barrier two phases ahead (parity aliasing: wrong rows, corrupted
+  // arrival counts -- seen as non-deterministic results and launch failures); the load of row g starts when the
+  // group has consumed row g - G, three row times before row g's accumulator is complete
+  p.n_rslots = res_smem ? groups : 0;
+  p.n_aslots = res_smem ? (groups <= 3 ? 5 : 4) : 7;
+  if (const char* e = getenv("B200_TC4_ASLOTS")) { const int v = atoi(e); if (v >= 2 && v <= p.n_aslots) p.n_aslots = v; }
   p.w_off = 2048;
   p.ones_off = 2048 + (uint32_t)align_up(3u * p.wkw_bytes, 1024);
   p.btile_off = p.ones_off + (C == 64 ? 4096u : 0u);
@@ -1727,8 +1754,6 @@ static int conv4_forward(const ConvLayer& L, const __half* in, const __half* res
   }
   const size_t smem = 1024 + p.r_off + (size_t)p.n_rslots * 16384;
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
-  int groups = (C == 64) ? 3 : 2;                          // epilogue warpgroups (A/B knob: B200_TC4_G = 2 | 3 | 4)
-  if (const char* e = getenv("B200_TC4_G")) { const int v = atoi(e); if (v >= 2 && v <= 4) groups = v; }
   auto launch = [&](auto kernel, int g) -> int {
     B200_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     kernel<<<grid, 96 + 128 * g, smem, stream>>>(tmA, tmB, tmR, p);

@@ -182,6 +182,7 @@ struct RecTcParams {
 };
 
 template <int NP, bool ASYNC>
+// (registers are allocated for 12 warps when 10 are launched: 168 per thread is the limit, __maxnreg__(200) fails to launch)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kRecThreads, 1)
 lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, RecTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -330,9 +331,10 @@ lstm_rec_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_consta
 #pragma unroll
       for (int chunk = 0; chunk < 4; ++chunk) {
         uint32_t acc[32];
-        tc_ld32(taddr + chunk * 32, acc);
+        // next chunk's Gx first (global loads: the longest latency of the step), then the TMEM load and its wait
         if (chunk < 3) load_gx(t, chunk + 1, gx[(chunk + 1) & 1]);
         else if (s + 1 < T) load_gx(tn, 0, gx[0]);
+        tc_ld32(taddr + chunk * 32, acc);
         const float4* gxc = gx[chunk & 1];
         uint4 ph, pl;
         __half2* ph2 = reinterpret_cast<__half2*>(&ph);

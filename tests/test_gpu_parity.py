@@ -328,9 +328,39 @@ def _rows(x):
     return [tuple(int(v) for v in r) for r in x]
 
 
-def _compare_with_oracle(art, out, ref, independent):
+LOW_ASSIGN_MARGIN = 1e-3
+
+
+def _low_margin_assignments(hard, ref):
+    """Chunks whose speaker -> cluster assignment differs from the INDEPENDENT oracle run although the CUDA choice is
+    within LOW_ASSIGN_MARGIN of the optimum under the oracle's own scores (2 - cosine distance to the centroids): a
+    near-tie of the reference's constrained argmax that fp16-level embedding noise (relative 1e-3) decides either
+    way -- the clustering counterpart of the low-margin frames of the segmentation.  Returns (differing chunks,
+    those of them that are low-margin)."""
+    soft = ref.soft_clusters
+    differ = np.flatnonzero((np.asarray(hard) != ref.hard_clusters).any(axis=1))
+    low = []
+    if soft is None or np.asarray(hard).shape != ref.hard_clusters.shape:
+        return differ, np.array(low, dtype=int)
+    for c in differ:
+        def objective(h):
+            return sum(soft[c, s, k] for s, k in enumerate(h) if 0 <= k < soft.shape[2])
+        if objective(ref.hard_clusters[c]) - objective(np.asarray(hard)[c]) < LOW_ASSIGN_MARGIN:
+            low.append(c)
+    return differ, np.array(low, dtype=int)
+
+
+def _compare_with_oracle(art, out, ref, independent, own_embeddings=False):
     """Integer outputs of the CUDA pipeline against an oracle run (bit-exact)."""
     assert np.array_equal(art["count"].cpu().numpy(), ref.count.data[:, 0])
+    if own_embeddings:
+        # the oracle clusters ITS OWN fp32 embeddings: identical decisions except reported near-ties
+        differ, low = _low_margin_assignments(art["hard_clusters"], ref)
+        print(f"[parity] independent run: {len(differ)} chunk(s) with a different assignment, {len(low)} of them "
+              f"within {LOW_ASSIGN_MARGIN} of the oracle's optimum")
+        assert len(differ) == len(low), "cluster assignment differs from the independent oracle with a clear margin"
+        if len(differ):
+            return False                                  # downstream stages are checked against the re-fed oracle
     assert np.array_equal(art["hard_clusters"], ref.hard_clusters), ("independent" if independent else "re-fed")
     assert np.array_equal(art["discrete"][:, : ref.discrete.data.shape[1]], ref.discrete.data.astype(np.uint8))
     assert not art["discrete"][:, ref.discrete.data.shape[1]:].any()
@@ -341,6 +371,7 @@ def _compare_with_oracle(art, out, ref, independent):
     assert got == ref.times
     gotx = [(s.start, s.end, lab) for s, _, lab in out.exclusive_speaker_diarization.itertracks(yield_label=True)]
     assert gotx == ref.exclusive_times
+    return True
 
 
 def _e2e_case(pipeline, oracle_models, wav, name, exclude_overlap=False, min_duration_off=0.0, emb_oracle=True):
@@ -377,12 +408,13 @@ def _e2e_case(pipeline, oracle_models, wav, name, exclude_overlap=False, min_dur
                       exclude_overlap=exclude_overlap, min_duration_off=min_duration_off)
         cos = (emb * ref.embeddings).sum(-1) / (np.linalg.norm(emb, axis=-1) * np.linalg.norm(ref.embeddings, axis=-1))
         assert (1 - cos).max() <= 1e-3, f"embedding cosine distance {np.nanmax(1 - cos)}"
-        _compare_with_oracle(art, out, ref, independent=identical)
+        same = _compare_with_oracle(art, out, ref, independent=identical, own_embeddings=True)
         a, b = out.speaker_embeddings, ref.speaker_embeddings
-        assert a.shape == b.shape
+        assert a.shape == b.shape or not same
         real = np.linalg.norm(b, axis=-1) > 0                # rows padded for labels without a centroid are all-zero
-        assert np.array_equal(real, np.linalg.norm(a, axis=-1) > 0)
-        if real.any():
+        if same:
+            assert np.array_equal(real, np.linalg.norm(a, axis=-1) > 0)
+        if same and real.any():
             ccos = (a * b).sum(-1)[real] / (np.linalg.norm(a, axis=-1) * np.linalg.norm(b, axis=-1))[real]
             assert (1 - ccos).max() <= 1e-3
     # and with the CUDA embeddings fed to the oracle's clustering: everything downstream is exact arithmetic
