@@ -48,6 +48,12 @@ __device__ __forceinline__ void fft16_stages(float (&xr)[16], float (&xi)[16], T
   }
 }
 
+// Round 2: one warp computes TWO frames.  A 512-point real FFT is a 256-point complex FFT of z[n] = x[2n] + i x[2n+1]
+// followed by   X[k] = E[k] + W_512^k O[k],  E = (Z[k] + conj Z[256-k]) / 2,  O = (Z[k] - conj Z[256-k]) / 2i,
+// and stages 0-7 of the register-blocked 512-point DIT schedule below already ARE two independent 256-point FFTs
+// on the two halves of the array (stage 8 was the only one that mixed them): frame A lives in elements [0, 256),
+// frame B in [256, 512), half a warp each.  Same arithmetic per butterfly, less than half of it per frame
+// (the padded imaginary half of the old complex transform was all zeros): 663 -> see profiles/ us per 256 segments.
 __global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wav,
                                                     const long long* __restrict__ chunk_off,
                                                     const int* __restrict__ chunk_valid,
@@ -61,57 +67,54 @@ __global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wa
   for (int i = threadIdx.x; i < 512; i += blockDim.x) (&s_tw[0][0])[i] = twiddle[i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int frame = blockIdx.x * 8 + warp;
+  const int l = lane & 15, f = lane >> 4;                  // half-warp f owns frame 2 * pair + f
+  const int pair = blockIdx.x * 8 + warp;
   const int b = blockIdx.y;
-  if (frame >= kFbankFrames) return;
+  if (2 * pair >= kFbankFrames) return;                    // warp-uniform (kFbankFrames is even)
+  const int frame = 2 * pair + f;
   float* re = s_re[warp];
   float* im = s_im[warp];
   const float* xw = wav + chunk_off[b];
   const int valid = chunk_valid[b];
   const int base = frame * kFrameHop;
+  const int h0 = f << 8;                                   // this frame's half of the arrays
 
-  // load + scale, frame mean
-  float x[13];
+  // load + scale, frame mean (sample i = l + 16 j)
+  float x[25];
   float sum = 0.f;
 #pragma unroll
-  for (int j = 0; j < 13; ++j) {
-    const int i = lane + 32 * j;
-    float v = 0.f;
-    if (i < kFrameLen) {
-      const int g = base + i;
-      v = (g < valid) ? xw[g] * 32768.0f : 0.f;
-    }
+  for (int j = 0; j < 25; ++j) {
+    const int g = base + l + 16 * j;
+    const float v = (g < valid) ? xw[g] * 32768.0f : 0.f;
     x[j] = v;
     sum += v;
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float mean = sum / (float)kFrameLen;
+  // DC removal, pre-emphasis (previous sample from the neighbouring lane; sample 0 replicates itself), window;
+  // z[n] = v[2n] + i v[2n+1] scattered to bit-reversed order: even lanes write real parts, odd lanes imaginary parts
+  float* dst = (l & 1) ? im : re;
+  float carry = 0.f;                                       // lane 15's sample of the previous j (for lane 0)
 #pragma unroll
-  for (int j = 0; j < 13; ++j) {
-    const int i = lane + 32 * j;
-    if (i < kFrameLen) im[fpad(i)] = x[j] - mean;      // stage DC-removed samples in im[]
-  }
-  __syncwarp();
-  // pre-emphasis + window, scatter to bit-reversed order in re[]
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int i = lane + 32 * j;
+  for (int j = 0; j < 32; ++j) {
+    const int i = l + 16 * j;
     float v = 0.f;
-    if (i < kFrameLen) {
-      const float cur = im[fpad(i)];
-      const float prev = im[fpad(i > 0 ? i - 1 : 0)];
+    if (j < 25) {
+      const float cur = x[j] - mean;
+      float prev = __shfl_up_sync(0xffffffffu, cur, 1, 16);
+      if (l == 0) prev = (j == 0) ? cur : carry;
+      carry = __shfl_sync(0xffffffffu, cur, 15, 16);
       v = (cur - 0.97f * prev) * window[i];
     }
-    re[fpad(bitrev9(i))] = v;
+    dst[fpad(h0 + (int)(__brev((unsigned)(i >> 1)) >> 24))] = v;
   }
   __syncwarp();
-  // 512-point radix-2 DIT FFT as 4 + 4 + 1 stages: two register-blocked passes of 16 values per lane, then the last
-  // stage.  (One shared-memory round trip per pass instead of one per stage.)
+  // two 256-point radix-2 DIT FFTs (one per half-warp) as 4 + 4 stages: two register-blocked passes of 16 values
   float xr[16], xi[16];
-  {  // stages 0-3: lane owns elements 16 lane .. 16 lane + 15; imaginary input is zero; twiddles are constants
+  {  // stages 0-3: lane owns elements 16 lane .. 16 lane + 15 (lanes 16-31: the second frame's half)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { xr[j] = re[fpad(16 * lane + j)]; xi[j] = 0.f; }
+    for (int j = 0; j < 16; ++j) { xr[j] = re[fpad(16 * lane + j)]; xi[j] = im[fpad(16 * lane + j)]; }
     fft16_stages(xr, xi, [&](int s, int pos, float& wr, float& wi) {
       const int k = pos * (256 >> s);                      // multiples of 32: compile-time after unrolling
       wr = s_tw[k][0];
@@ -121,13 +124,13 @@ __global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wa
     for (int j = 0; j < 16; ++j) { re[fpad(16 * lane + j)] = xr[j]; im[fpad(16 * lane + j)] = xi[j]; }
   }
   __syncwarp();
-  {  // stages 4-7: lane owns elements e0 + 16 j, e0 = (lane & 15) + 256 (lane >> 4)
-    const int e0 = (lane & 15) + ((lane >> 4) << 8);
+  {  // stages 4-7: lane owns elements e0 + 16 j of its frame's half
+    const int e0 = l + h0;
 #pragma unroll
     for (int j = 0; j < 16; ++j) { xr[j] = re[fpad(e0 + 16 * j)]; xi[j] = im[fpad(e0 + 16 * j)]; }
     fft16_stages(xr, xi, [&](int s, int pos, float& wr, float& wi) {
-      // global stage 4 + s, position inside the butterfly group = (lane & 15) + 16 pos
-      const int k = ((lane & 15) + 16 * pos) * (16 >> s);
+      // global stage 4 + s, position inside the butterfly group = l + 16 pos
+      const int k = (l + 16 * pos) * (16 >> s);
       wr = s_tw[k][0];
       wi = s_tw[k][1];
     });
@@ -135,27 +138,29 @@ __global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wa
     for (int j = 0; j < 16; ++j) { re[fpad(e0 + 16 * j)] = xr[j]; im[fpad(e0 + 16 * j)] = xi[j]; }
   }
   __syncwarp();
-  // stage 8 fused with the power spectrum of bins 0..255 (only the upper output of each butterfly is needed; the
-  // Nyquist bin carries zero mel weight: kaldi pads the bank with a zero column)
-  float pw[8];
+  // real-FFT split + power spectrum of bins 0..255 (the Nyquist bin carries zero mel weight: kaldi pads the bank with
+  // a zero column); this lane's bins are k = l + 16 j
+  float pw[16];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int k = lane + 32 * j;
+  for (int j = 0; j < 16; ++j) {
+    const int k = l + 16 * j, km = (256 - k) & 255;
+    const float zr = re[fpad(h0 + k)], zi = im[fpad(h0 + k)];
+    const float mr = re[fpad(h0 + km)], mi = im[fpad(h0 + km)];
+    const float er = 0.5f * (zr + mr), ei = 0.5f * (zi - mi);
+    const float orr = 0.5f * (zi + mi), oi = -0.5f * (zr - mr);
     const float wr = s_tw[k][0], wi = s_tw[k][1];
-    const float br = re[fpad(k + 256)], bi = im[fpad(k + 256)];
-    const float tr = wr * br - wi * bi, ti = wr * bi + wi * br;
-    const float zr = re[fpad(k)] + tr, zi = im[fpad(k)] + ti;
-    const float a = sqrtf(zr * zr + zi * zi);               // reference: rfft().abs().pow(2)
+    const float xr_ = er + (wr * orr - wi * oi), xi_ = ei + (wr * oi + wi * orr);
+    const float a = sqrtf(xr_ * xr_ + xi_ * xi_);            // reference: rfft().abs().pow(2)
     pw[j] = a * a;
   }
   __syncwarp();
 #pragma unroll
-  for (int j = 0; j < 8; ++j) re[lane + 32 * j] = pw[j];
+  for (int j = 0; j < 16; ++j) re[h0 + l + 16 * j] = pw[j];
   __syncwarp();
-  for (int m = lane; m < kMel; m += 32) {
+  for (int m = l; m < kMel; m += 16) {
     const int st = mel_start[m], ln = mel_len[m], off = mel_off[m];
     float acc = 0.f;
-    for (int i = 0; i < ln; ++i) acc = fmaf(re[st + i], mel_w[off + i], acc);
+    for (int i = 0; i < ln; ++i) acc = fmaf(re[h0 + st + i], mel_w[off + i], acc);
     out[((size_t)b * kFbankFrames + frame) * kMel + m] = logf(fmaxf(acc, kEps));
   }
 }
@@ -210,7 +215,7 @@ int frames_to_nchw(const __half* feat, float* out, int B, cudaStream_t stream) {
 
 int fbank_forward(const EmbWeights& W, const float* wav, const long long* chunk_off, const int* chunk_valid, int B,
                   float* fbank, float* fmean, cudaStream_t stream) {
-  dim3 grid(ceil_div(kFbankFrames, 8), B);
+  dim3 grid(ceil_div(kFbankFrames, 16), B);                 // 8 warps x 2 frames per block
   fbank_kernel<<<grid, 256, 0, stream>>>(wav, chunk_off, chunk_valid, W.window, W.twiddle, W.mel_w, W.mel_start,
                                          W.mel_len, W.mel_off, fbank);
   B200_CUDA_OK(cudaGetLastError());

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "seg.cuh"
 #include "tc_common.cuh"
+#include <cstdlib>
 
 namespace b200 {
 
@@ -35,6 +36,8 @@ struct GemmTcParams {
   // result overlaps the GEMM tile by tile and no separate collective runs
   float* C_peer[7];
   int n_peer;
+  int dbg;             // timing experiment only (B200_GEMM_DBG; wrong results): 1 = B tiles, 2 = A tiles are loaded only
+                       // for the first pass over the stages
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -76,9 +79,12 @@ gemm_tc_split_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_cons
       for (int kb = 0; kb < p.kblocks; ++kb) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
         if (leader) {
-          mbar_expect_tx(bar_full + 8 * stage, p.stage_bytes);
+          const bool warm = p.dbg && (tile != (int)blockIdx.x || kb >= (int)p.nstages);
+          const bool do_a = !(warm && p.dbg == 2), do_b = !(warm && p.dbg == 1);
+          mbar_expect_tx(bar_full + 8 * stage, (do_a ? 2 * p.a_bytes : 0u) + (do_b ? 2 * p.b_bytes : 0u));
           const uint32_t sa = stage0 + stage * p.stage_bytes;
-          if (p.gx_T > 0) {   // rows = 128 consecutive sequences at one time step of a [b][t][k] array
+          if (!do_a) {
+          } else if (p.gx_T > 0) {   // rows = 128 consecutive sequences at one time step of a [b][t][k] array
             const int t = tm % p.gx_T, b0 = (tm / p.gx_T) * kGemmM;
             tma_load_3d(&tmAh, bar_full + 8 * stage, sa, kb * kGemmK, t, b0);
             tma_load_3d(&tmAl, bar_full + 8 * stage, sa + p.a_bytes, kb * kGemmK, t, b0);
@@ -86,8 +92,10 @@ gemm_tc_split_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_cons
             tma_load_2d(&tmAh, bar_full + 8 * stage, sa, kb * kGemmK, tm * kGemmM);
             tma_load_2d(&tmAl, bar_full + 8 * stage, sa + p.a_bytes, kb * kGemmK, tm * kGemmM);
           }
-          tma_load_2d(&tmBh, bar_full + 8 * stage, sa + 2 * p.a_bytes, kb * kGemmK, tn * Nt);
-          tma_load_2d(&tmBl, bar_full + 8 * stage, sa + 2 * p.a_bytes + p.b_bytes, kb * kGemmK, tn * Nt);
+          if (do_b) {
+            tma_load_2d(&tmBh, bar_full + 8 * stage, sa + 2 * p.a_bytes, kb * kGemmK, tn * Nt);
+            tma_load_2d(&tmBl, bar_full + 8 * stage, sa + 2 * p.a_bytes + p.b_bytes, kb * kGemmK, tn * Nt);
+          }
         }
         __syncwarp();
         if (++stage == p.nstages) { stage = 0; phase ^= 1; }
@@ -268,6 +276,7 @@ static int launch_gemm(GemmTcParams& p, const CUtensorMap& tmAh, const CUtensorM
   p.stage_bytes = 2 * p.a_bytes + 2 * p.b_bytes;          // 64 KB (Nt = 128) or 96 KB (Nt = 256)
   p.nstages = p.Nt == 256 ? 2 : 3;
   p.idesc = (1u << 4) | ((uint32_t)(p.Nt >> 3) << 17) | ((uint32_t)(kGemmM >> 4) << 24);
+  if (const char* e = getenv("B200_GEMM_DBG")) p.dbg = atoi(e);
   CUtensorMap tmBh, tmBl;
   int rc;
   if ((rc = make_map_2d(&tmBh, B_hi, p.N, p.K, ldb, p.Nt))) return rc;

@@ -157,7 +157,6 @@ sinc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         }
       }
       asm volatile("bar.sync 2, 256;" ::: "memory");        // samples complete
-      if (item + (int)gridDim.x < p.num_items) load_raw(item + (int)gridDim.x);
       for (uint32_t ks = 0; ks < 16; ++ks, ++cnt) {
         const uint32_t stage = cnt & (kSTStages - 1);
         mbar_wait(bar_bempty + 8 * stage, ((cnt / kSTStages) & 1u) ^ 1u);
@@ -185,6 +184,11 @@ sinc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_bfull + 8 * stage);
       }
+      // The next tile's raw samples are requested only now: the proxy fence above is a MEMBAR that waits for every
+      // outstanding memory operation of the warp, so with the global loads issued before the k-step loop (round 1) the
+      // first fence of every tile sat out their DRAM latency (~1.5 us against 3.2 us of MMAs per tile: the "unexplained"
+      // 2x over the MMA floor).  Here the latency falls into the slack of the 8-stage ring instead.
+      if (item + (int)gridDim.x < p.num_items) load_raw(item + (int)gridDim.x);
     }
   } else {
     // ---- epilogue: abs, MaxPool1d(3), store, InstanceNorm partial sums -------------------------------------------

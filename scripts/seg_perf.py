@@ -12,15 +12,20 @@ valid = np.full(n, 160000, dtype=np.int32)
 buf = wav[0].to(dev).contiguous()
 ctx.load_segmentation(syn.make_segmentation_state_dict(0))
 import os
-if len(sys.argv) > 2 and sys.argv[2] == "tc":
-    # A/B over the tensor-core recurrence knobs (read per call by the library)
-    for np_, pf, asy in ((0, 0, 0), (0, 0, 1), (-1, 0, 1), (0, 2, 1), (0, 0, 0), (0, 0, 1)):
-        os.environ["B200_LSTM_NP"], os.environ["B200_LSTM_PF"], os.environ["B200_LSTM_ASYNC"] = str(np_), str(pf), str(asy)
+if len(sys.argv) > 2 and sys.argv[2] == "env":
+    # A/B inside one process: SEG_PERF_ENVS="A=1;A=2,B=3" runs one timing per ';'-separated setting (knobs are read per call)
+    for setting in os.environ.get("SEG_PERF_ENVS", "").split(";"):
+        for kv in filter(None, setting.split(",")):
+            k, v = kv.split("=")
+            os.environ[k] = v
         ctx.seg_forward(buf, off, valid); torch.cuda.synchronize()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(); out = ctx.seg_forward(buf, off, valid); e1.record(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); out = ctx.seg_forward(buf, off, valid); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
         cls = out[0] if isinstance(out, tuple) else out
-        print(f"np={np_} pf={pf} async={asy}: {n} chunks seg_forward {e0.elapsed_time(e1):.1f} ms, checksum {int(cls.sum())}", flush=True)
+        print(f"[{setting}] {n} chunks seg_forward min {min(ts):.1f} ms, checksum {int(cls.sum())}", flush=True)
     sys.exit(0)
 for impl in (1, 0):
     ctx.set_option("seg_rec_impl", impl)
