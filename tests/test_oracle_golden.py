@@ -134,3 +134,27 @@ def test_to_diarization_tie_rule_only_differs_from_numpy_default_on_ties():
         srt = np.sort(act[t])[::-1]
         assert 0 < c < len(srt) and srt[c - 1] == srt[c], f"frame {t}: outputs differ without a boundary tie"
         assert a.data[t].sum() == b.data[t].sum() == c
+
+
+def test_oracle_reports_assignment_scores():
+    """OracleOutput.soft_clusters (used by the GPU parity tests to tell near-ties of the constrained assignment from
+    real differences) is consistent with hard_clusters: every assigned (chunk, speaker) picks a valid cluster and the
+    oracle's own choice is optimal under its scores."""
+    import itertools
+
+    from oracle import pipeline as P
+    rng = np.random.default_rng(5)
+    emb = rng.standard_normal((9, 3, 256)).astype(np.float32)
+    emb[:, :2] += 4.0 * rng.standard_normal((1, 1, 256)).astype(np.float32)      # two similar speakers per chunk
+    seg = (rng.random((9, 589, 3)) > 0.4).astype(np.float32)
+    from pyannote_audio_b200 import synthetic as syn
+    hard, soft, _ = P.vbx_clustering(emb, seg, P.PLDA(**syn.make_plda(2)), 0.6, 0.07, 0.8, num_clusters=None,
+                                     min_clusters=1, max_clusters=np.inf)
+    assert soft.shape[:2] == hard.shape and soft.shape[2] >= int(hard.max()) + 1
+    K = soft.shape[2]
+    for c in range(hard.shape[0]):
+        got = sum(soft[c, s, k] for s, k in enumerate(hard[c]) if k >= 0)
+        best = max(sum(soft[c, s, k] for s, k in zip(sp, ks))
+                   for n in range(1, min(3, K) + 1)
+                   for sp in itertools.permutations(range(3), n) for ks in itertools.combinations(range(K), n))
+        assert got >= best - 1e-9
