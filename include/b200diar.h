@@ -141,6 +141,14 @@ int b200_push(b200_ctx* ctx, const void* src, int64_t bytes, void* const* dsts, 
 /* compute_fbank (wespeaker/__init__.py:113-139): fbank[num_chunks][998][80], global-mean centred. */
 int b200_emb_fbank(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, const int32_t* chunk_valid,
                    int32_t num_chunks, float* fbank, void* stream);
+/* Host-only (no device work): the shared-frame fbank layout b200_emb_forward uses for a chunk list processed in
+ * sub-batches of `sub_batch` chunks.  The reference computes 998 fbank frames per chunk (wespeaker/__init__.py:113-139)
+ * although consecutive chunks of Inference.slide (core/inference.py:235-257: step = 0.1 * duration = 100 frame hops)
+ * share 898 of them; overlapping, hop-aligned, full chunks are grouped into runs whose frames are computed once.
+ * frame0[num_chunks]: first fbank row of each chunk inside its sub-batch; rows_per_sub_batch[ceil(n / sub_batch)]:
+ * fbank rows computed per sub-batch (998 * chunks without sharing).  Returns the number of runs, < 0 on bad arguments. */
+int64_t b200_emb_fbank_plan(const int64_t* chunk_off, const int32_t* chunk_valid, int32_t num_chunks, int32_t sub_batch,
+                            int32_t share, int32_t* frame0, int32_t* rows_per_sub_batch);
 /* ResNet.forward_frames on a given fbank (resnet.py:399-419): frames[num_chunks][256][10][125] fp32 (NCHW). */
 int b200_emb_trunk(b200_ctx* ctx, const float* fbank, int32_t num_chunks, float* frames, void* stream);
 /* StatsPool.forward (models/blocks/pooling.py:76-130): seq[B][F][T], weights[B][S][Tw] or NULL -> out[B][S][2F]. */

@@ -86,6 +86,7 @@ _PROTOS = {
     "b200_vbx": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double,
                            C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200_audio_num_frames": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+    "b200_emb_fbank_plan": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "b200_audio_ingest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "b200_aggregate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,

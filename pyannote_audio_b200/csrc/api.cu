@@ -7,6 +7,8 @@
 #include "emb.cuh"
 #include "post.cuh"
 #include "seg.cuh"
+#include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 
@@ -25,6 +27,7 @@ struct b200_ctx {
   int conv_impl = 8;   // channels-as-M conv for C_out >= 128, strip-streaming conv for the narrow stride-1 3x3, per-tap conv otherwise
   int seg_max_batch = 4736;     // chunks per segmentation sub-batch (37 LSTM tiles of 128 sequences x 2 directions = 74 clusters)
   int emb_max_batch = 256;      // chunks per embedding sub-batch
+  int fbank_share = 1;          // 1 = overlapping hop-aligned chunks share their fbank frames (emb.cuh: FbankRun)
   int64_t launches = 0;
   SegWeights seg;
   EmbWeights emb;
@@ -34,6 +37,8 @@ struct b200_ctx {
   size_t ws_cap = 0;
   long long* d_off = nullptr;
   int* d_valid = nullptr;
+  int* d_frame0 = nullptr;         // first fbank row of every chunk inside its sub-batch
+  b200::FbankRun* d_runs = nullptr; // fbank runs of all sub-batches, back to back
   int meta_cap = 0;
   // optional CUDA-event timers around the dominant kernels (bench.py's live roofline measurement)
   int profile = 0;
@@ -106,10 +111,15 @@ int ensure_ws(b200_ctx* ctx, size_t bytes) {
 
 int ensure_meta(b200_ctx* ctx, int n) {
   if (n <= ctx->meta_cap) return B200_OK;
-  if (ctx->d_off) { cudaDeviceSynchronize(); cudaFree(ctx->d_off); cudaFree(ctx->d_valid); }
+  if (ctx->d_off) {
+    cudaDeviceSynchronize();
+    cudaFree(ctx->d_off); cudaFree(ctx->d_valid); cudaFree(ctx->d_frame0); cudaFree(ctx->d_runs);
+  }
   const int cap = n + 1024;
   B200_CUDA_OK(cudaMalloc((void**)&ctx->d_off, sizeof(long long) * cap));
   B200_CUDA_OK(cudaMalloc((void**)&ctx->d_valid, sizeof(int) * cap));
+  B200_CUDA_OK(cudaMalloc((void**)&ctx->d_frame0, sizeof(int) * cap));
+  B200_CUDA_OK(cudaMalloc((void**)&ctx->d_runs, sizeof(b200::FbankRun) * cap));
   ctx->meta_cap = cap;
   return B200_OK;
 }
@@ -122,6 +132,60 @@ int push_meta(b200_ctx* ctx, const int64_t* off, const int32_t* valid, int n, cu
                "chunk %d: offset %lld / valid %d out of range", i, (long long)off[i], (int)valid[i]);
   B200_CUDA_OK(cudaMemcpyAsync(ctx->d_off, off, sizeof(long long) * n, cudaMemcpyHostToDevice, st));
   B200_CUDA_OK(cudaMemcpyAsync(ctx->d_valid, valid, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  return B200_OK;
+}
+
+// fbank plan of a list of chunks processed in sub-batches of nbmax (emb.cuh: FbankRun): per sub-batch the runs
+// [run_base[s], run_base[s + 1]) and the number of fbank rows; frame0 / runs go to the device with the chunk table.
+// share = 0 (and every short or unaligned chunk): one private run per chunk, row0 = b * 998.
+struct FbankPlan {
+  std::vector<int> run_base, nrows;
+};
+void plan_fbank(const int64_t* off, const int32_t* valid, int n, int nbmax, bool share,
+                std::vector<b200::FbankRun>* runs_out, std::vector<int>* frame0_out, FbankPlan* plan) {
+  constexpr int kHop = 160;
+  std::vector<b200::FbankRun>& runs = *runs_out;
+  std::vector<int>& frame0 = *frame0_out;
+  runs.clear();
+  runs.reserve((size_t)n);
+  frame0.assign((size_t)n, 0);
+  plan->run_base.clear();
+  plan->nrows.clear();
+  for (int c0 = 0; c0 < n; c0 += nbmax) {
+    const int nb = (n - c0) < nbmax ? (n - c0) : nbmax;
+    plan->run_base.push_back((int)runs.size());
+    int rows = 0, run_rows = 0;
+    bool open = false;                                       // the last run is made of full chunks and may be extended
+    for (int b = 0; b < nb; ++b) {
+      const long long o = off[c0 + b];
+      const bool full = share && valid[c0 + b] == kChunk;
+      if (full && open) {
+        const long long d = o - runs.back().src;
+        if (d >= 0 && d % kHop == 0 && d / kHop <= run_rows) {
+          const int f0 = (int)(d / kHop);
+          frame0[c0 + b] = runs.back().row0 + f0;
+          if (f0 + kFbankFrames > run_rows) { rows += f0 + kFbankFrames - run_rows; run_rows = f0 + kFbankFrames; }
+          continue;
+        }
+      }
+      runs.push_back(b200::FbankRun{o, rows, full ? INT_MAX : (int)valid[c0 + b]});
+      frame0[c0 + b] = rows;
+      rows += kFbankFrames;
+      run_rows = kFbankFrames;
+      open = full;
+    }
+    plan->nrows.push_back(rows);
+  }
+  plan->run_base.push_back((int)runs.size());
+}
+
+int push_fbank_plan(b200_ctx* ctx, const int64_t* off, const int32_t* valid, int n, int nbmax, bool share,
+                    FbankPlan* plan, cudaStream_t st) {
+  std::vector<b200::FbankRun> runs;
+  std::vector<int> frame0;
+  plan_fbank(off, valid, n, nbmax, share, &runs, &frame0, plan);
+  B200_CUDA_OK(cudaMemcpyAsync(ctx->d_frame0, frame0.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  B200_CUDA_OK(cudaMemcpyAsync(ctx->d_runs, runs.data(), sizeof(b200::FbankRun) * runs.size(), cudaMemcpyHostToDevice, st));
   return B200_OK;
 }
 
@@ -243,6 +307,8 @@ int b200_ctx_destroy(b200_ctx* ctx) {
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->d_off) cudaFree(ctx->d_off);
   if (ctx->d_valid) cudaFree(ctx->d_valid);
+  if (ctx->d_frame0) cudaFree(ctx->d_frame0);
+  if (ctx->d_runs) cudaFree(ctx->d_runs);
   delete ctx;
   return B200_OK;
 }
@@ -261,6 +327,7 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value) {
   else if (k == "conv_ghost") ctx->conv_ghost = (int)value;
   else if (k == "conv_fold") ctx->conv_fold = (int)value;
   else if (k == "conv_scfold") ctx->conv_scfold = (int)value;
+  else if (k == "fbank_share") ctx->fbank_share = (int)value;
   else B200_CHECK(false, B200_ERR_INVALID, "unknown option '%s'", key);
   B200_CHECK(ctx->seg_max_batch >= 1 && ctx->emb_max_batch >= 1 && ctx->conv_impl >= 0 && ctx->conv_impl <= 8,
              B200_ERR_INVALID, "option '%s' value %lld out of range", key, (long long)value);
@@ -696,7 +763,8 @@ static int block_run(b200_ctx* ctx, const BlockWeights& B, __half* A, __half* Bf
 }
 
 // conv1 + 16 BasicBlocks; returns the buffer holding the result (NHWC fp16 [nb][10][125][256])
-static int trunk_run(b200_ctx* ctx, const EmbWs& w, int nb, cudaStream_t st, const __half** result) {
+static int trunk_run(b200_ctx* ctx, const EmbWs& w, const int* frame0, int nb, cudaStream_t st,
+                     const __half** result) {
   const EmbWeights& E = ctx->emb;
   int rc;
   int H = kMel, Wd = kFbankFrames;
@@ -705,7 +773,7 @@ static int trunk_run(b200_ctx* ctx, const EmbWs& w, int nb, cudaStream_t st, con
   __half* cur = w.A;            // current activation; the other two buffers are scratch
   __half* s1 = w.Bf;
   __half* s2 = w.Cf;
-  if ((rc = conv1_forward(w.fbank, w.fmean, E.conv1_w, E.conv1_b, cur, nb, st))) return rc;
+  if ((rc = conv1_forward(w.fbank, w.fmean, frame0, E.conv1_w, E.conv1_b, cur, nb, st))) return rc;
   ctx->launches += 1;
   for (const BlockWeights& B : E.blocks) {
     const int s = B.conv1.stride;
@@ -765,6 +833,8 @@ static int emb_forward_impl(b200_ctx* ctx, const float* wav, const int64_t* chun
   int rc = ensure_ws(ctx, sub_bytes + 2 * split_bytes + 4096);
   if (rc) return rc;
   if ((rc = push_meta(ctx, chunk_off, chunk_valid, num_chunks, st))) return rc;
+  FbankPlan plan;
+  if ((rc = push_fbank_plan(ctx, chunk_off, chunk_valid, num_chunks, nbmax, ctx->fbank_share != 0, &plan, st))) return rc;
   EmbWs w;
   carve_emb(nbmax, ctx->ws, &w);
   __half* st_hi = reinterpret_cast<__half*>(reinterpret_cast<char*>(ctx->ws) + sub_bytes);
@@ -772,11 +842,14 @@ static int emb_forward_impl(b200_ctx* ctx, const float* wav, const int64_t* chun
   const __half* feat = nullptr;
   for (int c0 = 0; c0 < num_chunks; c0 += nbmax) {
     const int nb = (num_chunks - c0) < nbmax ? (num_chunks - c0) : nbmax;
-    if ((rc = fbank_forward(ctx->emb, wav, ctx->d_off + c0, ctx->d_valid + c0, nb, w.fbank, w.fmean, st))) return rc;
+    const int sb = c0 / nbmax;
+    if ((rc = fbank_forward(ctx->emb, wav, ctx->d_runs + plan.run_base[sb], plan.run_base[sb + 1] - plan.run_base[sb],
+                            plan.nrows[sb], ctx->d_frame0 + c0, nb, w.fbank, w.fmean, st)))
+      return rc;
     ctx->launches += 2;
     {
       ScopedTimer timer(ctx, &ctx->trunk_events, st);
-      if ((rc = trunk_run(ctx, w, nb, st, &feat))) return rc;
+      if ((rc = trunk_run(ctx, w, ctx->d_frame0 + c0, nb, st, &feat))) return rc;
     }
     if (ctx->profile) ctx->trunk_segments += nb;
     const size_t o = (size_t)c0 * kSpeakers * 2 * kStatsDim;
@@ -803,10 +876,28 @@ int b200_emb_fbank(b200_ctx* ctx, const float* wav, const int64_t* chunk_off, co
   int rc = ensure_ws(ctx, (size_t)num_chunks * kMel * sizeof(float) + 4096);
   if (rc) return rc;
   if ((rc = push_meta(ctx, chunk_off, chunk_valid, num_chunks, st))) return rc;
+  FbankPlan plan;                                            // output layout [B][998][80]: one private run per chunk
+  if ((rc = push_fbank_plan(ctx, chunk_off, chunk_valid, num_chunks, num_chunks, false, &plan, st))) return rc;
   float* fmean = reinterpret_cast<float*>(ctx->ws);
-  if ((rc = fbank_forward(ctx->emb, wav, ctx->d_off, ctx->d_valid, num_chunks, fbank, fmean, st))) return rc;
+  if ((rc = fbank_forward(ctx->emb, wav, ctx->d_runs, num_chunks, plan.nrows[0], ctx->d_frame0, num_chunks, fbank, fmean,
+                          st)))
+    return rc;
   ctx->launches += 3;
   return fbank_center(fbank, fmean, num_chunks, st);
+}
+
+int64_t b200_emb_fbank_plan(const int64_t* chunk_off, const int32_t* chunk_valid, int32_t num_chunks, int32_t sub_batch,
+                            int32_t share, int32_t* frame0, int32_t* rows_per_sub_batch) {
+  if (!chunk_off || !chunk_valid || num_chunks < 0 || sub_batch < 1) return -1;
+  for (int i = 0; i < num_chunks; ++i)
+    if (chunk_valid[i] < 0 || chunk_valid[i] > kChunk || chunk_off[i] < 0) return -1;
+  std::vector<b200::FbankRun> runs;
+  std::vector<int> f0;
+  FbankPlan plan;
+  plan_fbank(chunk_off, chunk_valid, num_chunks, sub_batch, share != 0, &runs, &f0, &plan);
+  if (frame0) std::copy(f0.begin(), f0.end(), frame0);
+  if (rows_per_sub_batch) std::copy(plan.nrows.begin(), plan.nrows.end(), rows_per_sub_batch);
+  return (int64_t)runs.size();
 }
 
 int b200_emb_trunk(b200_ctx* ctx, const float* fbank, int32_t num_chunks, float* frames, void* stream) {
@@ -826,7 +917,7 @@ int b200_emb_trunk(b200_ctx* ctx, const float* fbank, int32_t num_chunks, float*
                                  (size_t)nb * kFbankFrames * kMel * sizeof(float), cudaMemcpyDeviceToDevice, st));
     B200_CUDA_OK(cudaMemsetAsync(w.fmean, 0, (size_t)nb * kMel * sizeof(float), st));
     const __half* feat = nullptr;
-    if ((rc = trunk_run(ctx, w, nb, st, &feat))) return rc;
+    if ((rc = trunk_run(ctx, w, nullptr, nb, st, &feat))) return rc;
     if ((rc = frames_to_nchw(feat, frames + (size_t)c0 * 256 * 10 * kEmbT, nb, st))) return rc;
     ctx->launches += 1;
   }

@@ -63,12 +63,24 @@ int conv_s2_shortcut_forward(const ConvLayer& L, const __half* in, __half* out, 
 // fused BasicBlock of layer1 (two 32->32 stride-1 convs + identity shortcut), out must not alias in
 int conv_block32_forward(const ConvLayer& L1, const ConvLayer& L2, const __half* in, __half* out, int B, int H, int W,
                          int num_sms, cudaStream_t stream, int ghost = 1);
-int conv1_forward(const float* fbank, const float* fmean, const float* w, const float* bias, __half* out, int B,
-                  cudaStream_t stream);
+// frame0 (device, [B], may be NULL = b * 998): first fbank row of each segment, see fbank_forward
+int conv1_forward(const float* fbank, const float* fmean, const int* frame0, const float* w, const float* bias,
+                  __half* out, int B, cudaStream_t stream);
 
-// fbank: wav chunks (device waveform, chunk c starts at c*step, zero padded past num_samples) -> [B][998][80] fp32
-int fbank_forward(const EmbWeights& W, const float* wav, const long long* chunk_off, const int* chunk_valid, int B,
-                  float* fbank, float* fmean, cudaStream_t stream);
+// fbank with SHARED FRAMES.  The sliding chunks of a file overlap by 90 % and a chunk step of 16000 samples is exactly
+// 100 frame hops, so frame k of chunk c IS frame k - 100 of chunk c + 1: the same 400 samples through the same
+// arithmetic.  The host groups a sub-batch's chunks into runs of hop-aligned, overlapping full chunks; a run's frames
+// are computed once into consecutive rows of `fbank` ([nrows][80] fp32) and segment b reads rows
+// frame0[b] .. frame0[b] + 997 (conv1_forward, the per-segment mean).  Chunks that are short (valid < 160000: samples
+// past `limit` read as zero) or not hop-aligned get a private run, which is also the layout of the public
+// b200_emb_fbank ([B][998][80]).  Bit-identical to one private run per chunk; 10x fewer frames on a pipeline batch.
+struct FbankRun {
+  long long src;   // sample offset of the run's first frame in `wav`
+  int row0;        // first row of the run in `fbank`
+  int limit;       // valid samples counted from src (INT_MAX for runs of full chunks)
+};
+int fbank_forward(const EmbWeights& W, const float* wav, const FbankRun* runs, int nruns, int nrows,
+                  const int* frame0, int B, float* fbank, float* fmean, cudaStream_t stream);
 int fbank_center(float* fbank, const float* fmean, int B, cudaStream_t stream);
 // NHWC fp16 [B][10][125][256] -> NCHW fp32 [B][256][10][125]
 int frames_to_nchw(const __half* feat, float* out, int B, cudaStream_t stream);

@@ -1604,19 +1604,20 @@ __global__ void conv_simt_kernel(const __half* __restrict__ in, const __half* __
 // then thread = time frame walks the 80 frequency rows so that every warp store is 32 x 64 B contiguous.
 constexpr int kC1Tile = 128;
 __global__ void __launch_bounds__(kC1Tile) conv1_kernel(const float* __restrict__ fbank, const float* __restrict__ fmean,
-                             const float* __restrict__ w /*[32][9] folded*/, const float* __restrict__ bias /*[32]*/,
+                             const int* __restrict__ frame0, const float* __restrict__ w /*[32][9] folded*/, const float* __restrict__ bias /*[32]*/,
                              __half* __restrict__ out, int B) {
   __shared__ __align__(16) float sw[9 * 32];               // [tap][channel]: one LDS.128 = 4 channels of a tap
   __shared__ __align__(16) float sb[32];
   __shared__ float sx[(kC1Tile + 2) * (kMel + 1)];        // [t][f], +1 padding against bank conflicts
   const int b = blockIdx.y, t0 = blockIdx.x * kC1Tile;
+  const size_t r0 = frame0 ? (size_t)frame0[b] : (size_t)b * kFbankFrames;     // first fbank row of this segment
   for (int i = threadIdx.x; i < 288; i += blockDim.x) sw[(i % 9) * 32 + i / 9] = w[i];
   if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
   for (int i = threadIdx.x; i < (kC1Tile + 2) * kMel; i += blockDim.x) {
     const int tt = i / kMel, f = i - tt * kMel;
     const int t = t0 - 1 + tt;
     float v = 0.f;
-    if (t >= 0 && t < kFbankFrames) v = fbank[((size_t)b * kFbankFrames + t) * kMel + f] - fmean[b * kMel + f];
+    if (t >= 0 && t < kFbankFrames) v = fbank[(r0 + t) * kMel + f] - fmean[b * kMel + f];
     sx[tt * (kMel + 1) + f] = v;
   }
   __syncthreads();
@@ -2138,10 +2139,10 @@ int conv_forward(const ConvLayer& L, const __half* in, const __half* residual, _
   return B200_OK;
 }
 
-int conv1_forward(const float* fbank, const float* fmean, const float* w, const float* bias, __half* out, int B,
-                  cudaStream_t stream) {
+int conv1_forward(const float* fbank, const float* fmean, const int* frame0, const float* w, const float* bias,
+                  __half* out, int B, cudaStream_t stream) {
   dim3 grid(ceil_div(kFbankFrames, kC1Tile), B);
-  conv1_kernel<<<grid, kC1Tile, 0, stream>>>(fbank, fmean, w, bias, out, B);
+  conv1_kernel<<<grid, kC1Tile, 0, stream>>>(fbank, fmean, frame0, w, bias, out, B);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }

@@ -55,8 +55,7 @@ __device__ __forceinline__ void fft16_stages(float (&xr)[16], float (&xi)[16], T
 // frame B in [256, 512), half a warp each.  Same arithmetic per butterfly, less than half of it per frame
 // (the padded imaginary half of the old complex transform was all zeros): 663 -> see profiles/ us per 256 segments.
 __global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wav,
-                                                    const long long* __restrict__ chunk_off,
-                                                    const int* __restrict__ chunk_valid,
+                                                    const FbankRun* __restrict__ runs, int nruns, int nrows,
                                                     const float* __restrict__ window,
                                                     const float* __restrict__ twiddle, const float* __restrict__ mel_w,
                                                     const int* __restrict__ mel_start, const int* __restrict__ mel_len,
@@ -64,19 +63,34 @@ __global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wa
   __shared__ float s_re[8][kFftPad];
   __shared__ float s_im[8][kFftPad];
   __shared__ float s_tw[256][2];
+  __shared__ long long s_src[16];                           // first sample of each of this block's 16 frame rows
+  __shared__ int s_lim[16];                                 // samples of the run still valid from there
   for (int i = threadIdx.x; i < 512; i += blockDim.x) (&s_tw[0][0])[i] = twiddle[i];
+  if (threadIdx.x < 16) {
+    // row -> run: last run whose first row is <= row (runs are sorted by row0, rows of a run are hop-spaced frames)
+    int row = blockIdx.x * 16 + threadIdx.x;
+    if (row >= nrows) row = nrows - 1;
+    int lo = 0, hi = nruns - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (runs[mid].row0 <= row) lo = mid; else hi = mid - 1;
+    }
+    const FbankRun r = runs[lo];
+    const int local = row - r.row0;
+    s_src[threadIdx.x] = r.src + (long long)local * kFrameHop;
+    const long long left = (long long)r.limit - (long long)local * kFrameHop;
+    s_lim[threadIdx.x] = left < 0 ? 0 : (left > kFrameLen ? kFrameLen : (int)left);
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int l = lane & 15, f = lane >> 4;                  // half-warp f owns frame 2 * pair + f
+  const int l = lane & 15, f = lane >> 4;                  // half-warp f owns frame row 2 * pair + f
   const int pair = blockIdx.x * 8 + warp;
-  const int b = blockIdx.y;
-  if (2 * pair >= kFbankFrames) return;                    // warp-uniform (kFbankFrames is even)
-  const int frame = 2 * pair + f;
+  if (2 * pair >= nrows) return;                           // warp-uniform
+  const int row = 2 * pair + f;                            // row == nrows (odd tail): computed on a clamped source, not stored
   float* re = s_re[warp];
   float* im = s_im[warp];
-  const float* xw = wav + chunk_off[b];
-  const int valid = chunk_valid[b];
-  const int base = frame * kFrameHop;
+  const float* xw = wav + s_src[2 * warp + f];
+  const int valid = s_lim[2 * warp + f];
   const int h0 = f << 8;                                   // this frame's half of the arrays
 
   // load + scale, frame mean (sample i = l + 16 j)
@@ -84,7 +98,7 @@ __global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wa
   float sum = 0.f;
 #pragma unroll
   for (int j = 0; j < 25; ++j) {
-    const int g = base + l + 16 * j;
+    const int g = l + 16 * j;                              // sample of the frame; xw already points at the frame
     const float v = (g < valid) ? xw[g] * 32768.0f : 0.f;
     x[j] = v;
     sum += v;
@@ -161,16 +175,18 @@ __global__ void __launch_bounds__(256) fbank_kernel(const float* __restrict__ wa
     const int st = mel_start[m], ln = mel_len[m], off = mel_off[m];
     float acc = 0.f;
     for (int i = 0; i < ln; ++i) acc = fmaf(re[h0 + st + i], mel_w[off + i], acc);
-    out[((size_t)b * kFbankFrames + frame) * kMel + m] = logf(fmaxf(acc, kEps));
+    if (row < nrows) out[(size_t)row * kMel + m] = logf(fmaxf(acc, kEps));
   }
 }
 
-__global__ void __launch_bounds__(640) fbank_mean_kernel(const float* __restrict__ fb, float* __restrict__ fmean) {
+__global__ void __launch_bounds__(640) fbank_mean_kernel(const float* __restrict__ fb, const int* __restrict__ frame0,
+                                                         float* __restrict__ fmean) {
   // 8 groups of 80 threads each sum an eighth of the frames in fp64, combined in group order
   __shared__ double part[8][kMel];
   const int b = blockIdx.x, m = threadIdx.x % kMel, g = threadIdx.x / kMel;
+  const size_t r0 = frame0 ? (size_t)frame0[b] : (size_t)b * kFbankFrames;
   double s = 0.0;
-  for (int t = g; t < kFbankFrames; t += 8) s += (double)fb[((size_t)b * kFbankFrames + t) * kMel + m];
+  for (int t = g; t < kFbankFrames; t += 8) s += (double)fb[(r0 + t) * kMel + m];
   part[g][m] = s;
   __syncthreads();
   if (g == 0) {
@@ -213,13 +229,13 @@ int frames_to_nchw(const __half* feat, float* out, int B, cudaStream_t stream) {
   return B200_OK;
 }
 
-int fbank_forward(const EmbWeights& W, const float* wav, const long long* chunk_off, const int* chunk_valid, int B,
-                  float* fbank, float* fmean, cudaStream_t stream) {
-  dim3 grid(ceil_div(kFbankFrames, 16), B);                 // 8 warps x 2 frames per block
-  fbank_kernel<<<grid, 256, 0, stream>>>(wav, chunk_off, chunk_valid, W.window, W.twiddle, W.mel_w, W.mel_start,
+int fbank_forward(const EmbWeights& W, const float* wav, const FbankRun* runs, int nruns, int nrows,
+                  const int* frame0, int B, float* fbank, float* fmean, cudaStream_t stream) {
+  const unsigned grid = (unsigned)ceil_div(nrows, 16);      // 8 warps x 2 frame rows per block
+  fbank_kernel<<<grid, 256, 0, stream>>>(wav, runs, nruns, nrows, W.window, W.twiddle, W.mel_w, W.mel_start,
                                          W.mel_len, W.mel_off, fbank);
   B200_CUDA_OK(cudaGetLastError());
-  fbank_mean_kernel<<<B, 640, 0, stream>>>(fbank, fmean);
+  fbank_mean_kernel<<<B, 640, 0, stream>>>(fbank, frame0, fmean);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }

@@ -77,6 +77,13 @@ class Context:
         self.seg_loaded = False
         self.emb_loaded = False
         self.owners = {}          # slot ("seg" | "emb") -> stamp of the model whose weights are resident (models.py)
+        # A/B knob for scripts (same role as the B200_* variables the library reads): B200_OPTIONS="key=value,..."
+        # is applied through b200_ctx_set_option, so unknown keys / bad values fail loudly
+        import os
+
+        for kv in filter(None, os.environ.get("B200_OPTIONS", "").split(",")):
+            key, value = kv.split("=")
+            self.set_option(key.strip(), int(value))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -216,6 +216,21 @@ def test_embedding_parity(ctx, dev, oracle_models):
     da = 1 - (a @ a.T) / np.outer(np.linalg.norm(a, axis=1), np.linalg.norm(a, axis=1))
     db = 1 - (b @ b.T) / np.outer(np.linalg.norm(b, axis=1), np.linalg.norm(b, axis=1))
     assert np.abs(da - db).max() <= 1e-3
+    # shared fbank frames (default: overlapping hop-aligned full chunks compute their common frames once) against one
+    # private run of 998 frames per chunk: the same samples through the same arithmetic -> bit-identical embeddings.
+    # The list mixes full chunks, the short last chunk, an unaligned chunk and a repeated one, in two sub-batches.
+    off2 = np.concatenate([off, [int(off[0]) + 37, int(off[1])]]).astype(np.int64)
+    valid2 = np.concatenate([valid, [160000, 160000]]).astype(np.int32)
+    masks2 = torch.from_numpy(np.concatenate([masks, masks[:2]])).to(dev)
+    ctx.set_option("emb_max_batch", 4)
+    shared = ctx.emb_forward(buf, off2, valid2, masks2).cpu().numpy()
+    ctx.set_option("fbank_share", 0)
+    private = ctx.emb_forward(buf, off2, valid2, masks2).cpu().numpy()
+    ctx.set_option("fbank_share", 1)
+    ctx.set_option("emb_max_batch", 256)
+    assert np.array_equal(shared, private)
+    np.testing.assert_allclose(shared[:n], emb, atol=1e-5, rtol=1e-5)     # other sub-batch split, same segments
+    np.testing.assert_allclose(shared[n + 1], shared[1], atol=1e-5, rtol=1e-5)   # a repeated chunk: its own run
 
 
 def test_post_processing_bit_exact(ctx, dev):
