@@ -229,15 +229,17 @@ def eager_cuda_baseline(args, dev, chunks=64):
 
 
 def trunk_traffic():
-    """DRAM bytes of one 256-segment trunk pass from the newest committed ncu capture (profiles/*_trunk_traffic.json,
-    produced by scripts/ncu_trunk_traffic.py from an `ncu --metrics dram__bytes_*` launch list)."""
+    """(DRAM bytes, segments, file) of one trunk pass over an embedding sub-batch from the newest committed ncu
+    capture (profiles/*_trunk_traffic.json, produced by scripts/ncu_trunk_traffic.py from an
+    `ncu --metrics dram__bytes_*` launch list)."""
     import glob
 
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_trunk_traffic.json")))
     if not files:
-        return None, None
+        return None, None, None
     d = json.load(open(files[-1]))
-    return d.get("dram_bytes_per_256_segments"), os.path.basename(files[-1])
+    return (d.get("dram_bytes_per_pass", d.get("dram_bytes_per_256_segments")), int(d.get("segments", 256)),
+            os.path.basename(files[-1]))
 
 
 def main():
@@ -361,13 +363,15 @@ def main():
     pk = peaks()
     peak = pk.get("bf16_tflops_sustained", 1400.0)
     achieved = trunk_segments * TRUNK_FLOP_PER_SEGMENT / (trunk_ms / 1e3) / 1e12 if trunk_ms > 0 else 0.0
-    traffic, traffic_src = trunk_traffic()
+    traffic, traffic_segments, traffic_src = trunk_traffic()
+    sub_batch = traffic_segments or 296                    # segments of the launch unit (one embedding sub-batch)
     roofline = {"bound": "tensor",
-                "kernel": "ResNet34 trunk = stem + tcgen05 conv kernels, one dependent chain per 256-segment sub-batch",
+                "kernel": "ResNet34 trunk = stem + tcgen05 conv kernels, one dependent chain per embedding sub-batch "
+                          "(296 segments in the library, the launch unit below is the captured one)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "traffic": traffic, "traffic_unit": "bytes per 256-segment trunk pass (ncu dram read+write)",
+                "traffic": traffic, "traffic_unit": f"bytes per {sub_batch}-segment trunk pass (ncu dram read+write)",
                 "traffic_source": traffic_src,
-                "algorithmic_flop_per_launch_unit": 256 * TRUNK_FLOP_PER_SEGMENT,
+                "algorithmic_flop_per_launch_unit": sub_batch * TRUNK_FLOP_PER_SEGMENT,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (fp16 = same tensor rate)"
                 if pk else "fallback 1.4 PFLOP/s sustained",
                 "trunk_ms_per_step": trunk_ms / args.steps, "seg_ms_per_step": seg_ms / args.steps}

@@ -26,7 +26,10 @@ struct b200_ctx {
   int conv_scfold = 1;     // 1 = layer2.0: the 1x1 stride-2 shortcut rides in the padded weight rows of the stride-2 conv
   int conv_impl = 8;   // channels-as-M conv for C_out >= 128, strip-streaming conv for the narrow stride-1 3x3, per-tap conv otherwise
   int seg_max_batch = 4736;     // chunks per segmentation sub-batch (37 LSTM tiles of 128 sequences x 2 directions = 74 clusters)
-  int emb_max_batch = 256;      // chunks per embedding sub-batch
+  // chunks per embedding sub-batch.  296 = 2 x 148: the persistent conv kernels stride their items over 148 CTAs and
+  // every layer's item count is a multiple of the sub-batch (8 / 4 strips, 20 / 10 pixel tiles per segment), so all
+  // CTAs get the same number of items (256 left the last wave 61-92 % full: 516 -> 511 ms per bench step)
+  int emb_max_batch = 296;
   int fbank_share = 1;          // 1 = overlapping hop-aligned chunks share their fbank frames (emb.cuh: FbankRun)
   int64_t launches = 0;
   SegWeights seg;

@@ -339,22 +339,41 @@ class Context:
     def frame_transitions(self, discrete: torch.Tensor, cap: int = 4096):
         """discrete (F, K) u8 on the device -> sorted flat event indices k * (F + 1) + f of onsets and offsets
         (host int64 arrays).  One kernel + one 32 KB D2H instead of shipping and scanning the whole matrix."""
-        F, K = int(discrete.shape[0]), int(discrete.shape[1])
-        d = discrete.contiguous()
-        while True:
-            buf = torch.empty((2 + 2 * cap,), dtype=torch.int32, device=self.device)
-            with torch.cuda.device(self.device):
-                _lib.check(self.lib.b200_frame_transitions(self._h, _ptr(d), F, K, cap, _ptr(buf),
-                                                           _stream(self.device)))
-            host = buf.cpu().numpy()
-            n_on, n_off = int(host[0]), int(host[1])
-            if max(n_on, n_off) <= cap:
-                break
-            cap = 1 << int(max(n_on, n_off) - 1).bit_length()
+        return self.frame_transitions_many([discrete], cap)[0]
+
+    def frame_transitions_many(self, matrices: Sequence[torch.Tensor], cap: int = 4096):
+        """frame_transitions of several (F_i, K_i) matrices with ONE device -> host copy (and one synchronisation)
+        for all of them: every matrix gets a row [n_on, n_off, on[cap], off[cap]] of one int32 buffer.  A row whose
+        event count exceeds ``cap`` is redone alone with a larger buffer."""
+        m = len(matrices)
+        self.last_transfer_bytes = 0
+        if m == 0:
+            return []
+        mats = [d.contiguous() for d in matrices]
+        buf = torch.empty((m, 2 + 2 * cap), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            for i, d in enumerate(mats):
+                _lib.check(self.lib.b200_frame_transitions(self._h, _ptr(d), int(d.shape[0]), int(d.shape[1]), cap,
+                                                           _ptr(buf[i]), _stream(self.device)))
+        host = buf.cpu().numpy()
         self.last_transfer_bytes = host.nbytes
-        on = np.sort(host[2: 2 + n_on].astype(np.int64))
-        off = np.sort(host[2 + cap: 2 + cap + n_off].astype(np.int64))
-        return on, off
+        out = []
+        for i, d in enumerate(mats):
+            row, c = host[i], cap
+            n_on, n_off = int(row[0]), int(row[1])
+            while max(n_on, n_off) > c:                       # rare: more events than slots -> this matrix again
+                c = 1 << int(max(n_on, n_off) - 1).bit_length()
+                big = torch.empty((2 + 2 * c,), dtype=torch.int32, device=self.device)
+                with torch.cuda.device(self.device):
+                    _lib.check(self.lib.b200_frame_transitions(self._h, _ptr(d), int(d.shape[0]), int(d.shape[1]), c,
+                                                               _ptr(big), _stream(self.device)))
+                row = big.cpu().numpy()
+                self.last_transfer_bytes += row.nbytes
+                n_on, n_off = int(row[0]), int(row[1])
+            on = np.sort(row[2: 2 + n_on].astype(np.int64))
+            off = np.sort(row[2 + c: 2 + c + n_off].astype(np.int64))
+            out.append((on, off))
+        return out
 
     # ---- audio ingest ------------------------------------------------------------------------------
     def audio_ingest(self, pcm: torch.Tensor, sample_rate: int, target_rate: Optional[int] = None,

@@ -479,6 +479,24 @@ class SpeakerDiarization:
             import cProfile
             _prof = cProfile.Profile()
             _prof.enable()
+        # run-length encoding: onsets / offsets are found on the device and only those events cross PCIe, in ONE
+        # device -> host copy for all files (plus one for the centroids); the full (frames, clusters) matrices are
+        # materialised on the host only for hooks / artifacts that look at them
+        _t0 = time.perf_counter()
+        live = [fi for fi in range(F) if not silent[fi]]
+        events = ctx.frame_transitions_many([m for fi in live for m in pending[fi][:2]])
+        self.d2h_bytes += ctx.last_transfer_bytes
+        cents_host = {}
+        if live:
+            allc = torch.cat([pending[fi][3].reshape(-1, pending[fi][3].shape[-1]) for fi in live]).cpu().numpy()
+            self.d2h_bytes += allc.nbytes + 8 * len(live)
+            pos = 0
+            for fi in live:
+                k = int(pending[fi][3].shape[0])
+                cents_host[fi] = allc[pos: pos + k]
+                pos += k
+        events = {fi: (events[2 * i], events[2 * i + 1]) for i, fi in enumerate(live)}
+        d2h_s += time.perf_counter() - _t0
         for fi, file in enumerate(files):
             uri = file.get("uri", None)
             artifacts = None
@@ -495,16 +513,8 @@ class SpeakerDiarization:
                 continue
             discrete, exclusive, hard, centroids, K = pending[fi]
             _, nF, fr = grids[fi]
-            _t0 = time.perf_counter()
-            # run-length encoding: onsets / offsets are found on the device, only those events cross PCIe; the full
-            # (frames, clusters) matrices are materialised on the host only for hooks / artifacts that look at them
-            ev_d = ctx.frame_transitions(discrete)
-            self.d2h_bytes += ctx.last_transfer_bytes
-            ev_x = ctx.frame_transitions(exclusive)
-            self.d2h_bytes += ctx.last_transfer_bytes
-            centroids = centroids.cpu().numpy()
-            self.d2h_bytes += centroids.nbytes + 8
-            d2h_s += time.perf_counter() - _t0
+            ev_d, ev_x = events[fi]
+            centroids = cents_host[fi]
             cmax = int(count_max[fi]) if not np.isfinite(max_speakers) else min(int(count_max[fi]), int(max_speakers))
             kd, kx = max(K, cmax), max(K, min(cmax, 1))
             if K < min_speakers or K > max_speakers:

@@ -1,6 +1,7 @@
 """Aggregates an `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv` launch list of
-`scripts/prof_emb.py emb 256` (two passes; the second is used) into profiles/rNN_trunk_traffic.json, which bench.py
-reads for `roofline.traffic`.   Usage: python scripts/ncu_trunk_traffic.py launches.csv out.json"""
+`scripts/prof_emb.py emb N` (N = one embedding sub-batch, 296 by default; two passes, the second is used) into
+profiles/rNN_trunk_traffic.json, which bench.py reads for `roofline.traffic`.
+Usage: python scripts/ncu_trunk_traffic.py launches.csv out.json [segments]"""
 import collections
 import csv
 import json
@@ -12,7 +13,7 @@ TRUNK = ("conv1_kernel", "conv_block32_kernel", "conv_block64_kernel", "conv_tc_
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
 
 
-def main(src, dst):
+def main(src, dst, segments=296):
     rows = list(csv.reader(open(src)))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     ix = {h: i for i, h in enumerate(rows[hi])}
@@ -31,12 +32,12 @@ def main(src, dst):
         a["dram_read_gb"] += d["dram__bytes_read.sum"] / 1e9
         a["dram_write_gb"] += d["dram__bytes_write.sum"] / 1e9
     total = sum(a["dram_read_gb"] + a["dram_write_gb"] for a in agg.values()) * 1e9
-    out = {"source": src, "segments": 256, "launches_per_pass": len(half),
-           "ms_per_pass_under_ncu": sum(a["ms"] for a in agg.values()), "dram_bytes_per_256_segments": total,
+    out = {"source": src, "segments": segments, "launches_per_pass": len(half),
+           "ms_per_pass_under_ncu": sum(a["ms"] for a in agg.values()), "dram_bytes_per_pass": total,
            "per_kernel": agg}
     json.dump(out, open(dst, "w"), indent=1)
     print(json.dumps(out, indent=1))
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 296)

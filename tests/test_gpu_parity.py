@@ -227,7 +227,7 @@ def test_embedding_parity(ctx, dev, oracle_models):
     ctx.set_option("fbank_share", 0)
     private = ctx.emb_forward(buf, off2, valid2, masks2).cpu().numpy()
     ctx.set_option("fbank_share", 1)
-    ctx.set_option("emb_max_batch", 256)
+    ctx.set_option("emb_max_batch", 296)                   # the library default
     assert np.array_equal(shared, private)
     np.testing.assert_allclose(shared[:n], emb, atol=1e-5, rtol=1e-5)     # other sub-batch split, same segments
     np.testing.assert_allclose(shared[n + 1], shared[1], atol=1e-5, rtol=1e-5)   # a repeated chunk: its own run
