@@ -266,15 +266,22 @@ class VBxClustering(BaseClustering):
         gamma, pi, _ = ctx.vbx_batched(fea, phi, gamma0, n_list, S_list, self.Fa, self.Fb, max_iters=20)
         pi_host = pi.cpu().numpy()                                                                 # sync
         tick("vbx")
-        gpos = spos = rpos = 0
-        for f, n, S in zip(todo, n_list, S_list):
+        # speakers that survive VBx (clustering.py:619: sp > 1e-7), for all files in ONE host -> device copy
+        kept_lists, spos = [], 0
+        for S in S_list:
+            kept_lists.append(np.nonzero(pi_host[spos: spos + S] > 1e-7)[0].astype(np.int32))
+            spos += S
+        kept_all = torch.from_numpy(np.concatenate(kept_lists)).to(dev)
+        gpos = spos = rpos = kpos = 0
+        for j, (f, n, S) in enumerate(zip(todo, n_list, S_list)):
             c0, c1 = int(bounds[f]), int(bounds[f + 1])
             q = gamma[gpos: gpos + n * S].reshape(n, S)
             sp = pi_host[spos: spos + S]
             train = x_link[rpos: rpos + n]
             gpos, spos, rpos = gpos + n * S, spos + S, rpos + n
-            kept = np.nonzero(sp > 1e-7)[0]
-            centroids = ctx.weighted_centroids(q, torch.as_tensor(kept, dtype=torch.int32), train)
+            kept = kept_all[kpos: kpos + len(kept_lists[j])]
+            kpos += len(kept_lists[j])
+            centroids = ctx.weighted_centroids(q, kept, train)
             constrained = self.constrained_assignment
             auto_num = centroids.shape[0]
             nc = num_clusters

@@ -129,22 +129,29 @@ __device__ __forceinline__ MinPair warp_min(MinPair m) {
   return m;
 }
 
-// nearest alive j > k of row k, computed by one warp (four independent loads in flight per lane)
-__device__ __forceinline__ void row_nn(const double* __restrict__ D, const unsigned char* alive, int n, int k, int lane,
-                                       double* nn_d, int* nn_i) {
+// nearest alive j > k of row k among the columns j = k + 1 + first, + stride, ...  (four independent loads in flight
+// per thread); min_pair is an order-independent (value, index) minimum, so any split of a row gives the same answer
+__device__ __forceinline__ MinPair row_nn_part(const double* __restrict__ D, const unsigned char* alive, int n, int k,
+                                               int first, int stride) {
   MinPair m{DBL_MAX, n};
   const double* row = D + (size_t)k * n;
-  int j = k + 1 + lane;
-  for (; j + 96 < n; j += 128) {
-    const double v0 = row[j], v1 = row[j + 32], v2 = row[j + 64], v3 = row[j + 96];
+  int j = k + 1 + first;
+  for (; j + 3 * stride < n; j += 4 * stride) {
+    const double v0 = row[j], v1 = row[j + stride], v2 = row[j + 2 * stride], v3 = row[j + 3 * stride];
     if (alive[j]) m = min_pair(m, MinPair{v0, j});
-    if (alive[j + 32]) m = min_pair(m, MinPair{v1, j + 32});
-    if (alive[j + 64]) m = min_pair(m, MinPair{v2, j + 64});
-    if (alive[j + 96]) m = min_pair(m, MinPair{v3, j + 96});
+    if (alive[j + stride]) m = min_pair(m, MinPair{v1, j + stride});
+    if (alive[j + 2 * stride]) m = min_pair(m, MinPair{v2, j + 2 * stride});
+    if (alive[j + 3 * stride]) m = min_pair(m, MinPair{v3, j + 3 * stride});
   }
-  for (; j < n; j += 32)
+  for (; j < n; j += stride)
     if (alive[j]) m = min_pair(m, MinPair{row[j], j});
-  m = warp_min(m);
+  return m;
+}
+
+// nearest alive j > k of row k, computed by one warp
+__device__ __forceinline__ void row_nn(const double* __restrict__ D, const unsigned char* alive, int n, int k, int lane,
+                                       double* nn_d, int* nn_i) {
+  const MinPair m = warp_min(row_nn_part(D, alive, n, k, lane, 32));
   if (lane == 0) { nn_d[k] = m.v; nn_i[k] = m.i; }
 }
 
@@ -267,10 +274,32 @@ __global__ void __launch_bounds__(1024) linkage_centroid_kernel(const LinkJob* _
       }
     }
     __syncthreads();
-    // C. rows whose candidate was x or y
+    // C. rows whose candidate was x or y are re-scanned.  Usually a handful: R rows at a time share the block's 32
+    // warps (W = 32 / R warps per row, every load of a row in flight at once) instead of one warp walking a whole
+    // row through ~n / 128 dependent round trips to L2, which was most of a merge's latency
     const int nt = s_ntodo;
     if (nt > 0) {
-      for (int t = warp; t < nt; t += 32) row_nn(D, alive, n, todo[t], lane, nn_d, nn_i);
+      int R = 1;
+      while (R < nt && R < 32) R <<= 1;                    // rows per pass, a power of two <= 32
+      const int W = 32 / R, g = warp / W, wl = warp % W;
+      for (int t0 = 0; t0 < nt; t0 += R) {
+        const int t = t0 + g;
+        const int k = t < nt ? todo[t] : -1;
+        MinPair part{DBL_MAX, n};
+        if (k >= 0) part = warp_min(row_nn_part(D, alive, n, k, wl * 32 + lane, W * 32));
+        if (W == 1) {
+          if (k >= 0 && lane == 0) { nn_d[k] = part.v; nn_i[k] = part.i; }
+        } else {
+          if (lane == 0) s_red[warp] = part;
+          __syncthreads();
+          if (wl == 0 && k >= 0) {
+            MinPair b = lane < W ? s_red[g * W + lane] : MinPair{DBL_MAX, n};
+            b = warp_min(b);
+            if (lane == 0) { nn_d[k] = b.v; nn_i[k] = b.i; }
+          }
+          __syncthreads();                                 // s_red is reused by the next pass / phase A
+        }
+      }
       __syncthreads();
     }
   }

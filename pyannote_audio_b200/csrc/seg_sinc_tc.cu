@@ -38,6 +38,7 @@ struct SincTcParams {
   float* P0;                // [NB][80][5325]
   double2* part;            // [NB][80][ntiles_part]
   int NB, tiles, num_items, ntiles_part;
+  int early_raw;            // A/B knob B200_SINC_EARLY=1: request the next tile's samples before the k-step loop (round 1)
 };
 
 __global__ void __launch_bounds__(kSTThreads, 1)
@@ -157,6 +158,7 @@ sinc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         }
       }
       asm volatile("bar.sync 2, 256;" ::: "memory");        // samples complete
+      if (p.early_raw && item + (int)gridDim.x < p.num_items) load_raw(item + (int)gridDim.x);
       for (uint32_t ks = 0; ks < 16; ++ks, ++cnt) {
         const uint32_t stage = cnt & (kSTStages - 1);
         mbar_wait(bar_bempty + 8 * stage, ((cnt / kSTStages) & 1u) ^ 1u);
@@ -188,7 +190,7 @@ sinc_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
       // outstanding memory operation of the warp, so with the global loads issued before the k-step loop (round 1) the
       // first fence of every tile sat out their DRAM latency (~1.5 us against 3.2 us of MMAs per tile: the "unexplained"
       // 2x over the MMA floor).  Here the latency falls into the slack of the 8-stage ring instead.
-      if (item + (int)gridDim.x < p.num_items) load_raw(item + (int)gridDim.x);
+      if (!p.early_raw && item + (int)gridDim.x < p.num_items) load_raw(item + (int)gridDim.x);
     }
   } else {
     // ---- epilogue: abs, MaxPool1d(3), store, InstanceNorm partial sums -------------------------------------------
@@ -280,6 +282,7 @@ int sinc_tc_forward(const float* wav, const long long* chunk_off, const int* chu
   p.tiles = ceil_div(kPool0, kSTPool);
   B200_CHECK(p.tiles <= ntiles_part, B200_ERR_STATE, "sinc_tc: partial-sum buffer too small");
   p.num_items = NB * p.tiles;
+  { const char* e = getenv("B200_SINC_EARLY"); p.early_raw = e ? atoi(e) : 0; }
   CUtensorMap tmAh, tmAl;
   int rc;
   if ((rc = make_a_map(&tmAh, Ah))) return rc;

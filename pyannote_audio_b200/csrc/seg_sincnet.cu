@@ -341,8 +341,11 @@ int sincnet_forward(const SegWeights& W, const float* wav, const long long* chun
     B200_CUDA_OK(cudaFuncSetAttribute(conv5_pool_kernel<60>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c60));
     attr = true;
   }
+  // conv_impl: 0 = fp32 CUDA-core kernels, 1 = tensor cores for all three layers (default); 2 = tensor-core sinc layer
+  // only, 3 = tensor-core Conv1d layers only (the mixed settings localise a difference between the twins)
+  const bool tc_sinc = conv_impl == 1 || conv_impl == 2, tc_conv = conv_impl == 1 || conv_impl == 3;
   wav_stats_kernel<<<NB, 512, 0, stream>>>(wav, chunk_off, chunk_valid, W.wav_w, W.wav_b, w.af_wav);
-  if (conv_impl == 1) {
+  if (tc_sinc) {
     const int nt0 = ceil_div(kPool0, 80);
     const int rc0 = sinc_tc_forward(wav, chunk_off, chunk_valid, w.af_wav, W.sinc_tc_hi, W.sinc_tc_lo, NB, w.P0, w.part0,
                                     nt0, num_sms, stream);
@@ -355,7 +358,7 @@ int sincnet_forward(const SegWeights& W, const float* wav, const long long* chun
     in_finalize_kernel<<<ceil_div(NB * 80, 128), 128, 0, stream>>>(w.part0, kTiles0, kPool0, 80, W.in_gamma[0],
                                                                    W.in_beta[0], w.af0, NB * 80);
   }
-  if (conv_impl == 1) {
+  if (tc_conv) {
     // tensor-core path: IN + leaky-relu + split to channels-last fp16 (hi, lo), then the implicit GEMM
     int rc;
     const int nt1 = ceil_div(kPool1, 80), nt2 = ceil_div(kPool2, 80);

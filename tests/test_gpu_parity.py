@@ -67,6 +67,28 @@ def _device_wave(wav, dev):
     return buf, off, valid
 
 
+def _diagnose_sincnet(ctx, buf, off, valid, first, ref):
+    import subprocess
+
+    def worst(a):
+        d = np.abs(a - ref).reshape(a.shape[0], -1).max(axis=1)
+        return f"max {d.max():.2e}, chunks over 2e-4: {np.nonzero(d > 2e-4)[0].tolist()}"
+
+    print(f"[sincnet diagnosis] first call: {worst(first)}")
+    for name, mode in (("tensor-core again", 1), ("fp32 CUDA-core twin", 0), ("sinc layer on tensor cores only", 2),
+                       ("Conv1d layers on tensor cores only", 3)):
+        ctx.set_option("seg_conv_impl", mode)
+        out = ctx.sincnet_forward(buf, off, valid).cpu().numpy()
+        print(f"[sincnet diagnosis] {name}: {worst(out)}; equal to the first call: {np.array_equal(out, first)}")
+    ctx.set_option("seg_conv_impl", 1)
+    try:
+        print("[sincnet diagnosis] " + subprocess.run(
+            ["nvidia-smi", "--query-gpu=name,serial,uuid,clocks.sm,temperature.gpu,ecc.errors.uncorrected.volatile.total",
+             "--format=csv,noheader"], capture_output=True, text=True, timeout=20).stdout.strip())
+    except Exception as exc:                                # diagnostics only
+        print(f"[sincnet diagnosis] nvidia-smi: {exc}")
+
+
 # ---------------------------------------------------------------------------------------------------------
 def test_stats_pool_known_answers_cuda(ctx, dev, golden):
     # /root/reference/tests/test_stats_pool.py:28-131, through b200_stats_pool
@@ -101,6 +123,10 @@ def test_segmentation_parity(ctx, dev, oracle_models):
         ref_sinc = seg_model.sincnet(chunks).transpose(1, 2).numpy()
         ref_logp = seg_model(chunks).numpy()
     sinc = ctx.sincnet_forward(buf, off, valid).cpu().numpy()
+    if np.abs(sinc - ref_sinc).max() > 2e-4:
+        # every kernel on this path is deterministic (scripts/seg_stress.py: thousands of calls in fresh processes,
+        # bitwise equal); say which implementation deviates and whether it repeats before failing
+        _diagnose_sincnet(ctx, buf, off, valid, sinc, ref_sinc)
     np.testing.assert_allclose(sinc, ref_sinc, atol=2e-4, rtol=0)
     cls, logp = ctx.seg_forward(buf, off, valid, return_logp=True)
     np.testing.assert_allclose(logp.cpu().numpy(), ref_logp, atol=2e-4, rtol=0)
