@@ -28,7 +28,7 @@ struct b200_ctx {
   int seg_max_batch = 4736;     // chunks per segmentation sub-batch (37 LSTM tiles of 128 sequences x 2 directions = 74 clusters)
   // chunks per embedding sub-batch.  296 = 2 x 148: the persistent conv kernels stride their items over 148 CTAs and
   // every layer's item count is a multiple of the sub-batch (8 / 4 strips, 20 / 10 pixel tiles per segment), so all
-  // CTAs get the same number of items (256 left the last wave 61-92 % full: 516 -> 511 ms per bench step)
+  // CTAs get the same number of items (256 left the last wave 30-92 % full: 516 -> 511 ms per bench step)
   int emb_max_batch = 296;
   int fbank_share = 1;          // 1 = overlapping hop-aligned chunks share their fbank frames (emb.cuh: FbankRun)
   int64_t launches = 0;

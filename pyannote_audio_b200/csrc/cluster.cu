@@ -353,6 +353,8 @@ __device__ __forceinline__ double block_sum_1024(double v, double* red) {
 }
 
 constexpr int kVbxCtas = 8;        // thread-block cluster per problem; phases separated by cluster barriers
+constexpr int kVbxTileD = 128;     // PLDA dimension the shared-memory speaker-model phase is written for
+constexpr int kVbxTileRows = 32;   // frames staged per tile
 
 __device__ __forceinline__ void vbx_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -383,6 +385,8 @@ vbx_kernel(const VbxJob* __restrict__ jobs, const double* __restrict__ fea_all, 
   double* alpha = alpha_all + (size_t)job.mod_off * D;
   double* invL = invL_all + (size_t)job.mod_off * D;
   __shared__ double red[33];
+  __shared__ double s_rho[kVbxTileRows][kVbxTileD];        // 32 KB: rho rows of the speaker-model phase
+  __shared__ double s_gam[kVbxTileRows][8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gtid = (int)rank * 1024 + tid, gthreads = kVbxCtas * 1024;
   const int gwarp = (int)rank * 32 + warp, gwarps = kVbxCtas * 32;
@@ -406,18 +410,54 @@ vbx_kernel(const VbxJob* __restrict__ jobs, const double* __restrict__ fea_all, 
   int it = 0;
   for (; it < max_iters; ++it) {
     // speaker models: one (s, d) pair per thread, frames summed in order
-    for (int e = gtid; e < S * D; e += gthreads) {
-      const int s = e / D, d = e - s * D;
-      double ng = 0.0, acc = 0.0;
-#pragma unroll 4
-      for (int i = 0; i < n; ++i) {
-        const double g = gamma[(size_t)i * S + s];
-        ng += g;
-        acc += g * rho[(size_t)i * D + d];
+    if (D == kVbxTileD) {
+      // a CTA's 1024 threads are 8 speakers x 128 dimensions, and every speaker needs the same rho rows: the rows (and
+      // the 8 gamma columns) are staged once per CTA in shared memory, 32 frames at a time, instead of each warp
+      // streaming its own copy from L2 (8 x the bytes into the SM, which bounded this phase).  Per thread the frames
+      // are still summed in ascending order with the same operations: bit-identical to the loop below.
+      for (int ebase = (int)rank * 1024; ebase < S * D; ebase += gthreads) {        // uniform over the CTA
+        const int e = ebase + tid, s0 = ebase / kVbxTileD;
+        const int ns = S - s0 < 8 ? S - s0 : 8;
+        const bool ok = e < S * D;
+        const int sl = tid / kVbxTileD, d = tid % kVbxTileD;
+        double ng = 0.0, acc = 0.0;
+        for (int i0 = 0; i0 < n; i0 += kVbxTileRows) {
+          const int cnt = n - i0 < kVbxTileRows ? n - i0 : kVbxTileRows;
+          __syncthreads();                                 // the previous tile has been consumed
+          for (int q = tid; q < cnt * kVbxTileD; q += 1024)
+            s_rho[q / kVbxTileD][q % kVbxTileD] = rho[(size_t)(i0 + q / kVbxTileD) * D + q % kVbxTileD];
+          for (int q = tid; q < cnt * 8; q += 1024)
+            s_gam[q >> 3][q & 7] = (q & 7) < ns ? gamma[(size_t)(i0 + (q >> 3)) * S + s0 + (q & 7)] : 0.0;
+          __syncthreads();
+          if (ok) {
+#pragma unroll 8
+            for (int ii = 0; ii < cnt; ++ii) {
+              const double g = s_gam[ii][sl];
+              ng += g;
+              acc += g * s_rho[ii][d];
+            }
+          }
+        }
+        if (ok) {
+          const double il = 1.0 / (1.0 + FaFb * ng * phi[d]);
+          invL[e] = il;
+          alpha[e] = FaFb * il * acc;
+        }
       }
-      const double il = 1.0 / (1.0 + FaFb * ng * phi[d]);
-      invL[e] = il;
-      alpha[e] = FaFb * il * acc;
+    } else {
+      for (int e = gtid; e < S * D; e += gthreads) {
+        const int s = e / D, d = e - s * D;
+        double ng = 0.0, acc = 0.0;
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+          const double g = gamma[(size_t)i * S + s];
+          ng += g;
+          acc += g * rho[(size_t)i * D + d];
+        }
+        const double il = 1.0 / (1.0 + FaFb * ng * phi[d]);
+        invL[e] = il;
+        alpha[e] = FaFb * il * acc;
+      }
     }
     vbx_cluster_sync();
     for (int s = gwarp; s < S; s += gwarps) {
