@@ -7,6 +7,7 @@ file (read with the stdlib / scipy -- torchcodec is not part of this image).
 from __future__ import annotations
 
 import math
+from io import IOBase
 from pathlib import Path
 from typing import Mapping, Optional, Tuple, Union
 
@@ -16,7 +17,7 @@ import torch.nn.functional as F
 
 from .core import Segment
 
-AudioFile = Union[str, Path, Mapping]
+AudioFile = Union[str, Path, IOBase, Mapping]
 
 
 class Audio:
@@ -26,26 +27,33 @@ class Audio:
 
     @staticmethod
     def validate_file(file: AudioFile) -> Mapping:
+        """io.py:151-214: mapping / path / file-like object -> validated mapping (same messages)."""
         if isinstance(file, Mapping):
-            if "waveform" in file:
-                waveform = file["waveform"]
-                if len(waveform.shape) != 2 or waveform.shape[0] > waveform.shape[1]:
-                    raise ValueError("'waveform' must be provided as a (channel, time) torch Tensor.")
-                if file.get("sample_rate", None) is None:
-                    raise ValueError("'waveform' must be provided with their 'sample_rate'.")
-                file.setdefault("uri", "waveform")       # in place like the reference (io.py:193): hooks store
-                return file                              # their artifacts in the caller's mapping
-            if "audio" in file:
-                path = Path(file["audio"])
-                if not path.is_file():
-                    raise ValueError(f"File {path} does not exist")
-                file.setdefault("uri", path.stem)
+            pass
+        elif isinstance(file, (str, Path)):
+            file = {"audio": str(file), "uri": Path(file).stem}
+        elif isinstance(file, IOBase):
+            return {"audio": file, "uri": "stream"}
+        else:
+            raise ValueError("AudioFile must be a path, a file-like object, or a mapping with an 'audio' or "
+                             "'waveform' (+ 'sample_rate') key.")
+        if "waveform" in file:
+            waveform = file["waveform"]
+            if len(waveform.shape) != 2 or waveform.shape[0] > waveform.shape[1]:
+                raise ValueError("'waveform' must be provided as a (channel, time) torch Tensor.")
+            if file.get("sample_rate", None) is None:
+                raise ValueError("'waveform' must be provided with their 'sample_rate'.")
+            file.setdefault("uri", "waveform")           # in place like the reference (io.py:193): hooks store
+        elif "audio" in file:                            # their artifacts in the caller's mapping
+            if isinstance(file["audio"], IOBase):
                 return file
+            path = Path(file["audio"])
+            if not path.is_file():
+                raise ValueError(f"File {path} does not exist")
+            file.setdefault("uri", path.stem)
+        else:
             raise ValueError("Neither 'waveform' nor 'audio' is available for this file.")
-        path = Path(file)
-        if not path.is_file():
-            raise ValueError(f"File {path} does not exist")
-        return {"audio": str(path), "uri": path.stem}
+        return file
 
     def get_num_samples(self, duration: float, sample_rate: Optional[int] = None) -> int:
         sample_rate = sample_rate or self.sample_rate
@@ -71,9 +79,11 @@ class Audio:
         return waveform, sample_rate
 
     @staticmethod
-    def _read_wav(path: str) -> Tuple[torch.Tensor, int]:
+    def _read_wav(path) -> Tuple[torch.Tensor, int]:
         from scipy.io import wavfile
 
+        if isinstance(path, IOBase):                     # file-like objects are read from their start (io.py:337-338)
+            path.seek(0)
         sr, data = wavfile.read(path)
         if data.ndim == 1:
             data = data[:, None]
@@ -94,6 +104,8 @@ class Audio:
         common case: half the bytes of float32), otherwise float32 (channels, frames) converted on the host."""
         from scipy.io import wavfile
 
+        if isinstance(path, IOBase):
+            path.seek(0)
         sr, data = wavfile.read(path)
         if data.ndim == 1:
             data = data[:, None]
