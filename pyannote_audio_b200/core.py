@@ -275,9 +275,37 @@ class Annotation:
     def __bool__(self):
         return len(self) > 0
 
-    def to_rttm(self) -> str:
+    def _iter_rttm(self):
+        """pyannote.core Annotation._iter_rttm: one SPEAKER line per track; names with spaces are refused."""
         uri = self.uri if self.uri else "<NA>"
-        lines = []
+        if isinstance(uri, str) and " " in uri:
+            raise ValueError(f'Space-separated RTTM file format does not allow file URIs containing spaces (got: "{uri}").')
         for s, _, lab in self.itertracks(yield_label=True):
-            lines.append(f"SPEAKER {uri} 1 {s.start:.3f} {s.duration:.3f} <NA> <NA> {lab} <NA> <NA>\n")
-        return "".join(lines)
+            if isinstance(lab, str) and " " in lab:
+                raise ValueError(f'Space-separated RTTM file format does not allow labels containing spaces (got: "{lab}").')
+            yield f"SPEAKER {uri} 1 {s.start:.3f} {s.duration:.3f} <NA> <NA> {lab} <NA> <NA>\n"
+
+    def to_rttm(self) -> str:
+        return "".join(self._iter_rttm())
+
+    def write_rttm(self, file) -> None:
+        """Dump to an open text file, as the reference's CLI does (__main__.py:705-706)."""
+        for line in self._iter_rttm():
+            file.write(line)
+
+    def get_timeline(self) -> List[Segment]:
+        """Segments in chronological order (pyannote.core returns a Timeline; a sorted list of unique segments here)."""
+        return sorted(set(self.itersegments()))
+
+    def label_duration(self, label) -> float:
+        """Total duration of the union of `label`'s segments (pyannote.core Annotation.label_duration)."""
+        total, end = 0.0, -np.inf
+        for s in sorted(seg for seg, _, lab in self.itertracks(yield_label=True) if lab == label):
+            if s.end > end:
+                total += s.end - max(s.start, end)
+                end = s.end
+        return total
+
+    def chart(self) -> List[Tuple[object, float]]:
+        """(label, duration) pairs, longest first (pyannote.core Annotation.chart)."""
+        return sorted(((lab, self.label_duration(lab)) for lab in self.labels()), key=lambda x: x[1], reverse=True)

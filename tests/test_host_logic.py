@@ -353,3 +353,32 @@ def test_binarize_drops_empty_segments_and_support_is_strict():
     assert got == P.support([(0.0, 1.0, "b"), (1.5, 2.0, "b"), (2.2, 3.0, "b"), (0.0, 1.0, "a"), (1.0, 2.0, "a")], 0.5)
     ann.add(Segment(5.0, 5.0), "_", "c")          # empty segments are never stored
     assert "c" not in ann.labels()
+
+
+def test_annotation_rttm_and_summaries():
+    """The pyannote.core conveniences downstream code relies on (reference CLI: speaker_diarization.write_rttm(rttm),
+    /root/reference/src/pyannote/audio/__main__.py:705-706)."""
+    import io
+
+    from pyannote_audio_b200.core import Annotation, Segment
+
+    a = Annotation(uri="file1")
+    a[Segment(0.5, 2.0), 1] = "SPEAKER_00"
+    a[Segment(0.0, 1.0), 0] = "SPEAKER_00"
+    a[Segment(3.0, 4.25), 2] = "SPEAKER_01"
+    expected = ("SPEAKER file1 1 0.000 1.000 <NA> <NA> SPEAKER_00 <NA> <NA>\n"
+                "SPEAKER file1 1 0.500 1.500 <NA> <NA> SPEAKER_00 <NA> <NA>\n"
+                "SPEAKER file1 1 3.000 1.250 <NA> <NA> SPEAKER_01 <NA> <NA>\n")
+    assert a.to_rttm() == expected
+    f = io.StringIO()
+    a.write_rttm(f)
+    assert f.getvalue() == expected
+    assert a.label_duration("SPEAKER_00") == 2.0 and a.label_duration("SPEAKER_01") == 1.25
+    assert a.chart() == [("SPEAKER_00", 2.0), ("SPEAKER_01", 1.25)]
+    assert a.get_timeline() == [Segment(0.0, 1.0), Segment(0.5, 2.0), Segment(3.0, 4.25)]
+    with pytest.raises(ValueError, match="URIs containing spaces"):
+        Annotation(uri="a b").to_rttm()
+    bad = Annotation(uri="ok")
+    bad[Segment(0, 1), 0] = "two words"
+    with pytest.raises(ValueError, match="labels containing spaces"):
+        bad.to_rttm()
