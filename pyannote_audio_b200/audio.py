@@ -6,7 +6,6 @@ file (read with the stdlib / scipy -- torchcodec is not part of this image).
 """
 from __future__ import annotations
 
-import math
 from io import IOBase
 from pathlib import Path
 from typing import Mapping, Optional, Tuple, Union

@@ -8,7 +8,7 @@ arithmetic runs in fp64 on the device through libb200diar.so: clean-frame filter
 from __future__ import annotations
 
 from pathlib import Path
-from typing import Optional, Tuple, Union
+from typing import Optional, Union
 
 import numpy as np
 import torch

@@ -11,9 +11,8 @@ The reference has no inference-time parallelism at all (SURVEY.md section 2.2); 
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Sequence, Tuple
+from typing import Callable, List, Sequence, Tuple
 
-import numpy as np
 import torch
 import torch.distributed as dist
 

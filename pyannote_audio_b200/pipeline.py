@@ -20,7 +20,7 @@ import sys
 import time
 import warnings
 from dataclasses import dataclass
-from typing import Any, Callable, Iterator, List, Mapping, Optional, Sequence, Tuple, Union
+from typing import Any, Callable, Iterator, Mapping, Optional, Sequence, Tuple, Union
 
 import numpy as np
 import torch
@@ -28,7 +28,7 @@ import torch
 from . import ops
 from .audio import Audio, AudioFile
 from .clustering import PLDA, AgglomerativeClustering, VBxClustering
-from .core import Annotation, Segment, SlidingWindow, SlidingWindowFeature
+from .core import Annotation, SlidingWindow, SlidingWindowFeature
 from .inference import Inference, chunk_layout
 from .models import PyanNet, WeSpeakerResNet34, get_context
 

@@ -1,5 +1,4 @@
 """CPU: host-side logic of the product package (no GPU, no compute calls into the CUDA library)."""
-import warnings
 
 import numpy as np
 import pytest
