@@ -381,3 +381,28 @@ def test_annotation_rttm_and_summaries():
     bad[Segment(0, 1), 0] = "two words"
     with pytest.raises(ValueError, match="labels containing spaces"):
         bad.to_rttm()
+
+
+def test_hooks_store_artifacts_and_timing():
+    """Mirror of the reference's hook protocol (pipelines/utils/hook.py:37-239): artifacts are deep-copied into the
+    file mapping, progress calls (artifact None) are ignored by ArtifactHook and drive TimingHook."""
+    from pyannote_audio_b200.hooks import ArtifactHook, Hooks, TimingHook
+
+    file = {"uri": "f"}
+    data = np.arange(6).reshape(2, 3)
+    with Hooks(ArtifactHook("segmentation", "embeddings"), TimingHook()) as hook:
+        hook("segmentation", None, file=file, total=4, completed=0)
+        hook("segmentation", None, file=file, total=4, completed=4)
+        hook("segmentation", data, file=file)
+        hook("speaker_counting", data, file=file)                       # not in the requested list
+        hook("embeddings", None, file=file, total=1, completed=0)
+        hook("embeddings", None, file=file, total=1, completed=1)
+        hook("embeddings", data * 2, file=file)
+    data[0, 0] = 99                                                     # stored artifacts are copies
+    assert set(file["artifact"]) == {"segmentation", "embeddings"}
+    assert file["artifact"]["segmentation"][0, 0] == 0 and file["artifact"]["embeddings"][1, 2] == 10
+    assert set(file["timing"]) == {"total", "segmentation", "embeddings"}
+    assert all(v >= 0.0 for v in file["timing"].values())
+    with ArtifactHook() as everything:                                  # no names: keep every artifact
+        everything("discrete_diarization", data, file=file)
+    assert "discrete_diarization" in file["artifact"]
