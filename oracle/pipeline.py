@@ -14,6 +14,10 @@ Follows (paths relative to /root/reference/src/pyannote/audio):
 * ``VBx`` / ``cluster_vbx`` / ``vbx_setup`` / PLDA   utils/vbx.py:27-218, core/plda.py:33-63
 * ``apply``                 pipelines/speaker_diarization.py:530-784
 
+Pinning: aggregate / trim / speaker_count / to_diarization / reconstruct / binarize / filter_embeddings /
+constrained_argmax / vbx_clustering / ahc_call are checked against outputs of the reference's own files executed by
+path (tests/golden/make_golden_pipeline.py -> reference_pipeline_vectors.npz, tests/test_oracle_pipeline_golden.py).
+
 pyannote.core 6.0.1 (SlidingWindow.closest_frame / crop / range_to_segment, Segment.middle) is NOT
 in the tree and not installed: restated from its published behaviour -- parity unpinned for the
 frame arithmetic (cross-checked against the shape facts in tutorials/applying_a_model.ipynb).
@@ -626,7 +630,8 @@ def ahc_call(embeddings, seg_data, threshold, min_cluster_size, method="centroid
 # ----------------------------------------------------------------------------------------
 
 
-def reconstruct(segmentations: SWF, hard_clusters, count: SWF) -> SWF:
+def clustered_segmentations(segmentations: SWF, hard_clusters) -> SWF:
+    """speaker_diarization.py:480-520: per chunk, the activity of a cluster is the max over its local speakers."""
     num_chunks, num_frames, _ = segmentations.data.shape
     num_clusters = int(np.max(hard_clusters)) + 1
     clustered = np.nan * np.zeros((num_chunks, num_frames, num_clusters))
@@ -637,7 +642,11 @@ def reconstruct(segmentations: SWF, hard_clusters, count: SWF) -> SWF:
             if k == -2:
                 continue
             clustered[c, :, k] = np.max(seg[:, cluster == k], axis=1)
-    return to_diarization(SWF(clustered, segmentations.sw), count)
+    return SWF(clustered, segmentations.sw)
+
+
+def reconstruct(segmentations: SWF, hard_clusters, count: SWF) -> SWF:
+    return to_diarization(clustered_segmentations(segmentations, hard_clusters), count)
 
 
 @dataclass
