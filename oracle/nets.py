@@ -13,6 +13,11 @@ Follows (paths relative to /root/reference/src/pyannote/audio):
 * ``Powerset``           utils/powerset.py:80-109, 115-140
 
 State-dict key names equal the reference's so that real checkpoints would load.
+
+Pinning: ResNet / StatsPool / Powerset against the reference's leaf files (tests/golden/make_golden.py); PyanNet and
+WeSpeakerResNet34 (compute_fbank, forward with weights) against the reference's own PyanNet.py / sincnet.py /
+wespeaker/__init__.py executed by path with these very state dicts loaded strictly (tests/golden/make_golden_apply.py,
+tests/test_oracle_apply_golden.py).  ParamSincFB / Encoder stay unpinned (asteroid-filterbanks is not available).
 """
 
 from __future__ import annotations

@@ -16,7 +16,9 @@ Follows (paths relative to /root/reference/src/pyannote/audio):
 
 Pinning: aggregate / trim / speaker_count / to_diarization / reconstruct / binarize / filter_embeddings /
 constrained_argmax / vbx_clustering / ahc_call are checked against outputs of the reference's own files executed by
-path (tests/golden/make_golden_pipeline.py -> reference_pipeline_vectors.npz, tests/test_oracle_pipeline_golden.py).
+path (tests/golden/make_golden_pipeline.py -> reference_pipeline_vectors.npz, tests/test_oracle_pipeline_golden.py);
+get_embeddings and apply against the reference's SpeakerDiarization.get_embeddings / apply run on a synthetic
+conversation (tests/golden/make_golden_apply.py -> reference_apply_vectors.npz, tests/test_oracle_apply_golden.py).
 
 pyannote.core 6.0.1 (SlidingWindow.closest_frame / crop / range_to_segment, Segment.middle) is NOT
 in the tree and not installed: restated from its published behaviour -- parity unpinned for the

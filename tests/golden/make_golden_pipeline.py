@@ -168,6 +168,17 @@ class Annotation:
         for (s, e, t) in sorted(self._tracks, key=lambda k: (k[0], k[1], str(k[2]))):
             yield (Segment(s, e), t, self._tracks[(s, e, t)]) if yield_label else (Segment(s, e), t)
 
+    def labels(self):
+        return sorted(set(self._tracks.values()), key=str)
+
+    def rename_labels(self, mapping=None, generator="string", copy=True):
+        renamed = Annotation(uri=self.uri)
+        renamed._tracks = {key: mapping.get(label, label) for key, label in self._tracks.items()}
+        return renamed
+
+    def __bool__(self):
+        return len(self._tracks) > 0
+
 
 class Timeline:
     pass
