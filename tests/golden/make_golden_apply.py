@@ -103,26 +103,28 @@ def main():
     chunks_sw = G.SlidingWindow(start=0.0, duration=10.0, step=1.0)
     powerset = ref["powerset"].Powerset(3, 2)
 
+    # the reference's Inference.slide / infer (core/inference.py:182-373) run verbatim on a hand-assembled instance
+    # (Inference.__init__ needs the Lightning model API: device moves, example outputs, ...)
+    Inference = ref["inference"].Inference
+    Spec = sys.modules["pyannote.audio.core.model"].Specifications
+    spec = Spec()
+    spec.powerset, spec.num_powerset_classes, spec.classes, spec.powerset_max_classes = True, 7, ["a", "b", "c"], 2
+    spec.permutation_invariant, spec.duration = True, 10.0
+    spec.resolution = sys.modules["pyannote.audio.core.task"].Resolution.FRAME
+    seg_model.specifications, seg_model.audio, seg_model.receptive_field = spec, audio, frames
+
+    def make_inference(**kw):
+        inf = object.__new__(Inference)
+        inf.model, inf.duration, inf.step, inf.batch_size, inf.device = seg_model, 10.0, 1.0, 4, torch.device("cpu")
+        inf.conversion, inf.warm_up = powerset, (0.0, 0.0)
+        inf.skip_aggregation, inf.pre_aggregation_hook = kw.get("skip_aggregation", False), kw.get("pre_aggregation_hook")
+        return inf
+
+    inf_skip = make_inference(skip_aggregation=True)
+
     def slide(f, hook=None):
-        """Inference.slide with skip_aggregation (core/inference.py:217-347): unfold, forward, last chunk padded."""
         waveform, sr = audio(f)
-        window, step = 160000, 16000
-        _, num_samples = waveform.shape
-        outs = []
-        with torch.inference_mode():
-            if num_samples >= window:
-                ch = waveform.unfold(1, window, step).permute(1, 0, 2)
-                outs.append(seg_model(ch))
-            has_last = (num_samples < window) or (num_samples - window) % step > 0
-            if has_last:
-                n = ch.shape[0] if num_samples >= window else 0
-                last = waveform[:, n * step:]
-                last = torch.nn.functional.pad(last, (0, window - last.shape[1]))
-                outs.append(seg_model(last[None]))
-            logp = torch.vstack(outs)
-            ml = powerset.to_multilabel(logp)
-        slide.logp = logp.numpy()
-        return G.SlidingWindowFeature(ml.numpy(), chunks_sw)
+        return Inference.slide(inf_skip, waveform, sr, hook=hook)
 
     SD = ref["speaker_diarization"].SpeakerDiarization
     art = {}
@@ -161,7 +163,6 @@ def main():
         art.clear()
         res = SD.apply(sd, dict(file), hook=hook)
         if name == "std":
-            out["logp"] = slide.logp
             out["segmentations"] = art["segmentation"].data.astype(np.uint8)
             out["count"] = art["speaker_counting"].data
         out[f"{name}_embeddings"] = art["embeddings"]
@@ -174,6 +175,36 @@ def main():
         print(name, "segments", len(out[f"{name}_diar"]), "exclusive", len(out[f"{name}_excl"]), "labels",
               out[f"{name}_labels"], "embeddings", art["embeddings"].shape, "nan", int(np.isnan(art["embeddings"]).sum()),
               "max count", int(art["speaker_counting"].data.max()))
+    with torch.inference_mode():
+        w16 = audio(file)[0]
+        ch = w16.unfold(1, 160000, 16000).permute(1, 0, 2)
+        last = torch.nn.functional.pad(w16[:, ch.shape[0] * 16000:], (0, 160000 - (w16.shape[1] - ch.shape[0] * 16000)))
+        out["logp"] = torch.vstack([seg_model(ch), seg_model(last[None])]).numpy()
+
+    # ---- VoiceActivityDetection.apply (pipelines/voice_activity_detection.py:66-204) verbatim ------------------------
+    G.stub("pyannote.metrics.detection")
+    vad_mod = G.load("pyannote.audio.pipelines.voice_activity_detection", "pipelines/voice_activity_detection.py")
+    VAD = vad_mod.VoiceActivityDetection
+    inf_vad = make_inference(pre_aggregation_hook=lambda scores: np.max(scores, axis=-1, keepdims=True))
+    for name, seconds in (("vad", 23.4), ("vad_short", 6.3)):
+        wav_v = syn.make_conversation(seconds, seed=seed)
+        f = {"waveform": wav_v, "sample_rate": 16000, "uri": "golden"}
+        vad = object.__new__(VAD)
+        vad.training = False
+        vad._segmentation = type("_Seg", (), {"__call__": staticmethod(
+            lambda ff, hook=None: Inference.slide(inf_vad, *audio(ff), hook=None))})()
+        vad.setup_hook = lambda ff, hook=None: (lambda *a, **k: None)
+        for sub, (mon, moff) in (("", (0.0, 0.0)), ("_on", (0.25, 0.0))):
+            vad._binarize = ref["signal"].Binarize(onset=0.5, offset=0.5, min_duration_on=mon, min_duration_off=moff)
+            speech = VAD.apply(vad, dict(f))
+            out[f"{name}{sub}_rows"] = np.array([(sg.start, sg.end) for sg, _ in speech.itertracks()],
+                                                dtype=np.float64).reshape(-1, 2)
+            assert speech.labels() in ([], ["SPEECH"])
+        scores = Inference.slide(inf_vad, *audio(f), hook=None)
+        out[f"{name}_scores"] = scores.data
+        out[f"{name}_scores_sw"] = np.array([scores.sliding_window.start, scores.sliding_window.duration,
+                                             scores.sliding_window.step])
+        print(name, "frames", scores.data.shape, "speech regions", len(out[f"{name}_rows"]), len(out[f"{name}_on_rows"]))
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_apply_vectors.npz")
     np.savez_compressed(dst, **out)
     print(f"wrote {dst}: {len(out)} arrays, {os.path.getsize(dst) / 1e6:.2f} MB")

@@ -272,10 +272,18 @@ def load_reference():
             pass
 
     sys.modules["pyannote.pipeline"].Pipeline = Pipeline
+    import enum
+
+    class Resolution(enum.Enum):                         # pyannote.audio.core.task.Resolution
+        FRAME = 1
+        CHUNK = 2
+
+    sys.modules["pyannote.audio.core.task"].Resolution = Resolution
     ref = {}
     ref["powerset"] = load("pyannote.audio.utils.powerset", "utils/powerset.py")
     ref["vbx"] = load("pyannote.audio.utils.vbx", "utils/vbx.py")
     ref["plda"] = load("pyannote.audio.core.plda", "core/plda.py")
+    ref["multi_task"] = load("pyannote.audio.utils.multi_task", "utils/multi_task.py")
     ref["inference"] = load("pyannote.audio.core.inference", "core/inference.py")
     sys.modules["pyannote.audio"].Inference = ref["inference"].Inference
     ref["signal"] = load("pyannote.audio.utils.signal", "utils/signal.py")

@@ -79,3 +79,22 @@ def test_apply_matches_the_reference_apply(ref, name, exclude_overlap):
         assert [lab for _, _, lab in times] == [f"SPEAKER_{int(k):02d}" for k in rows[:, 2]]
     assert out.labels == list(ref[f"{name}_labels"])
     np.testing.assert_allclose(out.speaker_embeddings, ref[f"{name}_speaker_embeddings"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["vad", "vad_short"])
+def test_vad_matches_the_reference_pipeline(ref, models, name):
+    # the reference: Inference.slide verbatim (pre_aggregation_hook = max over speakers, Hamming overlap-add, padded
+    # tail cropped; core/inference.py:217-373) and VoiceActivityDetection.apply (Binarize at 0.5, min_duration_on)
+    seg_model, _ = models
+    seconds = {"vad": float(ref["wav_seconds"]), "vad_short": 6.3}[name]
+    wav = syn.make_conversation(seconds, seed=int(ref["wav_seed"]))
+    scores = P.vad_scores(seg_model, wav)
+    want = ref[f"{name}_scores"]
+    assert scores.data.shape == want.shape and scores.data.dtype == want.dtype
+    np.testing.assert_allclose(scores.data, want, rtol=0, atol=1e-6)
+    np.testing.assert_allclose([scores.sw.start, scores.sw.duration, scores.sw.step], ref[f"{name}_scores_sw"], atol=1e-15)
+    for sub, mon in (("", 0.0), ("_on", 0.25)):
+        got = P.binarize_scores(P.SWF(want, scores.sw), onset=0.5, offset=0.5, min_duration_on=mon)
+        rows = ref[f"{name}{sub}_rows"]
+        assert len(got) == len(rows) and len(rows) >= 1
+        np.testing.assert_array_equal(np.array([[a, b] for a, b, _ in got]), rows)
