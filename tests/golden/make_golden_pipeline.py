@@ -429,6 +429,26 @@ def main():
                      ("forced3", dict(num_clusters=3)), ("min5", dict(min_clusters=5, max_clusters=20))):
         h, s_, c_ = ahc(emb.copy(), segmentations=SlidingWindowFeature(seg.copy(), chunks), **kw)
         out[f"ahc_{name}_hard"], out[f"ahc_{name}_soft"], out[f"ahc_{name}_centroids"] = h, s_, c_
+    # ---- Audio (core/io.py): in-memory waveforms through __call__ / crop / downmix_and_resample ---------------------
+    import torch
+
+    io_mod = load("pyannote.audio.core.io", "core/io.py")
+    g = torch.Generator().manual_seed(5)
+    stereo = torch.rand(2, 24000, generator=g) * 2 - 1
+    hi = torch.rand(1, 22050, generator=g) * 2 - 1                    # 0.5 s at 44.1 kHz
+    out["io_stereo"], out["io_hi"] = stereo.numpy(), hi.numpy()
+    A = io_mod.Audio
+    w, sr = A(sample_rate=16000, mono="downmix")({"waveform": stereo, "sample_rate": 16000})
+    out["io_downmix"] = w.numpy()
+    w, sr = A(sample_rate=16000, mono="downmix")({"waveform": stereo, "sample_rate": 16000, "channel": 1})
+    out["io_channel1"] = w.numpy()
+    w, sr = A(sample_rate=16000, mono="downmix")({"waveform": hi, "sample_rate": 44100})
+    out["io_resampled"], out["io_resampled_sr"] = w.numpy(), np.array(sr)
+    w, sr = A(sample_rate=8000, mono="downmix")({"waveform": stereo, "sample_rate": 16000})
+    out["io_half_rate"] = w.numpy()
+    for name, (a, b), mode in (("in", (0.2, 0.7), "raise"), ("pad_end", (1.2, 2.0), "pad"), ("pad_start", (-0.25, 0.5), "pad")):
+        w, sr = A(sample_rate=16000, mono="downmix").crop({"waveform": stereo, "sample_rate": 16000}, Segment(a, b), mode=mode)
+        out[f"io_crop_{name}"] = w.numpy()
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_pipeline_vectors.npz")
     np.savez_compressed(dst, **out)
     print(f"wrote {dst}: {len(out)} arrays, {os.path.getsize(dst) / 1e6:.2f} MB")

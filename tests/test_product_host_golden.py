@@ -65,3 +65,26 @@ def test_signal_binarize_matches_reference(ref, ref_apply):
             ann = Binarize(onset=0.5, offset=0.5, min_duration_on=mon)(SlidingWindowFeature(ref_apply[f"{name}_scores"], sw))
             got = np.array([(s.start, s.end) for s, _ in ann.itertracks()]).reshape(-1, 2)
             np.testing.assert_array_equal(got, ref_apply[f"{name}{sub}_rows"])
+
+
+def test_audio_matches_reference_io(ref):
+    """Audio.__call__ / crop / downmix_and_resample on in-memory waveforms against the reference's core/io.py executed
+    by path (downmix, channel selection, 44.1 -> 16 kHz and 16 -> 8 kHz resampling, crops inside / padded)."""
+    import torch
+
+    from pyannote_audio_b200.audio import Audio
+    from pyannote_audio_b200.core import Segment
+
+    stereo, hi = torch.from_numpy(ref["io_stereo"]), torch.from_numpy(ref["io_hi"])
+    a16 = Audio(sample_rate=16000, mono="downmix")
+    w, sr = a16({"waveform": stereo, "sample_rate": 16000})
+    assert sr == 16000 and np.array_equal(w.numpy(), ref["io_downmix"])
+    w, _ = a16({"waveform": stereo, "sample_rate": 16000, "channel": 1})
+    assert np.array_equal(w.numpy(), ref["io_channel1"])
+    w, sr = a16({"waveform": hi, "sample_rate": 44100})
+    assert sr == int(ref["io_resampled_sr"]) == 16000 and np.array_equal(w.numpy(), ref["io_resampled"])
+    w, sr = Audio(sample_rate=8000, mono="downmix")({"waveform": stereo, "sample_rate": 16000})
+    assert sr == 8000 and np.array_equal(w.numpy(), ref["io_half_rate"])
+    for name, (a, b), mode in (("in", (0.2, 0.7), "raise"), ("pad_end", (1.2, 2.0), "pad"), ("pad_start", (-0.25, 0.5), "pad")):
+        w, _ = a16.crop({"waveform": stereo, "sample_rate": 16000}, Segment(a, b), mode=mode)
+        assert np.array_equal(w.numpy(), ref[f"io_crop_{name}"]), name
