@@ -170,6 +170,9 @@ def main():
         for key, ann in (("diar", res.speaker_diarization), ("excl", res.exclusive_speaker_diarization)):
             rows = [(s.start, s.end, int(str(lab).split("_")[1])) for s, _, lab in ann.itertracks(yield_label=True)]
             out[f"{name}_{key}"] = np.array(rows, dtype=np.float64).reshape(-1, 3)
+        import json
+
+        out[f"{name}_serialized"] = np.array(json.dumps(res.serialize()))        # DiarizeOutput.serialize verbatim
         out[f"{name}_labels"] = np.array(res.speaker_diarization.labels())
         out[f"{name}_speaker_embeddings"] = res.speaker_embeddings
         print(name, "segments", len(out[f"{name}_diar"]), "exclusive", len(out[f"{name}_excl"]), "labels",

@@ -88,3 +88,21 @@ def test_audio_matches_reference_io(ref):
     for name, (a, b), mode in (("in", (0.2, 0.7), "raise"), ("pad_end", (1.2, 2.0), "pad"), ("pad_start", (-0.25, 0.5), "pad")):
         w, _ = a16.crop({"waveform": stereo, "sample_rate": 16000}, Segment(a, b), mode=mode)
         assert np.array_equal(w.numpy(), ref[f"io_crop_{name}"]), name
+
+
+def test_diarize_output_serialize_matches_reference(ref_apply):
+    """DiarizeOutput.serialize (speaker_diarization.py:78-124) on the reference's own output of the synthetic file."""
+    import json
+
+    from pyannote_audio_b200.core import Annotation
+    from pyannote_audio_b200.pipeline import DiarizeOutput
+
+    def annotation(rows):
+        labels = np.array([f"SPEAKER_{int(k):02d}" for k in rows[:, 2]], dtype=object)
+        return Annotation.from_rows(rows[:, 0], rows[:, 1], labels, uri="golden")
+
+    for name in ("std", "xo"):
+        out = DiarizeOutput(annotation(ref_apply[f"{name}_diar"]), annotation(ref_apply[f"{name}_excl"]),
+                            ref_apply[f"{name}_speaker_embeddings"])
+        assert out.serialize() == json.loads(str(ref_apply[f"{name}_serialized"]))
+        assert out.speaker_diarization.labels() == list(ref_apply[f"{name}_labels"])
