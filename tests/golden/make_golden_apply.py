@@ -178,6 +178,31 @@ def main():
         print(name, "segments", len(out[f"{name}_diar"]), "exclusive", len(out[f"{name}_excl"]), "labels",
               out[f"{name}_labels"], "embeddings", art["embeddings"].shape, "nan", int(np.isnan(art["embeddings"]).sum()),
               "max count", int(art["speaker_counting"].data.max()))
+    # ---- the same file with constraints on the number of speakers (KMeans branch, count capped by max_speakers) and a
+    # file on which no speaker is ever active (early exit, speaker_diarization.py:617-628) ----------------------------
+    for name, kw in (("forced3", dict(num_speakers=3)), ("max1", dict(max_speakers=1)), ("min3", dict(min_speakers=3))):
+        sd.embedding_exclude_overlap = False
+        art.clear()
+        import warnings as _w
+
+        with _w.catch_warnings():
+            _w.simplefilter("ignore")
+            res = SD.apply(sd, dict(file), hook=hook, **kw)
+        out[f"{name}_discrete"] = art["discrete_diarization"].data
+        for key, ann in (("diar", res.speaker_diarization), ("excl", res.exclusive_speaker_diarization)):
+            rows = [(sg.start, sg.end, int(str(lab).split("_")[1])) for sg, _, lab in ann.itertracks(yield_label=True)]
+            out[f"{name}_{key}"] = np.array(rows, dtype=np.float64).reshape(-1, 3)
+        out[f"{name}_labels"] = np.array(res.speaker_diarization.labels())
+        out[f"{name}_speaker_embeddings"] = res.speaker_embeddings
+        print(name, "segments", len(out[f"{name}_diar"]), "labels", out[f"{name}_labels"], res.speaker_embeddings.shape)
+    silent = object.__new__(SD)
+    silent.__dict__.update(sd.__dict__)
+    silent._segmentation = type("_Seg", (), {"model": sd._segmentation.model, "__call__": staticmethod(
+        lambda f, hook=None: G.SlidingWindowFeature(np.zeros((15, 589, 3), dtype=np.float32), chunks_sw))})()
+    res = SD.apply(silent, dict(file), hook=hook)
+    assert len(list(res.speaker_diarization.itertracks())) == 0 and res.speaker_embeddings.shape == (0, 256)
+    out["silent_speaker_embeddings_shape"] = np.array(res.speaker_embeddings.shape)
+
     with torch.inference_mode():
         w16 = audio(file)[0]
         ch = w16.unfold(1, 160000, 16000).permute(1, 0, 2)

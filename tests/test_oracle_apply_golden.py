@@ -98,3 +98,35 @@ def test_vad_matches_the_reference_pipeline(ref, models, name):
         rows = ref[f"{name}{sub}_rows"]
         assert len(got) == len(rows) and len(rows) >= 1
         np.testing.assert_array_equal(np.array([[a, b] for a, b, _ in got]), rows)
+
+
+@pytest.mark.parametrize("name,kw", [("forced3", dict(num_speakers=3)), ("max1", dict(max_speakers=1)),
+                                     ("min3", dict(min_speakers=3))])
+def test_apply_with_speaker_bounds_matches_the_reference(ref, name, kw):
+    # forced / minimum number of speakers -> KMeans on the normalised training embeddings (clustering.py:626-642),
+    # max_speakers=1 -> the instantaneous count is capped (speaker_diarization.py:735)
+    plda = P.PLDA(**syn.make_plda(2))
+    seg = P.SWF(ref["segmentations"].astype(np.float32), CHUNKS)
+    out = P.apply(None, None, plda, None, segmentations=seg, embeddings=ref["std_embeddings"], **kw)
+    want = ref[f"{name}_discrete"]
+    assert out.discrete.data.shape == want.shape
+    differ = np.nonzero((out.discrete.data != want).any(axis=1))[0]
+    if len(differ):                                         # only activation ties may differ (numpy's default argsort)
+        act = P.aggregate(P.clustered_segmentations(seg, out.hard_clusters), out.count.sw, hamming=False, missing=0.0,
+                          skip_average=True).data[: len(want)]
+        np.testing.assert_array_equal(out.discrete.data.sum(axis=1), want.sum(axis=1))
+        for t in differ:
+            assert sorted(act[t][out.discrete.data[t] > 0]) == sorted(act[t][want[t] > 0]), f"frame {t}: not a tie"
+        print(f"[apply {name}] {len(differ)} of {len(want)} frames differ from the reference's run, all of them ties")
+    else:
+        rows = ref[f"{name}_diar"]
+        np.testing.assert_array_equal(np.array([[a, b] for a, b, _ in out.times]), rows[:, :2])
+        assert [lab for _, _, lab in out.times] == [f"SPEAKER_{int(k):02d}" for k in rows[:, 2]]
+    assert out.labels == list(ref[f"{name}_labels"])
+    np.testing.assert_allclose(out.speaker_embeddings, ref[f"{name}_speaker_embeddings"], rtol=0, atol=1e-6)
+
+
+def test_apply_on_a_silent_file_matches_the_reference(ref):
+    plda = P.PLDA(**syn.make_plda(2))
+    out = P.apply(None, None, plda, None, segmentations=P.SWF(np.zeros((15, 589, 3), dtype=np.float32), CHUNKS))
+    assert out.segments == [] and tuple(out.speaker_embeddings.shape) == tuple(ref["silent_speaker_embeddings_shape"])
