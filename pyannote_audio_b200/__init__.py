@@ -15,7 +15,7 @@ _LAZY = {
     "WeSpeakerResNet34": "models", "SpeakerDiarization": "pipeline", "DiarizeOutput": "pipeline",
     "PretrainedSpeakerEmbedding": "pipeline", "VBxClustering": "clustering",
     "AgglomerativeClustering": "clustering", "PLDA": "clustering", "VoiceActivityDetection": "vad",
-    "Binarize": "signal",
+    "Binarize": "signal", "Pipeline": "loading",
 }
 
 

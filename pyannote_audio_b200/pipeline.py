@@ -166,6 +166,16 @@ class SpeakerDiarization:
         self.legacy = legacy
         device = device or torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
         self.device = device
+        # paths / {"checkpoint": ..., "subfolder": ...} entries as Pipeline.from_pretrained hands them over
+        # (pipelines/utils/getter.py get_model / get_plda); instances and state dicts pass through untouched
+        from .loading import get_model, get_plda, is_checkpoint_spec
+
+        if is_checkpoint_spec(segmentation):
+            segmentation = get_model(segmentation, token=token, cache_dir=cache_dir)
+        if is_checkpoint_spec(embedding):
+            embedding = get_model(embedding, token=token, cache_dir=cache_dir)
+        if is_checkpoint_spec(plda):
+            plda = get_plda(plda, token=token, cache_dir=cache_dir)
         if isinstance(segmentation, Mapping):
             model = PyanNet()
             model.load_state_dict(segmentation)

@@ -20,6 +20,10 @@ from .signal import Binarize
 class VoiceActivityDetection:
     def __init__(self, segmentation: Union[PyanNet, Mapping, None] = None, fscore: bool = False, token=None,
                  cache_dir=None, device: Optional[torch.device] = None, **inference_kwargs):
+        from .loading import get_model, is_checkpoint_spec
+
+        if is_checkpoint_spec(segmentation):               # path / {"checkpoint": ...} from Pipeline.from_pretrained
+            segmentation = get_model(segmentation, token=token, cache_dir=cache_dir)
         if isinstance(segmentation, Mapping):
             model = PyanNet()
             model.load_state_dict(segmentation)
