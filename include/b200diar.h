@@ -42,8 +42,14 @@ int b200_version(void);
 /* Model.to(device) / Inference.to(device)  (core/inference.py:169-180) */
 int b200_ctx_create(b200_ctx** ctx, int device);
 int b200_ctx_destroy(b200_ctx* ctx);
-/* options: "conv_impl" 0 = CUDA-core reference conv, 1 = tcgen05 per-tap conv, 2 = tcgen05 for stride-1 only,
- * 3..6 = tcgen05 strip-streaming conv (halo reuse) variants; "seg_max_batch", "emb_max_batch", "profile". */
+/* Tuning / A-B options (no reference counterpart; results do not depend on the sub-batch sizes):
+ *   "seg_max_batch" (4736) / "emb_max_batch" (296): chunks per sub-batch = workspace size;
+ *   "conv_impl" 8 = per-layer choice of the tcgen05 conv kernels (default), 0 = CUDA-core reference conv, 1 = per-tap,
+ *   2 = tcgen05 for stride-1 only, 3..6 = strip-streaming variants; "conv_fuse", "conv_fold", "conv_scfold", "conv_ghost";
+ *   "seg_gemm_impl" / "seg_rec_impl" 1 = tensor cores, 0 = fp32 CUDA-core twins; "seg_conv_impl" 0 twins, 1 tensor
+ *   cores, 2 sinc layer only, 3 Conv1d layers only; "fbank_share" 1 = overlapping chunks share their fbank frames;
+ *   "profile" 1 = CUDA-event timers around the trunk / the segmentation (b200_ctx_timer).  Unknown keys and values out
+ *   of range return B200_ERR_INVALID. */
 int b200_ctx_set_option(b200_ctx* ctx, const char* key, int64_t value);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches claim) */
 int64_t b200_ctx_launch_count(const b200_ctx* ctx);
@@ -73,6 +79,8 @@ typedef struct b200_seg_weights {
   const float* classifier_weight;             /* [7][128] */
   const float* classifier_bias;               /* [7]      */
 } b200_seg_weights;
+/* Model.load_state_dict / Model.from_pretrained (core/model.py:497-655) for PyanNet: host fp32 arrays in PyTorch layouts;
+ * fp16 (hi, lo) splits, LSTM shared-memory images and the sinc bank's tensor-core layout are made here, once. */
 int b200_seg_load(b200_ctx* ctx, const b200_seg_weights* w);
 
 /* WeSpeakerResNet34 (models/embedding/wespeaker/resnet.py:84-145, 214-252).  conv weight [Cout][Cin][k][k] fp32,
@@ -92,6 +100,8 @@ typedef struct b200_emb_weights {
   const float* seg1_weight;                   /* resnet.seg_1.weight [256][5120]                          */
   const float* seg1_bias;                     /* [256]                                                    */
 } b200_emb_weights;
+/* the same for WeSpeakerResNet34 (models/embedding/wespeaker/__init__.py:324-372): eval-mode BatchNorm is folded into
+ * the conv weights / biases, conv weights go to fp16 [tap][c_out][c_in] plus the per-kernel re-layouts. */
 int b200_emb_load(b200_ctx* ctx, const b200_emb_weights* w);
 
 /* ---- audio ingest: Audio.__call__ / Audio.downmix_and_resample (core/io.py:223-265, 306-351) -----------------
@@ -161,7 +171,9 @@ int b200_stats_pool(b200_ctx* ctx, const float* seq, const float* weights, float
  * inference.py:596 does); num_frames = size of the global grid. */
 int b200_speaker_count(b200_ctx* ctx, const uint8_t* seg, const int32_t* start_frame, int32_t num_chunks,
                        int32_t num_frames, uint8_t* count, void* stream);
-/* hard_clusters[num_chunks][3] int8 DEVICE (-2 = inactive/unassigned, values >= num_clusters_out are ignored);
+/* SpeakerDiarization.reconstruct + to_diarization (pipelines/speaker_diarization.py:480-528,
+ * pipelines/utils/diarization.py:221-268): per frame, the `count` most active clusters (ties: lower cluster index).
+ * hard_clusters[num_chunks][3] int8 DEVICE (-2 = inactive/unassigned, values >= num_clusters_out are ignored);
  * count[num_frames] u8 device (already capped); out: discrete[num_frames][num_clusters_out] u8 with
  * num_clusters_out >= max(K, max(count)), at most 127 (hard clusters are int8 like the reference's
  * constrained_argmax; up to 32 clusters the per-frame counters stay in registers). */
@@ -200,7 +212,7 @@ int b200_clean_frames(b200_ctx* ctx, const uint8_t* seg, int32_t num_chunks, int
  * bytes, 8.6 GB at the limit); longer recordings must be clustered in windows by the caller. */
 int b200_linkage_centroid(b200_ctx* ctx, const double* x, int32_t n, int32_t dim, int32_t normalize, double* Z,
                           void* stream);
-/* the same for num_problems independent problems in ONE launch (one CTA each): rows of problem f are
+/* the same (clustering.py:594-603) for num_problems independent problems in ONE launch (one CTA each): rows of problem f are
  * x[row_offsets[f] .. row_offsets[f+1]) (row_offsets: HOST int32[num_problems+1]); Z rows are concatenated, problem
  * f contributing max(n_f - 1, 0) rows. */
 int b200_linkage_centroid_batched(b200_ctx* ctx, const double* x, const int32_t* row_offsets, int32_t num_problems,
@@ -224,7 +236,8 @@ int b200_cdist_cosine(b200_ctx* ctx, const double* a, int32_t m, const double* b
 int b200_vbx(b200_ctx* ctx, const double* fea, const double* phi, int32_t n, int32_t D, int32_t S, double Fa,
              double Fb, int32_t max_iters, double epsilon, double* gamma, double* pi, int32_t* iters, void* stream);
 /* batched: problem f has n[f] frames (consecutive rows of fea) and S[f] speakers; gamma / pi are the per-problem
- * arrays concatenated; n, S, iters (nullable) are HOST int32[num_problems].  One persistent CTA per problem. */
+ * arrays concatenated; n, S, iters (nullable) are HOST int32[num_problems].  One 8-CTA thread-block cluster per
+ * problem runs all iterations (utils/vbx.py:98-136), convergence is tested on the device. */
 int b200_vbx_batched(b200_ctx* ctx, const double* fea, const double* phi, const int32_t* n, const int32_t* S,
                      int32_t num_problems, int32_t D, double Fa, double Fb, int32_t max_iters, double epsilon,
                      double* gamma, double* pi, int32_t* iters, void* stream);
